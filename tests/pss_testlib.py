@@ -1,0 +1,423 @@
+"""Shared test/bench helpers (NOT product code).
+
+* ``Synth``  -- ctypes binding of tests/synth/libpsssynth.so (seeded FASTA/SAM generators)
+* ``Oracle`` -- ctypes binding of oracle/liboracle.so (CPU restatement of the reference,
+  see oracle/oracle_pss.h for who may use it)
+* ``RefBin`` -- runner for the unmodified reference binaries in oracle/_ref (only when
+  they exist; they are built from /root/reference by ``make -C oracle ref``)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import tempfile
+from dataclasses import dataclass, field
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SYNTH_SO = os.path.join(ROOT, "tests", "synth", "libpsssynth.so")
+ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def _run(cmd, **kw):
+    r = subprocess.run(cmd, capture_output=True, text=True, **kw)
+    if r.returncode != 0:
+        raise RuntimeError(f"{' '.join(cmd)} failed:\n{r.stdout}\n{r.stderr}")
+    return r
+
+
+def build_synth(force=False):
+    src = os.path.join(ROOT, "tests", "synth", "pss_synth.c")
+    if force or not os.path.exists(SYNTH_SO) or os.path.getmtime(SYNTH_SO) < os.path.getmtime(src):
+        _run(["gcc", "-O2", "-g", "-fopenmp", "-fPIC", "-shared", "-o", SYNTH_SO, src, "-lm"])
+    return SYNTH_SO
+
+
+def build_oracle(force=False):
+    src = os.path.join(ROOT, "oracle", "oracle_pss.c")
+    hdr = os.path.join(ROOT, "oracle", "oracle_pss.h")
+    newest = max(os.path.getmtime(src), os.path.getmtime(hdr))
+    if force or not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < newest:
+        _run(["make", "-C", os.path.join(ROOT, "oracle"), "-B", "liboracle.so"])
+    return ORACLE_SO
+
+
+# --------------------------------------------------------------------------- synth
+class _ReadsCfg(C.Structure):
+    _fields_ = [
+        ("seed", C.c_uint64),
+        ("min_len", C.c_uint32), ("max_len", C.c_uint32),
+        ("p_reverse", C.c_double), ("p_indel", C.c_double), ("p_softclip", C.c_double),
+        ("p_badflag", C.c_double), ("p_paired", C.c_double), ("p_qualstar", C.c_double),
+        ("p_unknown_contig", C.c_double), ("p_edge", C.c_double), ("p_read_n", C.c_double),
+        ("damage5", C.c_double), ("damage3", C.c_double), ("err", C.c_double),
+        ("max_mapq", C.c_uint32), ("with_tags", C.c_uint32),
+    ]
+
+
+def reads_cfg_config1(seed=1, read_len=50):
+    """fixed-length unpaired reads, all '<n>M', damage + 0.2% errors."""
+    return _ReadsCfg(seed=seed, min_len=read_len, max_len=read_len, p_reverse=0.5,
+                     p_indel=0, p_softclip=0, p_badflag=0, p_paired=0, p_qualstar=0,
+                     p_unknown_contig=0, p_edge=0, p_read_n=0,
+                     damage5=0.3, damage3=0.3, err=0.002, max_mapq=60, with_tags=1)
+
+
+def reads_cfg_config2(seed=2, min_len=30, max_len=150):
+    """variable length, reject-path mix, paired mix."""
+    return _ReadsCfg(seed=seed, min_len=min_len, max_len=max_len, p_reverse=0.5,
+                     p_indel=0.10, p_softclip=0.10, p_badflag=0.05, p_paired=0.05,
+                     p_qualstar=0.01, p_unknown_contig=0.005, p_edge=0.002, p_read_n=0.02,
+                     damage5=0.3, damage3=0.3, err=0.002, max_mapq=60, with_tags=1)
+
+
+@dataclass
+class SynthGenome:
+    names: list
+    seqs: list            # list of np.uint8 arrays (ASCII, may contain lower case / N)
+    seed: int = 0
+    _keep: list = field(default_factory=list)
+
+    @property
+    def lens(self):
+        return [len(s) for s in self.seqs]
+
+    def fasta_bytes(self, width=60) -> bytes:
+        lib = Synth.lib()
+        out = []
+        for name, seq in zip(self.names, self.seqs):
+            cap = len(seq) + len(seq) // width + len(name) + 8
+            buf = np.empty(cap, dtype=np.uint8)
+            n = lib.synth_fasta_record(name.encode(), seq.ctypes.data_as(C.c_char_p),
+                                       C.c_uint64(len(seq)), C.c_uint32(width),
+                                       buf.ctypes.data_as(C.c_char_p))
+            out.append(buf[:n].tobytes())
+        return b"".join(out)
+
+
+class Synth:
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            build_synth()
+            lib = C.CDLL(SYNTH_SO)
+            lib.synth_contig.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_double, C.c_double, C.c_char_p]
+            lib.synth_contig.restype = None
+            lib.synth_sam_bound.argtypes = [C.POINTER(_ReadsCfg), C.c_uint64, C.c_uint64]
+            lib.synth_sam_bound.restype = C.c_size_t
+            lib.synth_sam.argtypes = [C.POINTER(_ReadsCfg), C.POINTER(C.c_char_p), C.POINTER(C.c_uint64),
+                                      C.POINTER(C.c_char_p), C.c_uint32, C.c_uint64, C.c_uint64,
+                                      C.c_void_p, C.c_size_t]
+            lib.synth_sam.restype = C.c_size_t
+            lib.synth_fasta_record.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, C.c_uint32, C.c_char_p]
+            lib.synth_fasta_record.restype = C.c_size_t
+            cls._lib = lib
+        return cls._lib
+
+    @classmethod
+    def genome(cls, seed, contig_lens, names=None, n_frac=0.0, lower_frac=0.0) -> SynthGenome:
+        lib = cls.lib()
+        names = names or [f"chr{i + 1}" for i in range(len(contig_lens))]
+        seqs = []
+        for i, L in enumerate(contig_lens):
+            a = np.empty(L, dtype=np.uint8)
+            lib.synth_contig(seed, i, L, n_frac, lower_frac, a.ctypes.data_as(C.c_char_p))
+            seqs.append(a)
+        return SynthGenome(names=list(names), seqs=seqs, seed=seed)
+
+    @classmethod
+    def sam_into(cls, cfg: _ReadsCfg, g: SynthGenome, begin: int, end: int, out_ptr: int, out_cap: int) -> int:
+        """Generate reads [begin,end) as SAM text into a caller buffer; returns bytes."""
+        lib = cls.lib()
+        nc = len(g.seqs)
+        seqp = (C.c_char_p * nc)(*[C.cast(s.ctypes.data, C.c_char_p) for s in g.seqs])
+        lens = (C.c_uint64 * nc)(*g.lens)
+        namep = (C.c_char_p * nc)(*[n.encode() for n in g.names])
+        n = lib.synth_sam(C.byref(cfg), seqp, lens, namep, nc, begin, end, C.c_void_p(out_ptr), out_cap)
+        if n == 0 and end > begin:
+            raise RuntimeError("synth_sam: output buffer too small")
+        return n
+
+    @classmethod
+    def sam_bound(cls, cfg, begin, end) -> int:
+        return cls.lib().synth_sam_bound(C.byref(cfg), begin, end)
+
+    @classmethod
+    def sam(cls, cfg: _ReadsCfg, g: SynthGenome, begin: int, end: int) -> bytes:
+        cap = cls.sam_bound(cfg, begin, end)
+        buf = np.empty(cap, dtype=np.uint8)
+        n = cls.sam_into(cfg, g, begin, end, buf.ctypes.data, cap)
+        return buf[:n].tobytes()
+
+
+# --------------------------------------------------------------------------- oracle
+class _OraContig(C.Structure):
+    _fields_ = [("id", C.c_char_p), ("seq", C.c_void_p), ("len", C.c_size_t)]
+
+
+class _OraGenome(C.Structure):
+    _fields_ = [("ctg", C.POINTER(_OraContig)), ("n", C.c_size_t)]
+
+
+class _OraPssParams(C.Structure):
+    _fields_ = [("region_len", C.c_int), ("min_len", C.c_ulong), ("max_len", C.c_ulong),
+                ("min_mq", C.c_int), ("up_ctx", C.c_char_p), ("down_ctx", C.c_char_p),
+                ("merged_only", C.c_uint)]
+
+
+class _OraFkParams(C.Structure):
+    _fields_ = [("klen", C.c_int), ("min_len", C.c_ulong), ("max_len", C.c_ulong),
+                ("min_mq", C.c_int), ("merged_only", C.c_int)]
+
+
+class _OraStats(C.Structure):
+    _fields_ = [(k, C.c_uint64) for k in ("lines", "counted", "no_contig", "filtered", "parse_fail", "undefined")]
+
+    def asdict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+@dataclass
+class PssParams:
+    region_len: int = 15
+    min_len: int = 0
+    max_len: int = 250000000
+    min_mq: int = 0
+    up_ctx: bytes = b"ACGT"
+    down_ctx: bytes = b"ACGT"
+    merged_only: int = 0
+
+    def cli_args(self):
+        a = ["-r", str(self.region_len), "-l", str(self.min_len), "-L", str(self.max_len),
+             "-q", str(self.min_mq), "-U", self.up_ctx.decode(), "-D", self.down_ctx.decode()]
+        if self.merged_only:
+            a.append("-m")
+        return a
+
+
+@dataclass
+class FkParams:
+    klen: int = 8
+    min_len: int = 0
+    max_len: int = 250000000
+    min_mq: int = 0
+    merged_only: int = 0
+
+    def cli_args(self):
+        a = ["-k", str(self.klen), "-l", str(self.min_len), "-L", str(self.max_len), "-q", str(self.min_mq)]
+        if self.merged_only:
+            a.append("-m")
+        return a
+
+
+class Oracle:
+    """CPU oracle (checker only)."""
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            build_oracle()
+            lib = C.CDLL(ORACLE_SO)
+            lib.ora_genome_parse.argtypes = [C.c_char_p, C.c_size_t]
+            lib.ora_genome_parse.restype = C.POINTER(_OraGenome)
+            lib.ora_genome_load.argtypes = [C.c_char_p]
+            lib.ora_genome_load.restype = C.POINTER(_OraGenome)
+            lib.ora_genome_free.argtypes = [C.POINTER(_OraGenome)]
+            lib.ora_pss_tally.argtypes = [C.POINTER(_OraGenome), C.c_void_p, C.c_size_t, C.POINTER(_OraPssParams),
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(_OraStats)]
+            lib.ora_pss_tally.restype = C.c_uint64
+            lib.ora_pss_rates.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+            lib.ora_pss_write_counts.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int]
+            lib.ora_pss_write_rates.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int]
+            lib.ora_fragkon_tally.argtypes = [C.POINTER(_OraGenome), C.c_void_p, C.c_size_t, C.POINTER(_OraFkParams),
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(_OraStats)]
+            lib.ora_fragkon_tally.restype = C.c_uint64
+            lib.ora_kmer_spectrum.argtypes = [C.POINTER(_OraGenome), C.c_int, C.c_void_p]
+            lib.ora_kmer_spectrum.restype = None
+            cls._lib = lib
+        return cls._lib
+
+    def __init__(self, fasta: bytes | None = None, fasta_path: str | None = None):
+        lib = self.lib()
+        if fasta is not None:
+            self.g = lib.ora_genome_parse(fasta, len(fasta))
+        else:
+            self.g = lib.ora_genome_load(fasta_path.encode())
+            if not self.g:
+                raise FileNotFoundError(fasta_path)
+
+    def close(self):
+        if self.g:
+            self.lib().ora_genome_free(self.g)
+            self.g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def n_contigs(self):
+        return int(self.g.contents.n)
+
+    def contigs(self):
+        out = []
+        for i in range(self.n_contigs):
+            c = self.g.contents.ctg[i]
+            out.append((c.id.decode("latin1"), C.string_at(c.seq, c.len)))
+        return out
+
+    def pss(self, sam, p: PssParams = PssParams(), want_status=False):
+        """Returns (fwd[(R+2),16] u64, rev, stats dict[, status int8 per line])."""
+        lib = self.lib()
+        R = p.region_len
+        fwd = np.zeros(((R + 2), 16), dtype=np.uint64)
+        rev = np.zeros(((R + 2), 16), dtype=np.uint64)
+        st = _OraStats()
+        cp = _OraPssParams(R, p.min_len, p.max_len, p.min_mq, p.up_ctx, p.down_ctx, p.merged_only)
+        sam_ptr, sam_len, keep = _as_ptr(sam)
+        status = None
+        cap = 0
+        if want_status:
+            cap = _count_lines(sam) + 8
+            status = np.full(cap, 99, dtype=np.int8)
+        n = lib.ora_pss_tally(self.g, sam_ptr, sam_len, C.byref(cp), fwd.ctypes.data, rev.ctypes.data,
+                              status.ctypes.data if want_status else None, cap, C.byref(st))
+        del keep
+        if want_status:
+            return fwd, rev, st.asdict(), status[:n]
+        return fwd, rev, st.asdict()
+
+    def rates(self, counts: np.ndarray, R: int):
+        out = np.zeros((R, 12), dtype=np.float64)
+        c = np.ascontiguousarray(counts, dtype=np.uint64)
+        self.lib().ora_pss_rates(c.ctypes.data, R, out.ctypes.data)
+        return out
+
+    def write_pss(self, fasta_fn, bam_fn, prefix, fwd, rev, R):
+        lib = self.lib()
+        fwd = np.ascontiguousarray(fwd, dtype=np.uint64)
+        rev = np.ascontiguousarray(rev, dtype=np.uint64)
+        fr, rr = self.rates(fwd, R), self.rates(rev, R)
+        assert lib.ora_pss_write_counts(fasta_fn.encode(), bam_fn.encode(), prefix.encode(),
+                                        fwd.ctypes.data, rev.ctypes.data, R) == 0
+        assert lib.ora_pss_write_rates(fasta_fn.encode(), bam_fn.encode(), prefix.encode(),
+                                       fr.ctypes.data, rr.ctypes.data, R) == 0
+
+    def fragkon(self, sam, p: FkParams = FkParams(), want_status=False):
+        lib = self.lib()
+        nb = 1 << (2 * p.klen)
+        fp = np.zeros(nb, dtype=np.uint64)
+        tp = np.zeros(nb, dtype=np.uint64)
+        st = _OraStats()
+        cp = _OraFkParams(p.klen, p.min_len, p.max_len, p.min_mq, p.merged_only)
+        sam_ptr, sam_len, keep = _as_ptr(sam)
+        status = None
+        cap = 0
+        if want_status:
+            cap = _count_lines(sam) + 8
+            status = np.full(cap, 99, dtype=np.int8)
+        n = lib.ora_fragkon_tally(self.g, sam_ptr, sam_len, C.byref(cp), fp.ctypes.data, tp.ctypes.data,
+                                  status.ctypes.data if want_status else None, cap, C.byref(st))
+        del keep
+        if want_status:
+            return fp, tp, st.asdict(), status[:n]
+        return fp, tp, st.asdict()
+
+    def kmer_spectrum(self, k: int):
+        counts = np.zeros(1 << (2 * k), dtype=np.uint64)
+        self.lib().ora_kmer_spectrum(self.g, k, counts.ctypes.data)
+        return counts
+
+
+def _as_ptr(buf):
+    """bytes / bytearray / np.uint8 array -> (void*, len, keepalive)."""
+    if isinstance(buf, np.ndarray):
+        a = np.ascontiguousarray(buf, dtype=np.uint8)
+        return C.c_void_p(a.ctypes.data), a.size, a
+    a = np.frombuffer(buf, dtype=np.uint8)
+    return C.c_void_p(a.ctypes.data), a.size, a
+
+
+def _count_lines(buf) -> int:
+    a = buf if isinstance(buf, np.ndarray) else np.frombuffer(buf, dtype=np.uint8)
+    n = int(np.count_nonzero(a == 10))
+    # fgets also splits lines longer than 200000 bytes
+    return n + 1 + a.size // 200000
+
+
+# --------------------------------------------------------------------------- reference binaries
+class RefBin:
+    """The unmodified reference programs (oracle/_ref), run with the samtools shim on PATH."""
+
+    @staticmethod
+    def available() -> bool:
+        return all(os.path.exists(os.path.join(REF_DIR, b))
+                   for b in ("pss-bam", "fragkon", "genome-kmer-count", "samtools"))
+
+    @staticmethod
+    def env():
+        e = dict(os.environ)
+        e["PATH"] = REF_DIR + os.pathsep + e.get("PATH", "")
+        return e
+
+    @classmethod
+    def pss_bam(cls, fasta_path, sam_path, prefix, extra=(), binary="pss-bam", cwd=None):
+        cmd = [os.path.join(REF_DIR, binary), "-F", fasta_path, "-B", sam_path, "-o", prefix, *extra]
+        r = subprocess.run(cmd, capture_output=True, env=cls.env(), cwd=cwd)
+        if r.returncode != 0:
+            raise RuntimeError(f"reference pss-bam failed ({r.returncode}): {r.stderr[-2000:]}")
+        with open((os.path.join(cwd, prefix) if cwd else prefix) + ".pss.counts.txt", "rb") as f:
+            counts = f.read()
+        with open((os.path.join(cwd, prefix) if cwd else prefix) + ".pss.rates.txt", "rb") as f:
+            rates = f.read()
+        return counts, rates
+
+    @classmethod
+    def fragkon(cls, fasta_path, sam_path, extra=(), binary="fragkon", cwd=None) -> bytes:
+        # stdbuf -oL: for k>8 the reference crashes in destroy_KSP (kmer.c:220-231) after
+        # printing; line buffering keeps the complete table.
+        cmd = ["stdbuf", "-oL", os.path.join(REF_DIR, binary), "-F", fasta_path, "-B", sam_path, *extra]
+        r = subprocess.run(cmd, capture_output=True, env=cls.env(), cwd=cwd)
+        return r.stdout
+
+    @classmethod
+    def genome_kmer_count(cls, fasta_path, k, binary="genome-kmer-count", cwd=None) -> bytes:
+        cmd = [os.path.join(REF_DIR, binary), "-f", fasta_path, "-k", str(k)]
+        r = subprocess.run(cmd, capture_output=True, env=cls.env(), cwd=cwd)
+        if r.returncode != 0:
+            raise RuntimeError(f"reference genome-kmer-count failed: {r.stderr[-2000:]}")
+        return r.stdout
+
+
+def parse_counts_file(text: bytes, R: int):
+    """Parse <prefix>.pss.counts.txt back into (fwd, rev) arrays laid out like the tally tables."""
+    rows = [ln for ln in text.decode().split("\n") if ln and not ln.startswith("#")]
+    assert len(rows) == 2 * (R + 2), len(rows)
+    fwd = np.zeros((R + 2, 16), dtype=np.uint64)
+    rev = np.zeros((R + 2, 16), dtype=np.uint64)
+    for i in range(R + 2):
+        f = rows[i].split("\t")
+        assert int(f[0]) == i - 2
+        fwd[i] = [int(x) for x in f[1:17]]
+    for j in range(R):                      # rows R-1 .. 0
+        f = rows[R + 2 + j].split("\t")
+        pos = int(f[0])
+        assert pos == R - 1 - j
+        rev[pos + 2] = [int(x) for x in f[1:17]]
+    f1 = rows[2 * R + 2].split("\t")        # labelled "1" -> rev row 1
+    f2 = rows[2 * R + 3].split("\t")        # labelled "2" -> rev row 0
+    rev[1] = [int(x) for x in f1[1:17]]
+    rev[0] = [int(x) for x in f2[1:17]]
+    return fwd, rev
+
+
+def tmpdir():
+    return tempfile.mkdtemp(prefix="psstest_")
