@@ -1,0 +1,208 @@
+/* pssgpu.h -- C ABI of the B200 (sm_100a) hot path of pss-bam / fragkon /
+ * genome-kmer-count.
+ *
+ * The reference has no plugin or FFI layer: its three programs call static
+ * functions in a per-read / per-base loop.  This header is the boundary a
+ * maintainer binds instead of those loops (see INTEGRATION.md for the patch
+ * to the reference's own mains):
+ *
+ *   reference loop replaced                       entry points here
+ *   -------------------------------------------   ---------------------------
+ *   init_genome() result made device resident     pssgpu_genome_upload
+ *     (fasta-genome-io.c:221-238, Seq/Genome
+ *      fasta-genome-io.h:13-24)
+ *   pss-bam.c:764-783  fgets + line2saml +        pssgpu_pss_begin / pssgpu_feed /
+ *     process_aln (sam-parse.c:10-91,               pssgpu_pss_finish
+ *     pss-bam.c:390-496, :169-326)
+ *   fragkon.c:342-363  fgets + line2saml +        pssgpu_fragkon_begin / pssgpu_feed /
+ *     process_aln (fragkon.c:122-216,               pssgpu_fragkon_finish
+ *     kmer.c:43-110)
+ *   genome-kmer-count.c:56-58 count_kmers         pssgpu_kmer_spectrum
+ *     (:68-79, kmer.c:43-110)
+ *
+ * Conventions: plain C, plain pointers and sizes, no CUDA or torch types.
+ * Every call returns 0 on success or a negative PSSGPU_E* code;
+ * pssgpu_last_error() gives the text.  A context is bound to one CUDA device
+ * and must be used from one host thread at a time (the reference is
+ * single-threaded and keeps its configuration in file-scope statics; here the
+ * configuration lives in the context).  There is NO CPU fallback: if the
+ * device or the kernels are unavailable the call fails.
+ */
+#ifndef PSSGPU_H
+#define PSSGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSSGPU_ABI_VERSION 1
+
+enum {
+    PSSGPU_OK        = 0,
+    PSSGPU_EINVAL    = -1,   /* bad argument / call out of order            */
+    PSSGPU_ECUDA     = -2,   /* CUDA runtime error (text in last_error)     */
+    PSSGPU_ENOMEM    = -3,   /* host or device allocation failed            */
+    PSSGPU_ENOGENOME = -4,   /* tally requested before pssgpu_genome_upload */
+    PSSGPU_EUNSUPP   = -5    /* parameter outside the supported range       */
+};
+
+typedef struct pssgpu_ctx pssgpu_ctx;
+
+/* ---- lifetime ------------------------------------------------------------ */
+int         pssgpu_abi_version(void);
+/* Number of visible CUDA devices (<0 on error). */
+int         pssgpu_device_count(void);
+/* Create a context on CUDA device `device` (one process per GPU: pass
+ * LOCAL_RANK).  Fails unless the device is sm_100 class. */
+int         pssgpu_init(int device, pssgpu_ctx **out);
+void        pssgpu_destroy(pssgpu_ctx *ctx);
+const char *pssgpu_last_error(const pssgpu_ctx *ctx);   /* ctx may be NULL: last init error */
+/* The cudaStream_t (as void*) every kernel and copy of this context is issued
+ * on, so a caller can bracket calls with its own CUDA events. */
+void       *pssgpu_cuda_stream(pssgpu_ctx *ctx);
+
+/* Pinned host memory for SAM staging (pssgpu_feed copies straight from it). */
+void       *pssgpu_host_alloc(size_t bytes);
+void        pssgpu_host_free(void *p);
+
+/* ---- genome residency ------------------------------------------------------
+ * One entry per FASTA record, exactly the three fields of the reference's
+ * `Seq` (fasta-genome-io.h:13-17): id (NUL terminated), seq (upper-cased
+ * ASCII as produced by read_fasta, fasta-genome-io.c:120-131; need not be NUL
+ * terminated) and len.  Pointers are borrowed for the duration of the call.
+ * The contigs may be given in any order; lookup by name reproduces
+ * find_seq()/chr_cmp() (fasta-genome-io.c:202-219): exact byte equality.
+ * The genome is packed on the device to 4 bits per base (2-bit base code +
+ * 2-bit class) and stays resident until the next upload or
+ * pssgpu_destroy. */
+typedef struct pssgpu_contig {
+    const char *id;
+    const char *seq;
+    uint64_t    len;
+} pssgpu_contig;
+
+int pssgpu_genome_upload(pssgpu_ctx *ctx, const pssgpu_contig *contigs, uint64_t n_contigs);
+/* Same, but each seq pointer is DEVICE memory holding the ASCII contig. */
+int pssgpu_genome_upload_device(pssgpu_ctx *ctx, const pssgpu_contig *contigs, uint64_t n_contigs);
+/* Total bases resident / bytes of HBM used by the packed genome. */
+int pssgpu_genome_info(const pssgpu_ctx *ctx, uint64_t *n_contigs, uint64_t *n_bases, uint64_t *hbm_bytes);
+
+/* ---- pss-bam tally -----------------------------------------------------------
+ * Mirrors the file-scope options of pss-bam.c:12-18 (same defaults via
+ * pssgpu_pss_default_params). */
+typedef struct pssgpu_pss_params {
+    int           region_len;   /* -r  REGION_LEN   (default 15)          */
+    unsigned long min_len;      /* -l  MIN_READ_LEN (default 0)           */
+    unsigned long max_len;      /* -L  MAX_READ_LEN (default 250000000)   */
+    int           min_mq;       /* -q  MIN_MQ       (default 0)           */
+    const char   *up_ctx;       /* -U  UP_CTX       (default "ACGT")      */
+    const char   *down_ctx;     /* -D  DOWN_CTX     (default "ACGT")      */
+    unsigned int  merged_only;  /* -m  MERGED_ONLY  (default 0)           */
+} pssgpu_pss_params;
+
+void pssgpu_pss_default_params(pssgpu_pss_params *p);
+
+/* Per-record outcome counters, in the vocabulary of process_aln's return
+ * codes (pss-bam.c:387-389, fragkon.c:119-121). */
+typedef struct pssgpu_stats {
+    uint64_t lines;        /* fgets() lines seen                                   */
+    uint64_t counted;      /* process_aln returned 0                               */
+    uint64_t no_contig;    /* returned 1: RNAME not in the genome                  */
+    uint64_t filtered;     /* returned -1 (pss-bam) / 2 or -1 (fragkon)            */
+    uint64_t parse_fail;   /* line2saml returned 1 (sam-parse.c:88-90)             */
+    uint64_t undefined;    /* dropped because the reference's result depends on
+                              stale buffer contents (see DESIGN.md "domain")       */
+} pssgpu_stats;
+
+/* Start a tally: zeroes the device tables.  Needs a resident genome. */
+int pssgpu_pss_begin(pssgpu_ctx *ctx, const pssgpu_pss_params *p);
+
+/* Feed SAM text (what `samtools view` writes: pss-bam.c:148-162), any
+ * chunking; partial trailing lines are carried to the next call; `last` != 0
+ * flushes a final line without '\n'.  Host memory; pinned memory from
+ * pssgpu_host_alloc is copied without an extra staging pass.  Asynchronous:
+ * returns once the bytes are staged, kernels may still be running. */
+int pssgpu_feed(pssgpu_ctx *ctx, const char *sam_bytes, size_t len, int last);
+
+/* Same for SAM text already resident in device memory.  `d_sam` must be
+ * 16-byte aligned and hold WHOLE lines (last byte '\n'); it must stay valid
+ * until the next pssgpu_*_finish / pssgpu_sync.  No copy is made. */
+int pssgpu_feed_device(pssgpu_ctx *ctx, const void *d_sam, size_t len);
+
+/* Wait for all fed bytes to be tallied. */
+int pssgpu_sync(pssgpu_ctx *ctx);
+
+/* Finish: waits, then copies the tables out.  fwd/rev: (region_len+2)*16
+ * counters each, row-major, same layout as the reference's count matrices
+ * (pss-bam.c:24-35): row 0/1 = context bases 2/1 away, row i+2 = position i,
+ * column 4*code(read)+code(ref), A=0 C=1 G=2 T=3.  May be called repeatedly;
+ * the tally stays open for more pssgpu_feed calls until the next *_begin. */
+int pssgpu_pss_finish(pssgpu_ctx *ctx, uint64_t *fwd, uint64_t *rev);
+/* Same into DEVICE memory: d_tables receives 2*(region_len+2)*16 u64 (fwd
+ * then rev), e.g. the buffer handed to ncclAllReduce(ncclSum, ncclUint64). */
+int pssgpu_pss_finish_device(pssgpu_ctx *ctx, void *d_tables);
+
+int pssgpu_get_stats(pssgpu_ctx *ctx, pssgpu_stats *out);
+
+/* ---- fragkon ----------------------------------------------------------------
+ * Options of fragkon.c:14-18. */
+typedef struct pssgpu_fragkon_params {
+    int           klen;         /* -k KLEN (default 8); 1 <= klen <= 14 */
+    unsigned long min_len;      /* -l */
+    unsigned long max_len;      /* -L */
+    int           min_mq;       /* -q */
+    int           merged_only;  /* -m */
+} pssgpu_fragkon_params;
+
+void pssgpu_fragkon_default_params(pssgpu_fragkon_params *p);
+int  pssgpu_fragkon_begin(pssgpu_ctx *ctx, const pssgpu_fragkon_params *p);
+/* (feed with pssgpu_feed / pssgpu_feed_device) */
+/* fp/tp: 4^klen counters each, index = 2-bit MSB-first k-mer code
+ * (kmer.c:184-214), UNSATURATED u64; the reference's `unsigned int` clamp
+ * (kmer.c:102-104) is applied by the table writer. */
+int  pssgpu_fragkon_finish(pssgpu_ctx *ctx, uint64_t *fp, uint64_t *tp);
+int  pssgpu_fragkon_finish_device(pssgpu_ctx *ctx, void *d_tables /* 2*4^k u64: 5' then 3' */);
+
+/* ---- genome-kmer-count ---------------------------------------------------------
+ * Whole-genome forward-strand k-mer spectrum over every contig
+ * (genome-kmer-count.c:56-58,68-79).  counts: 4^k u64, unsaturated.
+ * shard/n_shards split the packed genome into contiguous ranges (k-mers are
+ * attributed to the shard holding their first base; contig boundaries are
+ * respected by construction); summing the shards' outputs gives the full
+ * spectrum.  1 <= k <= 14. */
+int pssgpu_kmer_spectrum(pssgpu_ctx *ctx, int k, uint64_t *counts);
+int pssgpu_kmer_spectrum_shard(pssgpu_ctx *ctx, int k, int shard, int n_shards, uint64_t *counts);
+int pssgpu_kmer_spectrum_shard_device(pssgpu_ctx *ctx, int k, int shard, int n_shards, void *d_counts);
+
+/* ---- measurement hooks ------------------------------------------------------------
+ * CUDA-event timing of the kernels this library launches, on the stream it
+ * launches them on (a caller's torch.cuda.Event only sees torch's stream).
+ * pssgpu_timing_reset zeroes the accumulators; every tally / spectrum / pack
+ * launch afterwards is bracketed by events. */
+typedef struct pssgpu_timing {
+    uint64_t launches;        /* kernel launches since reset               */
+    double   kernel_ms;       /* sum of their event-measured durations     */
+    uint64_t bytes_scanned;   /* SAM bytes (or packed-genome bytes) they read */
+    uint64_t h2d_bytes;       /* bytes copied host->device by pssgpu_feed  */
+    uint64_t d2h_bytes;       /* bytes copied device->host by *_finish     */
+} pssgpu_timing;
+
+int pssgpu_timing_reset(pssgpu_ctx *ctx, int enable);
+int pssgpu_timing_get(pssgpu_ctx *ctx, pssgpu_timing *out);
+
+/* ---- test hook ------------------------------------------------------------------------
+ * Per-record outcomes for parity debugging: after pssgpu_debug_status(ctx,1)
+ * every processed line appends (byte offset of the line within everything fed
+ * since *_begin, outcome code) to a device log; pssgpu_debug_fetch copies up
+ * to `cap` entries out (unordered) and returns the count in *n.
+ * Outcome codes: 0 counted, 1 no contig, -1 filtered, -2 parse fail, -3 undefined. */
+int pssgpu_debug_status(pssgpu_ctx *ctx, int enable);
+int pssgpu_debug_fetch(pssgpu_ctx *ctx, uint64_t *offsets, int8_t *codes, uint64_t cap, uint64_t *n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSSGPU_H */

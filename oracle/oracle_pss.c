@@ -198,7 +198,22 @@ typedef struct ora_rec {
  * (:66-68).  Returns 0 ok / 1 bad. */
 static int parse_line(const char *line, ora_rec *r)
 {
-    int got = sscanf(line,
+    int got;
+    {   /* The reference scans with unbounded "%s" into 2048-byte fields
+         * (sam-parse.h:10,21-48): a token longer than 2047 bytes overflows
+         * them.  Not reproducible -> the line is reported as undefined.  Only
+         * the first eleven white-space delimited runs can reach a field. */
+        const unsigned char *p = (const unsigned char *)line;
+        int runs = 0;
+        while (*p && runs < 11) {
+            size_t n = 0;
+            while (*p && isspace(*p)) p++;
+            while (*p && !isspace(*p)) { p++; n++; }
+            if (n > ORA_FIELD_W) return 2;
+            if (n) runs++;
+        }
+    }
+    got = sscanf(line,
                      "%2047s %u %2047s %lu %u %2047s %2047s %u %i %2047s %2047s",
                      r->qname, &r->flag, r->rname, &r->pos, &r->mapq, r->cigar,
                      r->mrnm, &r->mpos, &r->isize, r->seq, r->qual);
@@ -206,6 +221,35 @@ static int parse_line(const char *line, ora_rec *r)
     if (strlen(r->seq) != strlen(r->qual)) return 1;
     r->seq_len = (int)strlen(r->seq);
     if (!(r->flag & FL_PAIRED)) r->isize = r->seq_len;
+    return 0;
+}
+
+/* Test hook: the conversions of one line, for fuzzing other sscanf
+ * restatements against glibc's.  Returns 0 ok / 1 line2saml fails / 2 undefined.
+ * isize is reported BEFORE the unpaired override of sam-parse.c:66-68. */
+int ora_parse_line(const char *line, unsigned int *flag, unsigned long *pos, unsigned int *mapq,
+                   int *isize, char *rname, char *cigar, char *seq)
+{
+    ora_rec *r = (ora_rec *)calloc(1, sizeof *r);
+    int      rc;
+    {
+        const unsigned char *p = (const unsigned char *)line;
+        int runs = 0;
+        while (*p && runs < 11) {
+            size_t n = 0;
+            while (*p && isspace(*p)) p++;
+            while (*p && !isspace(*p)) { p++; n++; }
+            if (n > ORA_FIELD_W) { free(r); return 2; }
+            if (n) runs++;
+        }
+    }
+    rc = sscanf(line, "%2047s %u %2047s %lu %u %2047s %2047s %u %i %2047s %2047s",
+                r->qname, &r->flag, r->rname, &r->pos, &r->mapq, r->cigar,
+                r->mrnm, &r->mpos, &r->isize, r->seq, r->qual);
+    if (rc < 11 || strlen(r->seq) != strlen(r->qual)) { free(r); return 1; }
+    *flag = r->flag; *pos = r->pos; *mapq = r->mapq; *isize = r->isize;
+    strcpy(rname, r->rname); strcpy(cigar, r->cigar); strcpy(seq, r->seq);
+    free(r);
     return 0;
 }
 
@@ -297,6 +341,14 @@ static int pss_process(const ora_genome *g, const ora_pss_params *P, ora_rec *r,
 
     if (ci < 0) return ORA_NO_CONTIG;
     ref = &g->ctg[ci];
+    /* `ref->len-1` wraps for an empty contig (:408) and the window copy then
+     * reads past the string: undefined. */
+    if (ref->len == 0) return ORA_UNDEFINED;
+    /* :402 puts three char[n+5] arrays on the stack before any filter runs;
+     * a paired record with a huge TLEN overflows the stack (SIGSEGV observed
+     * at TLEN=5e7).  Beyond 1e6 the record is reported as
+     * undefined; abs(INT_MIN) is negative and lands here too. */
+    if (r->isize == INT_MIN || abs(r->isize) > 1000000) return ORA_UNDEFINED;
 
     n = abs(r->isize);                       /* :401 */
     s = (long)(r->pos - 1);                  /* :403 */
@@ -420,8 +472,9 @@ uint64_t ora_pss_tally(const ora_genome *g, const char *sam, size_t sam_len,
     if (st) memset(st, 0, sizeof *st);
     while (next_line(&it)) {
         int code;
-        if (parse_line(it.buf, r)) {
-            code = ORA_PARSE_FAIL;
+        int pr = parse_line(it.buf, r);
+        if (pr) {
+            code = pr == 2 ? ORA_UNDEFINED : ORA_PARSE_FAIL;
         } else {
             size_t need = (size_t)abs(r->isize) + 8;
             if (need > cap) need = cap;
@@ -632,6 +685,7 @@ static int fk_process(const ora_genome *g, const ora_fk_params *P, const ora_rec
 
     if (ci < 0) return ORA_NO_CONTIG;
     ref = &g->ctg[ci];
+    if (ref->len == 0) return ORA_UNDEFINED;   /* `ref->len-1` wraps (:138) */
     s = r->pos - 1;                                                        /* :129 */
     e = s + (unsigned long)n - 1;                                          /* :130 */
 
@@ -685,7 +739,8 @@ uint64_t ora_fragkon_tally(const ora_genome *g, const char *sam, size_t sam_len,
 
     if (st) memset(st, 0, sizeof *st);
     while (next_line(&it)) {
-        int code = parse_line(it.buf, r) ? ORA_PARSE_FAIL : fk_process(g, P, r, fp, tp);
+        int pr = parse_line(it.buf, r);
+        int code = pr == 2 ? ORA_UNDEFINED : pr ? ORA_PARSE_FAIL : fk_process(g, P, r, fp, tp);
         if (status && nlines < status_cap) status[nlines] = (int8_t)code;
         tally_status(st, code);
         nlines++;

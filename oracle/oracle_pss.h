@@ -94,6 +94,12 @@ int ora_pss_write_counts(const char *fasta_fn, const char *bam_fn, const char *o
 int ora_pss_write_rates(const char *fasta_fn, const char *bam_fn, const char *out_prefix,
                         const double *fwd_rates, const double *rev_rates, int region_len);
 
+/* Test hook: glibc's conversions of one NUL-terminated line (sam-parse.c:36-50).
+ * 0 ok / 1 line2saml fails / 2 undefined (a token would overflow a field).
+ * rname/cigar/seq: caller buffers of 2048 bytes. */
+int ora_parse_line(const char *line, unsigned int *flag, unsigned long *pos, unsigned int *mapq,
+                   int *isize, char *rname, char *cigar, char *seq);
+
 /* ---- fragkon (fragkon.c) ------------------------------------------------ */
 typedef struct ora_fk_params {
     int           klen;         /* -k KLEN         fragkon.c:14 */

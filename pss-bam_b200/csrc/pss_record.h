@@ -1,0 +1,661 @@
+// pss_record.h -- per-record logic of the pss-bam / fragkon hot path, written
+// once for both the sm_100a kernels (pss_kernels.cuh) and a host build that
+// the CPU test-suite fuzzes against the oracle (tests/host_emul).  The host
+// build is a TEST of this logic; the product library (libpssgpu.so) only ever
+// executes it inside CUDA kernels.
+//
+// What lives here:
+//   * the packed-genome layout (DevGenome) and its 16-symbol alphabet
+//   * scan11(): an exact emulation of the reference's 11-conversion sscanf
+//     (sam-parse.c:36-48) for lines that are not clean tab-separated SAM
+//   * split_fast(): the common case -- clean records located through the
+//     separator bit masks the tile scan produced
+//   * pss_record(): filters + window gather of pss-bam.c:390-496 expressed on
+//     2-bit streams (no string copies, no reverse-complement pass)
+//   * fk_record(): fragkon.c:122-216
+#pragma once
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define PSS_HD __host__ __device__ __forceinline__
+#define PSS_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define PSS_HD inline
+#define PSS_HD_NOINLINE inline
+#endif
+
+namespace pssgpu {
+
+// ---------------------------------------------------------------------------
+// Packed genome.
+//
+// 16 bases per 64-bit "group": low 32 bits = 16 x 2-bit base code (base j of
+// the group at bits 2j..2j+1), high 32 bits = 16 x 2-bit class.  The pair
+// (class, code) names one of 16 symbols:
+//   class 0: A C G T      (code = the reference's A=0 C=1 G=2 T=3, kmer.c:196-211)
+//   class 1: N R Y S
+//   class 2: W K M B
+//   class 3: D H V other  ("other" = any byte not listed; its exact value is
+//                           kept in a sorted exception list, needed only for
+//                           the -U/-D membership test, pss-bam.c:134-142)
+// Keeping code and class of a base in the same 8-byte word means one window
+// gather (R+2 <= 32 bases) touches 16-24 contiguous bytes = one 32-byte
+// sector in most cases, instead of one sector in a 2-bit plane plus one in a
+// mask plane.
+//
+// Every contig starts on a group boundary and is surrounded by >= kPadBases of
+// "other" symbols, so windows that hang over a contig end (fragkon.c:156-177
+// can ask for them) read invalid symbols instead of a neighbouring contig.
+// ---------------------------------------------------------------------------
+constexpr int      kBasesPerGroup = 16;
+constexpr int      kPadGroups     = 4;                       // 64 bases each side
+constexpr int      kPadBases      = kPadGroups * kBasesPerGroup;
+constexpr uint32_t kSymOther      = 15;
+
+struct DevContig {
+    uint64_t base_off;    // global base index of position 0 (multiple of 16)
+    uint64_t len;
+    uint32_t name_off;    // into DevGenome::names
+    uint32_t name_len;
+};
+
+struct DevGenome {
+    const uint64_t  *groups;
+    uint64_t         n_groups;
+    const DevContig *contigs;
+    uint32_t         n_contigs;
+    const char      *names;
+    const uint32_t  *hash;        // open addressing; value = contig index + 1, 0 = empty
+    uint32_t         hash_mask;
+    const uint64_t  *exc_pos;     // sorted global base indices of "other" symbols
+    const uint8_t   *exc_chr;
+    uint32_t         n_exc;
+};
+
+constexpr uint32_t kNameHashSeed = 2166136261u;
+PSS_HD uint32_t name_hash_step(uint32_t h, uint8_t c) { return (h ^ c) * 16777619u; }
+
+#define PSSGPU_SYM_CHARS "ACGTNRYSWKMBDHV"
+
+// Symbol (0..15) of an upper-cased byte.
+PSS_HD uint32_t sym_of_upper(uint8_t c)
+{
+    switch (c) {
+    case 'A': return 0;  case 'C': return 1;  case 'G': return 2;  case 'T': return 3;
+    case 'N': return 4;  case 'R': return 5;  case 'Y': return 6;  case 'S': return 7;
+    case 'W': return 8;  case 'K': return 9;  case 'M': return 10; case 'B': return 11;
+    case 'D': return 12; case 'H': return 13; case 'V': return 14;
+    default:  return kSymOther;
+    }
+}
+
+// toupper() in the C locale (fasta-genome-io.c:127, pss-bam.c:84-89)
+PSS_HD uint8_t upper_c(uint8_t c) { return (c >= 'a' && c <= 'z') ? (uint8_t)(c - 32) : c; }
+
+// One packed group from 16 upper-cased-or-not ASCII bytes; `n_valid` bases are
+// real, the rest of the group is padding ("other").
+template <class ByteAt>
+PSS_HD uint64_t pack_group(const ByteAt &at, int n_valid, uint32_t *other_mask, uint32_t *nul_seen)
+{
+    uint32_t codes = 0, classes = 0, om = 0;
+    for (int j = 0; j < 16; j++) {
+        uint32_t s = kSymOther;
+        if (j < n_valid) {
+            uint8_t c = at(j);
+            if (c == 0) *nul_seen = 1;
+            s = sym_of_upper(upper_c(c));
+            if (s == kSymOther) om |= 1u << j;
+        }
+        codes   |= (s & 3u) << (2 * j);
+        classes |= (s >> 2) << (2 * j);
+    }
+    *other_mask = om;
+    return (uint64_t)codes | ((uint64_t)classes << 32);
+}
+
+// ---------------------------------------------------------------------------
+// small bit helpers with host twins
+// ---------------------------------------------------------------------------
+PSS_HD int ffs32(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x);
+#else
+    return __builtin_ffs((int)x);
+#endif
+}
+PSS_HD uint32_t brev32(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __brev(x);
+#else
+    x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+    x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+    x = ((x >> 4) & 0x0f0f0f0fu) | ((x & 0x0f0f0f0fu) << 4);
+    x = ((x >> 8) & 0x00ff00ffu) | ((x & 0x00ff00ffu) << 8);
+    return (x >> 16) | (x << 16);
+#endif
+}
+// low 32 bits of (hi:lo) >> sh, 0 <= sh <= 31
+PSS_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh)
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+#endif
+}
+// reverse the order of the sixteen 2-bit fields of x
+PSS_HD uint32_t rev_fields32(uint32_t x)
+{
+    uint32_t y = brev32(x);
+    return ((y & 0x55555555u) << 1) | ((y >> 1) & 0x55555555u);
+}
+PSS_HD uint64_t low_fields_mask(int n_fields)   // n_fields in [0,32]
+{
+    return n_fields >= 32 ? ~0ull : ((1ull << (2 * n_fields)) - 1ull);
+}
+// reverse the order of the first n (1..32) 2-bit fields of x; higher fields must be 0
+PSS_HD uint64_t rev_fields64(uint64_t x, int n)
+{
+    uint64_t r = ((uint64_t)rev_fields32((uint32_t)x) << 32) | rev_fields32((uint32_t)(x >> 32));
+    return r >> (64 - 2 * n);
+}
+
+// ---------------------------------------------------------------------------
+// outcomes and options
+// ---------------------------------------------------------------------------
+enum : int { kModePss = 0, kModeFragkon = 1 };
+
+enum : int {          // per-record outcomes (pssgpu.h pssgpu_debug_fetch)
+    kCounted = 0, kNoContig = 1, kFiltered = -1, kParseFail = -2, kUndefined = -3,
+    kNeedSlow = 100   // internal: split_fast() declined, run scan11()
+};
+enum : int { kStLines = 0, kStCounted, kStNoContig, kStFiltered, kStParseFail, kStUndefined, kStN };
+
+constexpr int kMaxCtxChars = 48;
+constexpr int kMaxRegion   = 30;        // R + 2 <= 32 bases per window
+constexpr int kMaxFragK    = 14;
+constexpr int kMaxField    = 2047;      // sam-parse.h:10 MAX_FIELD_WIDTH - 1
+constexpr int kMaxLine     = 200000;    // sam-parse.h:8  MAX_LINE_LEN (fgets chunk, pss-bam.c:764)
+constexpr int kMaxTlen     = 1000000;   // beyond this the reference's VLAs overflow its stack (pss-bam.c:402)
+
+struct TallyCfg {
+    int      mode;
+    // pss-bam.c:12-18 / fragkon.c:14-18
+    int      R;
+    uint64_t min_len, max_len;
+    uint32_t min_mq;                    // compared unsigned, like `sp->mapq < MIN_MQ`
+    uint32_t merged_only;
+    uint32_t up_mask, down_mask;        // bit s set: symbol s (0..14) is in -U / -D
+    uint32_t up_other, down_other;      // ctx string holds bytes outside the 15 named symbols
+    char     up_ctx[kMaxCtxChars], down_ctx[kMaxCtxChars];
+    int      K;
+};
+
+// one SAM line after the 11 conversions of sam-parse.c:36-48 (offsets are
+// relative to whatever byte accessor produced it)
+struct RecView {
+    uint32_t flag;
+    uint64_t pos;
+    uint32_t mapq;
+    int32_t  tlen;
+    int32_t  rname_off, rname_len;
+    int32_t  cigar_off, cigar_len;
+    int32_t  seq_off, seq_len;
+};
+
+PSS_HD bool is_ws(uint32_t c) { return c == 32u || (c - 9u) <= 4u; }     // isspace(), C locale
+PSS_HD bool is_digit(uint32_t c) { return (c - 48u) <= 9u; }
+
+// ---------------------------------------------------------------------------
+// scan11: the reference's
+//   sscanf(line, "%s\t%u\t%s\t%lu\t%u\t%s\t%s\t%u\t%i\t%s\t%s", ...)   sam-parse.c:36-48
+// on bytes b(0..L), following glibc's conversion rules: every conversion and
+// every "\t" directive skips any run of isspace() bytes; %s takes a maximal
+// run of non-space bytes; %u / %lu take [+-]digits and stop at the first other
+// byte (the rest of the token is left for the next conversion) with strtoul's
+// overflow rule; %i also takes 0x... and 0... with strtol's clamping; a NUL
+// byte ends the string.
+//   return kCounted (0)  -> 11 conversions succeeded and strlen(seq)==strlen(qual)
+//          kParseFail     -> line2saml returns 1
+//          kUndefined     -> one of the first eleven white-space delimited
+//                            runs is longer than the reference's 2048-byte
+//                            fields: its sscanf would overflow them.
+// ---------------------------------------------------------------------------
+template <class B>
+PSS_HD_NOINLINE int scan11(const B &b, int L, RecView &r)
+{
+    {
+        int i = 0, runs = 0;
+        while (i < L && runs < 11) {
+            uint32_t c = b(i);
+            if (c == 0) break;
+            if (is_ws(c)) { i++; continue; }
+            int st = i;
+            while (i < L) { c = b(i); if (c == 0 || is_ws(c)) break; i++; }
+            if (i - st > kMaxField) return kUndefined;
+            runs++;
+        }
+    }
+    int i = 0;
+    int qual_len = 0;
+    for (int conv = 0; conv < 11; conv++) {
+        uint32_t c;
+        for (;;) {                               // leading white space
+            c = i < L ? b(i) : 0u;
+            if (!is_ws(c)) break;
+            i++;
+        }
+        if (c == 0) return kParseFail;           // input failure: fewer than 11 conversions
+        const bool is_str = (conv == 0 || conv == 2 || conv == 5 || conv == 6 || conv == 9 || conv == 10);
+        if (is_str) {
+            int st = i;
+            while (i < L) { c = b(i); if (c == 0 || is_ws(c)) break; i++; }
+            int len = i - st;
+            if (conv == 2)  { r.rname_off = st; r.rname_len = len; }
+            if (conv == 5)  { r.cigar_off = st; r.cigar_len = len; }
+            if (conv == 9)  { r.seq_off = st;   r.seq_len = len; }
+            if (conv == 10) qual_len = len;
+        } else {
+            bool neg = false;
+            if (c == '+' || c == '-') { neg = (c == '-'); i++; c = i < L ? b(i) : 0u; }
+            uint32_t base = 10;
+            int      nd = 0;
+            uint64_t v = 0;
+            bool     ovf = false;
+            if (conv == 8 && c == '0') {         // %i: prefix decides the base
+                uint32_t c1 = (i + 1 < L) ? b(i + 1) : 0u;
+                if ((c1 | 32u) == 'x') { base = 16; i += 2; nd = 1; }   // "0x" alone still converts (to 0)
+                else base = 8;
+            }
+            for (;;) {
+                c = i < L ? b(i) : 0u;
+                uint32_t d;
+                if (is_digit(c)) d = c - '0';
+                else if (base == 16 && (((c | 32u) - 'a') <= 5u)) d = (c | 32u) - 'a' + 10;
+                else break;
+                if (d >= base) break;
+                if (v > (~0ull - d) / base) ovf = true; else v = v * base + d;
+                nd++;
+                i++;
+            }
+            if (nd == 0) return kParseFail;      // matching failure
+            if (conv == 8) {                     // strtol
+                int64_t x;
+                if (!neg) x = (ovf || v > 0x7fffffffffffffffull) ? 0x7fffffffffffffffll : (int64_t)v;
+                else      x = (ovf || v > 0x8000000000000000ull) ? (int64_t)0x8000000000000000ull : (int64_t)(0ull - v);
+                r.tlen = (int32_t)(uint32_t)(uint64_t)x;
+            } else {                             // strtoul
+                const uint64_t x = ovf ? ~0ull : (neg ? 0ull - v : v);
+                if (conv == 1) r.flag = (uint32_t)x;
+                if (conv == 3) r.pos = x;
+                if (conv == 4) r.mapq = (uint32_t)x;
+            }
+        }
+    }
+    if (r.seq_len != qual_len) return kParseFail;    // sam-parse.c:50,88
+    return kCounted;
+}
+
+// ---------------------------------------------------------------------------
+// split_fast: a record [p0, pe) whose terminator sits at pe, located through
+// `le`, the bit mask of bytes <= 0x20 (bit i of le[w] = byte 32w+i).  Accepts
+// only clean records: ten '\t' between eleven non-empty fields, plain decimal
+// numbers.  Everything else is handed to scan11.
+// ---------------------------------------------------------------------------
+template <class B>
+PSS_HD int split_fast(const B &b, const uint32_t *le, int p0, int pe, RecView &r)
+{
+    int      sep[11];
+    int      w = p0 >> 5;
+    uint32_t bits = le[w] & (0xffffffffu << (p0 & 31));
+    int      prev = p0 - 1;
+#pragma unroll
+    for (int f = 0; f < 11; f++) {
+        while (bits == 0) bits = le[++w];          // pe's bit is always set
+        const int p = (w << 5) + ffs32(bits) - 1;
+        bits &= bits - 1;
+        if (p == prev + 1) return kNeedSlow;       // empty field / leading separator
+        if (f < 10) {
+            if (p >= pe) return kNeedSlow;         // fewer than 11 clean fields: let scan11 decide
+            if (b(p) != '\t') return kNeedSlow;
+        }
+        sep[f] = p;
+        prev = p;
+    }
+    if (sep[10] < pe && !is_ws(b(sep[10]))) return kNeedSlow;
+
+    const int qname_len = sep[0] - p0;
+    r.rname_off = sep[1] + 1; r.rname_len = sep[2] - sep[1] - 1;
+    r.cigar_off = sep[4] + 1; r.cigar_len = sep[5] - sep[4] - 1;
+    const int mrnm_len = sep[6] - sep[5] - 1;
+    r.seq_off = sep[8] + 1;   r.seq_len = sep[9] - sep[8] - 1;
+    const int qual_len = sep[10] - sep[9] - 1;
+    if ((qname_len | r.rname_len | r.cigar_len | mrnm_len | r.seq_len | qual_len) > kMaxField) return kNeedSlow;
+
+    // FLAG %u
+    {
+        int a = sep[0] + 1, e = sep[1];
+        if (e - a > 9) return kNeedSlow;
+        uint32_t v = 0;
+        for (; a < e; a++) { uint32_t c = b(a); if (!is_digit(c)) return kNeedSlow; v = v * 10 + (c - '0'); }
+        r.flag = v;
+    }
+    // POS %lu
+    {
+        int a = sep[2] + 1, e = sep[3];
+        if (e - a > 18) return kNeedSlow;
+        uint64_t v = 0;
+        for (; a < e; a++) { uint32_t c = b(a); if (!is_digit(c)) return kNeedSlow; v = v * 10 + (c - '0'); }
+        r.pos = v;
+    }
+    // MAPQ %u
+    {
+        int a = sep[3] + 1, e = sep[4];
+        if (e - a > 9) return kNeedSlow;
+        uint32_t v = 0;
+        for (; a < e; a++) { uint32_t c = b(a); if (!is_digit(c)) return kNeedSlow; v = v * 10 + (c - '0'); }
+        r.mapq = v;
+    }
+    // MPOS %u: value is never read, it only has to convert cleanly
+    {
+        int a = sep[6] + 1, e = sep[7];
+        if (e - a > 18) return kNeedSlow;
+        for (; a < e; a++) if (!is_digit(b(a))) return kNeedSlow;
+    }
+    // TLEN %i: plain decimal only (a leading 0 would switch glibc to octal/hex)
+    {
+        int a = sep[7] + 1, e = sep[8];
+        bool neg = false;
+        uint32_t c = b(a);
+        if (c == '-' || c == '+') { neg = (c == '-'); a++; }
+        if (a >= e || e - a > 9) return kNeedSlow;
+        if (b(a) == '0' && e - a > 1) return kNeedSlow;
+        uint32_t v = 0;
+        for (; a < e; a++) { c = b(a); if (!is_digit(c)) return kNeedSlow; v = v * 10 + (c - '0'); }
+        r.tlen = neg ? -(int32_t)v : (int32_t)v;
+    }
+    if (r.seq_len != qual_len) return kParseFail;     // sam-parse.c:50,88
+    return kCounted;
+}
+
+// ---------------------------------------------------------------------------
+// genome access
+// ---------------------------------------------------------------------------
+// find_seq (fasta-genome-io.c:202-213): exact byte equality of RNAME and a
+// contig id.  Returns contig index or -1.
+template <class B>
+PSS_HD int find_contig(const DevGenome &g, const B &b, int off, int len)
+{
+    uint32_t h = kNameHashSeed;
+    for (int i = 0; i < len; i++) h = name_hash_step(h, (uint8_t)b(off + i));
+    uint32_t slot = h & g.hash_mask;
+    for (;;) {
+        uint32_t v = g.hash[slot];
+        if (v == 0) return -1;
+        const DevContig &c = g.contigs[v - 1];
+        if ((int)c.name_len == len) {
+            const char *nm = g.names + c.name_off;
+            int i = 0;
+            while (i < len && (uint8_t)nm[i] == (uint8_t)b(off + i)) i++;
+            if (i == len) return (int)(v - 1);
+        }
+        slot = (slot + 1) & g.hash_mask;
+    }
+}
+
+// n_fields (<= 32) symbols starting at global base index gb: 2-bit codes and
+// 2-bit classes, field j at bits 2j.
+PSS_HD void load_window(const DevGenome &g, uint64_t gb, int n_fields, uint64_t &codes, uint64_t &classes)
+{
+    const uint64_t gi = gb >> 4;
+    const uint32_t o = (uint32_t)(gb & 15u), sh = 2 * o;
+    const uint64_t g0 = g.groups[gi];
+    const uint64_t g1 = g.groups[gi + 1];
+    const uint64_t g2 = (o + (uint32_t)n_fields > 32u) ? g.groups[gi + 2] : 0ull;
+    const uint32_t c_lo = funnel_r((uint32_t)g0, (uint32_t)g1, sh);
+    const uint32_t c_hi = funnel_r((uint32_t)g1, (uint32_t)g2, sh);
+    const uint32_t k_lo = funnel_r((uint32_t)(g0 >> 32), (uint32_t)(g1 >> 32), sh);
+    const uint32_t k_hi = funnel_r((uint32_t)(g1 >> 32), (uint32_t)(g2 >> 32), sh);
+    const uint64_t m = low_fields_mask(n_fields);
+    codes   = (((uint64_t)c_hi << 32) | c_lo) & m;
+    classes = (((uint64_t)k_hi << 32) | k_lo) & m;
+}
+
+// the byte behind an "other" symbol (binary search in the exception list)
+PSS_HD uint8_t other_char(const DevGenome &g, uint64_t gb)
+{
+    uint32_t lo = 0, hi = g.n_exc;
+    while (lo < hi) {
+        uint32_t mid = lo + (hi - lo) / 2;
+        uint64_t p = g.exc_pos[mid];
+        if (p == gb) return g.exc_chr[mid];
+        if (p < gb) lo = mid + 1; else hi = mid;
+    }
+    return 0xff;
+}
+
+// strchr(UP_CTX|DOWN_CTX, c) != NULL for the genome symbol at gb, after the
+// optional complement of a reverse-strand read (pss-bam.c:60-79 leaves
+// non-ACGT bytes as they are).
+PSS_HD bool ctx_member(const DevGenome &g, const TallyCfg &P, bool down, uint32_t sym, bool complement, uint64_t gb)
+{
+    if (sym < 4u && complement) sym ^= 3u;
+    if (sym != kSymOther) return (((down ? P.down_mask : P.up_mask) >> sym) & 1u) != 0u;
+    if (!(down ? P.down_other : P.up_other)) return false;
+    const uint8_t c = other_char(g, gb);
+    const char *s = down ? P.down_ctx : P.up_ctx;
+    for (int i = 0; i < kMaxCtxChars && s[i]; i++)
+        if ((uint8_t)s[i] == c) return true;
+    return false;
+}
+
+// CIGAR must be the bytes of printf("%dM", n)  (pss-bam.c:113-123, fragkon.c:68-78)
+template <class B>
+PSS_HD bool cigar_is_nM(const B &b, int off, int len, int64_t n)
+{
+    if (len < 2 || len > 11 || n < 0) return false;
+    if (b(off + len - 1) != 'M') return false;
+    if (b(off) == '0' && len != 2) return false;
+    int64_t v = 0;
+    for (int i = 0; i < len - 1; i++) {
+        uint32_t c = b(off + i);
+        if (!is_digit(c)) return false;
+        v = v * 10 + (c - '0');
+    }
+    return v == n;
+}
+
+// read base -> 2-bit code / validity after toupper (pss-bam.c:425, :203-255)
+PSS_HD uint32_t read_code(uint32_t c, uint32_t &bad)
+{
+    c |= 32u;
+    const uint32_t k = (c >> 1) & 3u;            // a->0 c->1 g->3 t->2
+    bad = !(c == 'a' || c == 'c' || c == 'g' || c == 't');
+    return k ^ (k >> 1);                         // a->0 c->1 g->2 t->3
+}
+
+// What one record contributes to the two count tables, in table-row order:
+// field j of *_ref/*_read = row j (rows 0,1 = the context bases two / one
+// away, read := ref there; row i+2 = position i from that end).  A set bit 2j
+// of *_bad means "row j adds nothing".
+struct PssStreams {
+    uint64_t a_ref, a_read, a_bad;     // -> fwd_counts (5' end of the molecule)
+    uint64_t b_ref, b_read, b_bad;     // -> rev_counts (3' end)
+};
+
+constexpr uint64_t kEvenBits = 0x5555555555555555ull;
+
+// pss-bam.c:390-496 process_aln.  Fills `st` (all-bad unless counted).
+template <class B>
+PSS_HD int pss_record(const B &b, const RecView &r, const DevGenome &g, const TallyCfg &P, PssStreams &st)
+{
+    st.a_ref = st.a_read = st.b_ref = st.b_read = 0;
+    st.a_bad = st.b_bad = kEvenBits;
+
+    const int ci = find_contig(g, b, r.rname_off, r.rname_len);            // :393
+    if (ci < 0) return kNoContig;
+    const DevContig ctg = g.contigs[ci];
+    if (ctg.len == 0) return kUndefined;          // `ref->len-1` wraps (:408) and the window copy reads past the string
+
+    const bool paired = r.flag & 1u;
+    // sam-parse.c:66-68: unpaired -> isize = strlen(seq); pss-bam.c:401: n = abs(isize)
+    int64_t n = paired ? (r.tlen < 0 ? -(int64_t)r.tlen : (int64_t)r.tlen) : (int64_t)r.seq_len;
+    if (n > kMaxTlen) return kUndefined;          // reference: stack overflow in its VLAs before any filter
+    const int     R = P.R;
+    const int64_t s = (int64_t)(r.pos - 1);       // :403
+    const int64_t e = s + n - 1;                  // :404
+
+    if (s - 2 < 0) return kFiltered;                                        // :407
+    if ((uint64_t)(e + 2) > ctg.len - 1) return kFiltered;                  // :408
+    if (r.mapq < P.min_mq) return kFiltered;                                // :409
+    if (!((uint64_t)n >= P.min_len && (uint64_t)n <= P.max_len && n >= R)) return kFiltered;   // :96-103
+    if (!cigar_is_nM(b, r.cigar_off, r.cigar_len, n)) return kFiltered;     // :411
+    if (r.flag & (4u | 256u | 512u | 1024u | 2048u)) return kFiltered;      // :412-416
+    if (P.merged_only && paired) return kFiltered;                          // :417
+    // paired: n comes from TLEN; with a shorter SEQ the reference reads bytes
+    // of earlier records that are still in its Saml buffer
+    if (paired && (int64_t)r.seq_len < n) return kUndefined;
+
+    const bool rev = r.flag & 16u;
+    bool want_a, want_b;                          // which table(s) this record feeds
+    const uint64_t gb_up = ctg.base_off + (uint64_t)(s - 1);   // g[1]
+    const uint64_t gb_dn = ctg.base_off + (uint64_t)(e + 1);   // g[n+2]
+
+    const int W = R + 2;
+    uint64_t lc, lk, rc, rk;
+    load_window(g, ctg.base_off + (uint64_t)(s - 2), W, lc, lk);            // g[0 .. W)
+    load_window(g, ctg.base_off + (uint64_t)(e + 2 - (W - 1)), W, rc, rk);  // g[n+3-(W-1) .. n+3]
+    rc = rev_fields64(rc, W);                                               // row j <-> g[n+3-j]
+    rk = rev_fields64(rk, W);
+
+    // symbols of the two adjacent context bases (row 1 of each side)
+    const uint32_t sym_up = (uint32_t)((lc >> 2) & 3u) | ((uint32_t)((lk >> 2) & 3u) << 2);
+    const uint32_t sym_dn = (uint32_t)((rc >> 2) & 3u) | ((uint32_t)((rk >> 2) & 3u) << 2);
+    // molecule orientation: forward read -> 5' context is g[1]; reverse read ->
+    // 5' context is comp(g[n+2]) (pss-bam.c:430-436)
+    const bool up_ok = rev ? ctx_member(g, P, false, sym_dn, true, gb_dn) : ctx_member(g, P, false, sym_up, false, gb_up);
+    const bool dn_ok = rev ? ctx_member(g, P, true, sym_up, true, gb_up) : ctx_member(g, P, true, sym_dn, false, gb_dn);
+
+    if (!paired) {                                                          // :428-447
+        if (!(up_ok && dn_ok)) return kFiltered;
+        want_a = want_b = true;
+    } else if ((r.flag & 2u) && !(r.flag & 8u)) {                           // :450-452
+        if ((r.flag & 64u) && up_ok)       { want_a = true;  want_b = false; }   // :460 / :482
+        else if ((r.flag & 128u) && dn_ok) { want_a = false; want_b = true;  }   // :471 / :488
+        else return kFiltered;
+    } else {
+        return kFiltered;
+    }
+
+    // read bases: prefix r[0..R) in rows 2.., suffix r[n-1-i] in rows 2..
+    uint64_t pre = 0, pre_bad = 0, suf = 0, suf_bad = 0;
+    for (int i = 0; i < R; i++) {
+        uint32_t bad0, bad1;
+        const uint32_t c0 = read_code(b(r.seq_off + i), bad0);
+        const uint32_t c1 = read_code(b(r.seq_off + (int)n - 1 - i), bad1);
+        pre |= (uint64_t)c0 << (2 * i + 4);  pre_bad |= (uint64_t)bad0 << (2 * i + 4);
+        suf |= (uint64_t)c1 << (2 * i + 4);  suf_bad |= (uint64_t)bad1 << (2 * i + 4);
+    }
+    const uint64_t m = low_fields_mask(W);
+    // class != 0 -> not one of ACGT -> the cell is skipped (:253-255, :176-188)
+    const uint64_t l_bad = ((lk | (lk >> 1)) & kEvenBits) | pre_bad;
+    const uint64_t r_bad = ((rk | (rk >> 1)) & kEvenBits) | suf_bad;
+    const uint64_t l_read = (lc & 0xfull) | pre;      // rows 0,1: diagonal cell of the context base
+    const uint64_t r_read = (rc & 0xfull) | suf;
+
+    if (!rev) {
+        st.a_ref = lc; st.a_read = l_read; st.a_bad = want_a ? l_bad : kEvenBits;
+        st.b_ref = rc; st.b_read = r_read; st.b_bad = want_b ? r_bad : kEvenBits;
+    } else {                                      // complement = flip both code bits
+        st.a_ref = ~rc & m; st.a_read = ~r_read & m; st.a_bad = want_a ? r_bad : kEvenBits;
+        st.b_ref = ~lc & m; st.b_read = ~l_read & m; st.b_bad = want_b ? l_bad : kEvenBits;
+    }
+    return kCounted;
+}
+
+// ---------------------------------------------------------------------------
+// fragkon.c:122-216 process_aln.  Outputs up to two histogram indices
+// (MSB-first 2-bit k-mer code, kmer.c:184-214); *_ok says whether to count.
+// ---------------------------------------------------------------------------
+struct FkHits {
+    uint32_t idx5, idx3;
+    bool     add5, add3;
+};
+
+// K (<= 14) symbols starting at gb -> LSB-first code word; false if any is not ACGT
+PSS_HD bool load_kmer(const DevGenome &g, uint64_t gb, int K, uint32_t &lsb_first)
+{
+    const uint64_t gi = gb >> 4;
+    const uint32_t sh = 2 * (uint32_t)(gb & 15u);
+    const uint64_t g0 = g.groups[gi], g1 = g.groups[gi + 1];
+    const uint32_t m = (K >= 16) ? 0xffffffffu : ((1u << (2 * K)) - 1u);
+    lsb_first = funnel_r((uint32_t)g0, (uint32_t)g1, sh) & m;
+    return (funnel_r((uint32_t)(g0 >> 32), (uint32_t)(g1 >> 32), sh) & m) == 0u;
+}
+PSS_HD uint32_t kmer_index_fwd(uint32_t lsb_first, int K) { return rev_fields32(lsb_first) >> (32 - 2 * K); }
+// reverse complement: the LSB-first word of the forward strand IS the
+// MSB-first word of the reversed k-mer; complement = flip all bits
+PSS_HD uint32_t kmer_index_rc(uint32_t lsb_first, int K) { return ~lsb_first & ((1u << (2 * K)) - 1u); }
+
+template <class B>
+PSS_HD int fk_record(const B &b, const RecView &r, const DevGenome &g, const TallyCfg &P, FkHits &h)
+{
+    h.add5 = h.add3 = false;
+    h.idx5 = h.idx3 = 0;
+    const int ci = find_contig(g, b, r.rname_off, r.rname_len);            // :124
+    if (ci < 0) return kNoContig;
+    const DevContig ctg = g.contigs[ci];
+    if (ctg.len == 0) return kUndefined;          // `ref->len-1` wraps (:138)
+
+    const int      K = P.K;
+    const uint64_t ok = (uint64_t)(K / 2), ik = (uint64_t)K - ok;          // :134-135
+    const uint64_t n = (uint64_t)r.seq_len;                                 // :130 (strlen(seq), not TLEN)
+    const uint64_t s = r.pos - 1;                                           // :129, unsigned: POS 0 wraps
+    const uint64_t e = s + n - 1;
+    // `aln_start-(KLEN/2) >= 0` is an unsigned tautology (:137)
+    if (!(e + ok <= ctg.len - 1)) return kFiltered;                        // :138
+    if (!(r.mapq >= P.min_mq)) return kFiltered;                           // :139
+    if (!(n >= P.min_len && n <= P.max_len)) return kFiltered;             // :52-58
+    if (!cigar_is_nM(b, r.cigar_off, r.cigar_len, (int64_t)n)) return kFiltered;   // :141
+    if (r.flag & (4u | 256u | 512u | 1024u | 2048u)) return kFiltered;     // :142-146
+
+    const bool    rev = r.flag & 16u;
+    const int64_t ss = (int64_t)s;                // -1 when POS was 0
+    bool     v5, v3;
+    uint32_t w5, w3;
+    if (!rev) {
+        // 5' window G[s-ok, s-ok+K), 3' window G[s+n-ik, s+n-ik+K)  (:176-177).
+        // Left of the contig the reference reads the allocator's header,
+        // whose last byte is 0 -> such a window never validates; the packed
+        // genome has "other" symbols there.
+        v5 = load_kmer(g, ctg.base_off + (uint64_t)(ss - (int64_t)ok), K, w5);
+        v3 = load_kmer(g, ctg.base_off + (uint64_t)(ss + (int64_t)n - (int64_t)ik), K, w3);
+        h.idx5 = kmer_index_fwd(w5, K);
+        h.idx3 = kmer_index_fwd(w3, K);
+    } else {
+        // sub = G[s-ok, s-ok+n+K) copied with strncpy (:156): a terminator
+        // left of the contig zero-fills everything after it, so s < ok kills
+        // both k-mers.  5' = RC(sub)[0,K) = RC(G[s-ok+n, +K)) (:164);
+        // 3' = RC(sub)[ok+n-ik, +K) = RC(G[s-ok+(ik-ok), +K)) (:167).
+        v5 = load_kmer(g, ctg.base_off + (uint64_t)(ss - (int64_t)ok + (int64_t)n), K, w5);
+        v3 = load_kmer(g, ctg.base_off + (uint64_t)(ss - (int64_t)ok + (int64_t)(ik - ok)), K, w3);
+        if (ss < (int64_t)ok) v5 = v3 = false;
+        h.idx5 = kmer_index_rc(w5, K);
+        h.idx3 = kmer_index_rc(w3, K);
+    }
+
+    if (!(r.flag & 1u)) {                                                   // :149-184
+        h.add5 = v5; h.add3 = v3;                // both ends attempted independently
+        return (v5 && v3) ? kCounted : kFiltered;
+    }
+    if (!P.merged_only && (r.flag & 2u) && !(r.flag & 8u)) {                // :187-190
+        if (r.flag & 64u)  { h.add5 = v5; return v5 ? kCounted : kFiltered; }
+        if (r.flag & 128u) { h.add3 = v3; return v3 ? kCounted : kFiltered; }
+    }
+    return kFiltered;
+}
+
+}  // namespace pssgpu

@@ -1,0 +1,797 @@
+// pssgpu.cu -- the C ABI of include/pssgpu.h on top of the sm_100a kernels.
+//
+// One context = one CUDA device + one stream.  All work of a context is
+// stream ordered on that stream: H2D staging copies, pack / tally / spectrum
+// kernels and the final D2H of the tables.  There is no CPU implementation of
+// any entry point in this library.
+#include "../../include/pssgpu.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "pss_kernels.cuh"
+
+using namespace pssgpu;
+
+namespace {
+
+constexpr size_t kFeedPiece   = 64ull << 20;     // bytes of SAM text per tally launch when fed from the host
+constexpr size_t kCarryCap    = 4ull << 20;      // longest partial line carried between feeds
+constexpr size_t kStageCap    = kFeedPiece + kCarryCap;
+constexpr size_t kPackPiece   = 128ull << 20;    // ASCII bases per pack launch when uploading from the host
+constexpr uint64_t kExcCap    = 4ull << 20;      // logged "other" symbols (beyond: -U/-D with such bytes unsupported)
+
+thread_local std::string g_init_error;
+
+}  // namespace
+
+struct pssgpu_ctx {
+    int          device = -1;
+    int          sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::string  err;
+
+    // genome
+    uint64_t  *d_groups = nullptr;
+    uint64_t   n_groups = 0, n_bases = 0, n_contigs = 0, genome_bytes = 0;
+    DevContig *d_contigs = nullptr;
+    char      *d_names = nullptr;
+    uint32_t  *d_hash = nullptr;
+    uint32_t   hash_mask = 0;
+    uint64_t  *d_exc_pos = nullptr;
+    uint8_t   *d_exc_chr = nullptr;
+    uint32_t   n_exc = 0;
+    bool       exc_overflow = false;
+    bool       have_genome = false;
+
+    // tally
+    int       mode = -1;
+    TallyCfg  cfg{};
+    unsigned long long *d_tables = nullptr;   // pss: 2*(R+2)*16
+    unsigned long long *d_fk = nullptr;       // fragkon: 2*4^K
+    size_t    fk_elems = 0;
+    unsigned long long *d_stats = nullptr;    // kStN
+    int       tally_grid_pss = 0, tally_grid_fk = 0;
+
+    // host feed staging
+    uint8_t  *d_stage[2] = { nullptr, nullptr };
+    int       cur = 0;
+    size_t    carry_len = 0;
+    uint64_t  fed_bytes = 0;                  // bytes handed to pssgpu_feed* since *_begin
+    cudaEvent_t copy_done = nullptr;
+
+    // timing
+    bool      timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+    std::vector<cudaEvent_t> ev_pool;
+    uint64_t  launches = 0, bytes_scanned = 0, h2d_bytes = 0, d2h_bytes = 0;
+    double    kernel_ms = 0.0;
+
+    // debug log
+    bool      dbg = false;
+    uint64_t *d_dbg_off = nullptr;
+    int8_t   *d_dbg_code = nullptr;
+    unsigned long long *d_dbg_n = nullptr;
+    uint64_t  dbg_cap = 0;
+};
+
+namespace {
+
+int fail(pssgpu_ctx *c, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_init_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? PSSGPU_ENOMEM : PSSGPU_ECUDA,       \
+                        "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);      \
+    } while (0)
+
+struct Bind {          // make the context's device current for the duration of a call
+    int prev = -1;
+    explicit Bind(const pssgpu_ctx *c) { cudaGetDevice(&prev); if (prev != c->device) cudaSetDevice(c->device); else prev = -1; }
+    ~Bind() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+cudaEvent_t take_event(pssgpu_ctx *c)
+{
+    cudaEvent_t e = nullptr;
+    if (!c->ev_pool.empty()) { e = c->ev_pool.back(); c->ev_pool.pop_back(); return e; }
+    cudaEventCreate(&e);
+    return e;
+}
+void time_begin(pssgpu_ctx *c, uint64_t bytes)
+{
+    c->launches++;
+    c->bytes_scanned += bytes;
+    if (!c->timing) return;
+    cudaEvent_t a = take_event(c), b = take_event(c);
+    cudaEventRecord(a, c->stream);
+    c->ev.emplace_back(a, b);
+}
+void time_end(pssgpu_ctx *c)
+{
+    if (!c->timing) return;
+    cudaEventRecord(c->ev.back().second, c->stream);
+}
+void time_collect(pssgpu_ctx *c)       // stream must be idle
+{
+    for (auto &p : c->ev) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) c->kernel_ms += ms;
+        c->ev_pool.push_back(p.first);
+        c->ev_pool.push_back(p.second);
+    }
+    c->ev.clear();
+}
+
+void free_genome(pssgpu_ctx *c)
+{
+    cudaFree(c->d_groups);  c->d_groups = nullptr;
+    cudaFree(c->d_contigs); c->d_contigs = nullptr;
+    cudaFree(c->d_names);   c->d_names = nullptr;
+    cudaFree(c->d_hash);    c->d_hash = nullptr;
+    cudaFree(c->d_exc_pos); c->d_exc_pos = nullptr;
+    cudaFree(c->d_exc_chr); c->d_exc_chr = nullptr;
+    c->n_groups = c->n_bases = c->n_contigs = c->genome_bytes = 0;
+    c->n_exc = 0;
+    c->exc_overflow = false;
+    c->have_genome = false;
+}
+
+DevGenome dev_genome(const pssgpu_ctx *c)
+{
+    DevGenome g;
+    g.groups = c->d_groups;   g.n_groups = c->n_groups;
+    g.contigs = c->d_contigs; g.n_contigs = (uint32_t)c->n_contigs;
+    g.names = c->d_names;     g.hash = c->d_hash; g.hash_mask = c->hash_mask;
+    g.exc_pos = c->d_exc_pos; g.exc_chr = c->d_exc_chr; g.n_exc = c->n_exc;
+    return g;
+}
+
+int upload_impl(pssgpu_ctx *ctx, const pssgpu_contig *contigs, uint64_t n, bool src_on_device)
+{
+    if (!ctx || (!contigs && n)) return fail(ctx, PSSGPU_EINVAL, "genome_upload: null argument");
+    if (n > 0x7fffffffull) return fail(ctx, PSSGPU_EUNSUPP, "genome_upload: too many contigs");
+    Bind bind(ctx);
+    CU(cudaStreamSynchronize(ctx->stream));
+    free_genome(ctx);
+
+    // layout + name table
+    std::vector<DevContig> tab(n);
+    std::string            names;
+    uint64_t               cur = kPadBases, total = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        if (!contigs[i].id || (!contigs[i].seq && contigs[i].len)) return fail(ctx, PSSGPU_EINVAL, "genome_upload: contig %llu has a null field", (unsigned long long)i);
+        const size_t nl = strlen(contigs[i].id);
+        if (names.size() + nl > 0xfffffff0ull) return fail(ctx, PSSGPU_EUNSUPP, "genome_upload: contig names exceed 4 GiB");
+        tab[i].base_off = cur;
+        tab[i].len = contigs[i].len;
+        tab[i].name_off = (uint32_t)names.size();
+        tab[i].name_len = (uint32_t)nl;
+        names.append(contigs[i].id, nl);
+        cur += ((contigs[i].len + 15) / 16) * 16 + kPadBases;
+        total += contigs[i].len;
+    }
+    {   // find_seq() on duplicate ids depends on qsort/bsearch internals: refuse
+        std::vector<uint64_t> order(n);
+        for (uint64_t i = 0; i < n; i++) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return strcmp(contigs[a].id, contigs[b].id) < 0; });
+        for (uint64_t i = 1; i < n; i++)
+            if (strcmp(contigs[order[i - 1]].id, contigs[order[i]].id) == 0)
+                return fail(ctx, PSSGPU_EUNSUPP, "genome_upload: duplicate contig id '%s' (find_seq result would be unspecified)", contigs[order[i]].id);
+    }
+    const uint64_t n_groups = cur / 16 + 2;       // + slack for the (gi+2) read of a 3-group window
+    uint32_t hash_size = 16;
+    while (hash_size < 2 * n + 1) hash_size <<= 1;
+    std::vector<uint32_t> hash(hash_size, 0);
+    for (uint64_t i = 0; i < n; i++) {
+        uint32_t h = kNameHashSeed;
+        for (uint32_t k = 0; k < tab[i].name_len; k++) h = name_hash_step(h, (uint8_t)names[tab[i].name_off + k]);
+        uint32_t slot = h & (hash_size - 1);
+        while (hash[slot]) slot = (slot + 1) & (hash_size - 1);
+        hash[slot] = (uint32_t)i + 1;
+    }
+
+    uint32_t *d_flags = nullptr;
+    unsigned long long *d_exc_n = nullptr;
+    uint8_t *d_piece = nullptr;
+    auto cleanup = [&]() { cudaFree(d_flags); cudaFree(d_exc_n); cudaFree(d_piece); };
+#define CUX(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            cleanup(); free_genome(ctx);                                                           \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? PSSGPU_ENOMEM : PSSGPU_ECUDA,       \
+                        "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);      \
+        }                                                                                          \
+    } while (0)
+
+    CUX(cudaMalloc(&ctx->d_groups, n_groups * sizeof(uint64_t)));
+    CUX(cudaMemsetAsync(ctx->d_groups, 0xff, n_groups * sizeof(uint64_t), ctx->stream));   // everything "other" until packed
+    CUX(cudaMalloc(&ctx->d_exc_pos, kExcCap * sizeof(uint64_t)));
+    CUX(cudaMalloc(&ctx->d_exc_chr, kExcCap));
+    CUX(cudaMalloc(&d_flags, sizeof(uint32_t)));
+    CUX(cudaMalloc(&d_exc_n, sizeof(unsigned long long)));
+    CUX(cudaMemsetAsync(d_flags, 0, sizeof(uint32_t), ctx->stream));
+    CUX(cudaMemsetAsync(d_exc_n, 0, sizeof(unsigned long long), ctx->stream));
+    if (!src_on_device) CUX(cudaMalloc(&d_piece, kPackPiece));
+
+    for (uint64_t i = 0; i < n; i++) {
+        for (uint64_t off = 0; off < contigs[i].len; off += kPackPiece) {
+            const uint64_t nb = std::min<uint64_t>(kPackPiece, contigs[i].len - off);
+            PackArgs a;
+            if (src_on_device) {
+                a.src = reinterpret_cast<const uint8_t *>(contigs[i].seq) + off;
+            } else {
+                CUX(cudaMemcpyAsync(d_piece, contigs[i].seq + off, nb, cudaMemcpyHostToDevice, ctx->stream));
+                ctx->h2d_bytes += nb;
+                a.src = d_piece;
+            }
+            a.n_bases = nb;
+            a.dst = ctx->d_groups + (tab[i].base_off + off) / 16;
+            a.gbase = tab[i].base_off + off;
+            a.exc_pos = ctx->d_exc_pos; a.exc_chr = ctx->d_exc_chr; a.exc_n = d_exc_n; a.exc_cap = kExcCap;
+            a.flags = d_flags;
+            const uint64_t groups = (nb + 15) / 16;
+            const unsigned grid = (unsigned)std::min<uint64_t>((groups + 255) / 256, (uint64_t)ctx->sm_count * 8);
+            time_begin(ctx, nb);
+            pack_kernel<<<grid, 256, 0, ctx->stream>>>(a);
+            time_end(ctx);
+            CUX(cudaGetLastError());
+        }
+    }
+    uint32_t flags = 0;
+    unsigned long long exc_n = 0;
+    CUX(cudaMemcpyAsync(&flags, d_flags, sizeof flags, cudaMemcpyDeviceToHost, ctx->stream));
+    CUX(cudaMemcpyAsync(&exc_n, d_exc_n, sizeof exc_n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUX(cudaStreamSynchronize(ctx->stream));
+    time_collect(ctx);
+    if (flags & 1u) {
+        cleanup(); free_genome(ctx);
+        return fail(ctx, PSSGPU_EUNSUPP, "genome_upload: a contig contains a NUL byte");
+    }
+    if (exc_n > kExcCap) {
+        ctx->exc_overflow = true;
+        ctx->n_exc = 0;
+    } else if (exc_n > 0) {
+        std::vector<uint64_t> pos(exc_n);
+        std::vector<uint8_t>  chr(exc_n);
+        CUX(cudaMemcpy(pos.data(), ctx->d_exc_pos, exc_n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        CUX(cudaMemcpy(chr.data(), ctx->d_exc_chr, exc_n, cudaMemcpyDeviceToHost));
+        std::vector<uint32_t> order(exc_n);
+        for (uint32_t k = 0; k < exc_n; k++) order[k] = k;
+        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return pos[a] < pos[b]; });
+        std::vector<uint64_t> spos(exc_n);
+        std::vector<uint8_t>  schr(exc_n);
+        for (uint32_t k = 0; k < exc_n; k++) { spos[k] = pos[order[k]]; schr[k] = chr[order[k]]; }
+        CUX(cudaMemcpy(ctx->d_exc_pos, spos.data(), exc_n * sizeof(uint64_t), cudaMemcpyHostToDevice));
+        CUX(cudaMemcpy(ctx->d_exc_chr, schr.data(), exc_n, cudaMemcpyHostToDevice));
+        ctx->n_exc = (uint32_t)exc_n;
+    }
+    CUX(cudaMalloc(&ctx->d_contigs, std::max<size_t>(1, n) * sizeof(DevContig)));
+    CUX(cudaMalloc(&ctx->d_names, std::max<size_t>(1, names.size())));
+    CUX(cudaMalloc(&ctx->d_hash, hash_size * sizeof(uint32_t)));
+    if (n) CUX(cudaMemcpy(ctx->d_contigs, tab.data(), n * sizeof(DevContig), cudaMemcpyHostToDevice));
+    if (!names.empty()) CUX(cudaMemcpy(ctx->d_names, names.data(), names.size(), cudaMemcpyHostToDevice));
+    CUX(cudaMemcpy(ctx->d_hash, hash.data(), hash_size * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    cleanup();
+#undef CUX
+    ctx->hash_mask = hash_size - 1;
+    ctx->n_groups = n_groups;
+    ctx->n_bases = total;
+    ctx->n_contigs = n;
+    ctx->genome_bytes = n_groups * sizeof(uint64_t) + kExcCap * 9 + n * sizeof(DevContig) + names.size() + hash_size * 4;
+    ctx->have_genome = true;
+    return PSSGPU_OK;
+}
+
+// bit mask over the 15 named symbols + list of other bytes of a -U / -D string
+int ctx_string(pssgpu_ctx *ctx, const char *s, uint32_t *mask, uint32_t *other, char *copy)
+{
+    static const char named[] = PSSGPU_SYM_CHARS;
+    *mask = 0; *other = 0;
+    memset(copy, 0, kMaxCtxChars);
+    if (!s) return fail(ctx, PSSGPU_EINVAL, "context string is null");
+    const size_t n = strlen(s);
+    if (n >= (size_t)kMaxCtxChars) return fail(ctx, PSSGPU_EUNSUPP, "context string longer than %d bytes", kMaxCtxChars - 1);
+    memcpy(copy, s, n);
+    for (size_t i = 0; i < n; i++) {
+        const char *p = strchr(named, s[i]);
+        if (p && *p) *mask |= 1u << (p - named);
+        else *other = 1;      // lower case letters land here too: the genome is upper-cased, they can never match
+    }
+    return PSSGPU_OK;
+}
+
+template <int MODE>
+int launch_tally(pssgpu_ctx *ctx, const uint8_t *d_sam, size_t len, uint64_t stream_off)
+{
+    if (len == 0) return PSSGPU_OK;
+    TallyArgs a;
+    a.sam = d_sam; a.len = len; a.stream_off = stream_off;
+    a.g = dev_genome(ctx);
+    a.cfg = ctx->cfg;
+    a.pss_tables = ctx->d_tables;
+    a.fk_hist = ctx->d_fk;
+    a.stats = ctx->d_stats;
+    a.dbg_off = ctx->dbg ? ctx->d_dbg_off : nullptr;
+    a.dbg_code = ctx->dbg ? ctx->d_dbg_code : nullptr;
+    a.dbg_n = ctx->dbg ? ctx->d_dbg_n : nullptr;
+    a.dbg_cap = ctx->dbg_cap;
+    const uint64_t n_tiles = (len + kTileMain - 1) / kTileMain;
+    const int      max_grid = MODE == kModePss ? ctx->tally_grid_pss : ctx->tally_grid_fk;
+    const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)max_grid);
+    time_begin(ctx, len);
+    tally_kernel<MODE><<<grid, kThreads, sizeof(TallySmem), ctx->stream>>>(a);
+    time_end(ctx);
+    CU(cudaGetLastError());
+    return PSSGPU_OK;
+}
+
+int launch_tally_mode(pssgpu_ctx *ctx, const uint8_t *d_sam, size_t len, uint64_t stream_off)
+{
+    return ctx->mode == kModePss ? launch_tally<kModePss>(ctx, d_sam, len, stream_off)
+                                 : launch_tally<kModeFragkon>(ctx, d_sam, len, stream_off);
+}
+
+int begin_common(pssgpu_ctx *ctx)
+{
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (!ctx->d_stats) CU(cudaMalloc(&ctx->d_stats, kStN * sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(ctx->d_stats, 0, kStN * sizeof(unsigned long long), ctx->stream));
+    if (ctx->d_dbg_n) CU(cudaMemsetAsync(ctx->d_dbg_n, 0, sizeof(unsigned long long), ctx->stream));
+    ctx->carry_len = 0;
+    ctx->cur = 0;
+    ctx->fed_bytes = 0;
+    return PSSGPU_OK;
+}
+
+}  // namespace
+
+// ===========================================================================
+extern "C" {
+
+int pssgpu_abi_version(void) { return PSSGPU_ABI_VERSION; }
+
+int pssgpu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return n;
+}
+
+int pssgpu_init(int device, pssgpu_ctx **out)
+{
+    pssgpu_ctx *ctx = nullptr;       // CU() reports through g_init_error while ctx is null
+    if (!out) return fail(nullptr, PSSGPU_EINVAL, "pssgpu_init: out is null");
+    *out = nullptr;
+    int n = 0;
+    CU(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return fail(nullptr, PSSGPU_EINVAL, "pssgpu_init: device %d of %d", device, n);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(nullptr, PSSGPU_EUNSUPP, "pssgpu_init: device %d is sm_%d%d; this library holds sm_100a code only",
+                    device, prop.major, prop.minor);
+    CU(cudaSetDevice(device));
+    pssgpu_ctx *c = new pssgpu_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tally_kernel<kModePss>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TallySmem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tally_kernel<kModeFragkon>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TallySmem));
+    int occ_p = 0, occ_f = 0;
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, tally_kernel<kModePss>, kThreads, sizeof(TallySmem));
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, tally_kernel<kModeFragkon>, kThreads, sizeof(TallySmem));
+    if (e != cudaSuccess || occ_p < 1 || occ_f < 1) {
+        fail(nullptr, PSSGPU_ECUDA, "pssgpu_init: %s (occupancy %d/%d)", cudaGetErrorString(e), occ_p, occ_f);
+        if (c->stream) cudaStreamDestroy(c->stream);
+        if (c->copy_done) cudaEventDestroy(c->copy_done);
+        delete c;
+        return PSSGPU_ECUDA;
+    }
+    c->tally_grid_pss = c->sm_count * occ_p;
+    c->tally_grid_fk = c->sm_count * occ_f;
+    *out = c;
+    return PSSGPU_OK;
+}
+
+void pssgpu_destroy(pssgpu_ctx *ctx)
+{
+    if (!ctx) return;
+    Bind bind(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    free_genome(ctx);
+    cudaFree(ctx->d_tables); cudaFree(ctx->d_fk); cudaFree(ctx->d_stats);
+    cudaFree(ctx->d_stage[0]); cudaFree(ctx->d_stage[1]);
+    cudaFree(ctx->d_dbg_off); cudaFree(ctx->d_dbg_code); cudaFree(ctx->d_dbg_n);
+    for (auto &p : ctx->ev) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *pssgpu_last_error(const pssgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_init_error.c_str(); }
+
+void *pssgpu_cuda_stream(pssgpu_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+void *pssgpu_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void pssgpu_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// ---- genome ---------------------------------------------------------------
+int pssgpu_genome_upload(pssgpu_ctx *ctx, const pssgpu_contig *contigs, uint64_t n) { return upload_impl(ctx, contigs, n, false); }
+int pssgpu_genome_upload_device(pssgpu_ctx *ctx, const pssgpu_contig *contigs, uint64_t n) { return upload_impl(ctx, contigs, n, true); }
+
+int pssgpu_genome_info(const pssgpu_ctx *ctx, uint64_t *n_contigs, uint64_t *n_bases, uint64_t *hbm_bytes)
+{
+    if (!ctx || !ctx->have_genome) return PSSGPU_ENOGENOME;
+    if (n_contigs) *n_contigs = ctx->n_contigs;
+    if (n_bases) *n_bases = ctx->n_bases;
+    if (hbm_bytes) *hbm_bytes = ctx->genome_bytes;
+    return PSSGPU_OK;
+}
+
+// ---- pss-bam ----------------------------------------------------------------
+void pssgpu_pss_default_params(pssgpu_pss_params *p)
+{
+    if (!p) return;
+    p->region_len = 15;          // pss-bam.c:12
+    p->min_len = 0;              // :13
+    p->max_len = 250000000UL;    // :14
+    p->min_mq = 0;               // :15
+    p->up_ctx = "ACGT";          // :16
+    p->down_ctx = "ACGT";        // :17
+    p->merged_only = 0;          // :18
+}
+
+int pssgpu_pss_begin(pssgpu_ctx *ctx, const pssgpu_pss_params *p)
+{
+    if (!ctx || !p) return fail(ctx, PSSGPU_EINVAL, "pss_begin: null argument");
+    if (!ctx->have_genome) return fail(ctx, PSSGPU_ENOGENOME, "pss_begin: no genome resident");
+    if (p->region_len < 0 || p->region_len > kMaxRegion)
+        return fail(ctx, PSSGPU_EUNSUPP, "pss_begin: region_len %d outside [0,%d]", p->region_len, kMaxRegion);
+    Bind bind(ctx);
+    TallyCfg c{};
+    c.mode = kModePss;
+    c.R = p->region_len;
+    c.min_len = p->min_len;
+    c.max_len = p->max_len;
+    c.min_mq = (uint32_t)p->min_mq;      // `sp->mapq < MIN_MQ` converts MIN_MQ to unsigned (pss-bam.c:409)
+    c.merged_only = p->merged_only ? 1u : 0u;
+    c.K = 0;
+    int rc;
+    if ((rc = ctx_string(ctx, p->up_ctx, &c.up_mask, &c.up_other, c.up_ctx)) != PSSGPU_OK) return rc;
+    if ((rc = ctx_string(ctx, p->down_ctx, &c.down_mask, &c.down_other, c.down_ctx)) != PSSGPU_OK) return rc;
+    if ((c.up_other || c.down_other) && ctx->exc_overflow)
+        return fail(ctx, PSSGPU_EUNSUPP, "pss_begin: -U/-D name bytes outside " PSSGPU_SYM_CHARS " and the genome holds more than %llu such bytes",
+                    (unsigned long long)kExcCap);
+    if ((rc = begin_common(ctx)) != PSSGPU_OK) return rc;
+    cudaFree(ctx->d_tables); ctx->d_tables = nullptr;
+    const size_t elems = 2 * (size_t)(c.R + 2) * 16;
+    CU(cudaMalloc(&ctx->d_tables, elems * sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(ctx->d_tables, 0, elems * sizeof(unsigned long long), ctx->stream));
+    ctx->cfg = c;
+    ctx->mode = kModePss;
+    return PSSGPU_OK;
+}
+
+int pssgpu_feed(pssgpu_ctx *ctx, const char *sam, size_t len, int last)
+{
+    if (!ctx || (!sam && len)) return fail(ctx, PSSGPU_EINVAL, "feed: null argument");
+    if (ctx->mode < 0) return fail(ctx, PSSGPU_EINVAL, "feed: no tally open (call *_begin first)");
+    Bind bind(ctx);
+    for (int s = 0; s < 2; s++)
+        if (!ctx->d_stage[s]) CU(cudaMalloc(&ctx->d_stage[s], kStageCap + 64));
+    size_t off = 0;
+    bool   copied = false;
+    while (off < len) {
+        const size_t room = kStageCap - ctx->carry_len;
+        if (room == 0) return fail(ctx, PSSGPU_EUNSUPP, "feed: a line longer than %zu bytes", kStageCap);
+        const size_t plen = std::min(std::min(len - off, kFeedPiece), room);
+        const char  *piece = sam + off;
+        const char  *nl = (const char *)memrchr(piece, '\n', plen);
+        uint8_t     *slot = ctx->d_stage[ctx->cur];
+        if (!nl) {                       // no line ends in this piece: it only grows the carry
+            CU(cudaMemcpyAsync(slot + ctx->carry_len, piece, plen, cudaMemcpyHostToDevice, ctx->stream));
+            ctx->carry_len += plen;
+        } else {
+            const size_t cut = (size_t)(nl - piece) + 1, tail = plen - cut;
+            CU(cudaMemcpyAsync(slot + ctx->carry_len, piece, cut, cudaMemcpyHostToDevice, ctx->stream));
+            const size_t   klen = ctx->carry_len + cut;
+            const uint64_t soff = ctx->fed_bytes + off - ctx->carry_len;
+            int rc = launch_tally_mode(ctx, slot, klen, soff);
+            if (rc != PSSGPU_OK) return rc;
+            ctx->cur ^= 1;
+            if (tail) CU(cudaMemcpyAsync(ctx->d_stage[ctx->cur], piece + cut, tail, cudaMemcpyHostToDevice, ctx->stream));
+            ctx->carry_len = tail;
+        }
+        ctx->h2d_bytes += plen;
+        copied = true;
+        off += plen;
+    }
+    ctx->fed_bytes += len;
+    if (last && ctx->carry_len) {        // final line without '\n' (fgets hands it out as is)
+        const uint64_t soff = ctx->fed_bytes - ctx->carry_len;
+        int rc = launch_tally_mode(ctx, ctx->d_stage[ctx->cur], ctx->carry_len, soff);
+        if (rc != PSSGPU_OK) return rc;
+        ctx->cur ^= 1;
+        ctx->carry_len = 0;
+    }
+    if (copied) {                        // the caller may reuse `sam` as soon as we return
+        CU(cudaEventRecord(ctx->copy_done, ctx->stream));
+        // the record sits behind the last tally launch too; waiting for it keeps the contract simple
+        CU(cudaEventSynchronize(ctx->copy_done));
+    }
+    return PSSGPU_OK;
+}
+
+int pssgpu_feed_device(pssgpu_ctx *ctx, const void *d_sam, size_t len)
+{
+    if (!ctx || (!d_sam && len)) return fail(ctx, PSSGPU_EINVAL, "feed_device: null argument");
+    if (ctx->mode < 0) return fail(ctx, PSSGPU_EINVAL, "feed_device: no tally open (call *_begin first)");
+    if (ctx->carry_len) return fail(ctx, PSSGPU_EINVAL, "feed_device: a partial line from pssgpu_feed is pending");
+    if ((uintptr_t)d_sam & 15u) return fail(ctx, PSSGPU_EINVAL, "feed_device: pointer must be 16-byte aligned");
+    Bind bind(ctx);
+    int rc = launch_tally_mode(ctx, (const uint8_t *)d_sam, len, ctx->fed_bytes);
+    ctx->fed_bytes += len;
+    return rc;
+}
+
+int pssgpu_sync(pssgpu_ctx *ctx)
+{
+    if (!ctx) return PSSGPU_EINVAL;
+    Bind bind(ctx);
+    CU(cudaStreamSynchronize(ctx->stream));
+    time_collect(ctx);
+    return PSSGPU_OK;
+}
+
+int pssgpu_pss_finish(pssgpu_ctx *ctx, uint64_t *fwd, uint64_t *rev)
+{
+    if (!ctx || !fwd || !rev) return fail(ctx, PSSGPU_EINVAL, "pss_finish: null argument");
+    if (ctx->mode != kModePss) return fail(ctx, PSSGPU_EINVAL, "pss_finish: no pss tally open");
+    if (ctx->carry_len) return fail(ctx, PSSGPU_EINVAL, "pss_finish: %zu bytes of an unterminated line pending (feed with last=1)", ctx->carry_len);
+    Bind bind(ctx);
+    const size_t half = (size_t)(ctx->cfg.R + 2) * 16 * sizeof(uint64_t);
+    CU(cudaMemcpyAsync(fwd, ctx->d_tables, half, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(rev, (const char *)ctx->d_tables + half, half, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->d2h_bytes += 2 * half;
+    time_collect(ctx);
+    return PSSGPU_OK;
+}
+
+int pssgpu_pss_finish_device(pssgpu_ctx *ctx, void *d_tables)
+{
+    if (!ctx || !d_tables) return fail(ctx, PSSGPU_EINVAL, "pss_finish_device: null argument");
+    if (ctx->mode != kModePss) return fail(ctx, PSSGPU_EINVAL, "pss_finish_device: no pss tally open");
+    if (ctx->carry_len) return fail(ctx, PSSGPU_EINVAL, "pss_finish_device: unterminated line pending");
+    Bind bind(ctx);
+    const size_t bytes = 2 * (size_t)(ctx->cfg.R + 2) * 16 * sizeof(uint64_t);
+    CU(cudaMemcpyAsync(d_tables, ctx->d_tables, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    time_collect(ctx);
+    return PSSGPU_OK;
+}
+
+int pssgpu_get_stats(pssgpu_ctx *ctx, pssgpu_stats *out)
+{
+    if (!ctx || !out) return fail(ctx, PSSGPU_EINVAL, "get_stats: null argument");
+    if (!ctx->d_stats) return fail(ctx, PSSGPU_EINVAL, "get_stats: no tally was opened");
+    Bind bind(ctx);
+    unsigned long long h[kStN];
+    CU(cudaMemcpyAsync(h, ctx->d_stats, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    time_collect(ctx);
+    out->lines = h[kStLines];
+    out->counted = h[kStCounted];
+    out->no_contig = h[kStNoContig];
+    out->filtered = h[kStFiltered];
+    out->parse_fail = h[kStParseFail];
+    out->undefined = h[kStUndefined];
+    return PSSGPU_OK;
+}
+
+// ---- fragkon ------------------------------------------------------------------
+void pssgpu_fragkon_default_params(pssgpu_fragkon_params *p)
+{
+    if (!p) return;
+    p->klen = 8;                 // fragkon.c:14
+    p->min_mq = 0;               // :15
+    p->min_len = 0;              // :16
+    p->max_len = 250000000UL;    // :17
+    p->merged_only = 0;          // :18
+}
+
+int pssgpu_fragkon_begin(pssgpu_ctx *ctx, const pssgpu_fragkon_params *p)
+{
+    if (!ctx || !p) return fail(ctx, PSSGPU_EINVAL, "fragkon_begin: null argument");
+    if (!ctx->have_genome) return fail(ctx, PSSGPU_ENOGENOME, "fragkon_begin: no genome resident");
+    if (p->klen < 1 || p->klen > kMaxFragK)
+        return fail(ctx, PSSGPU_EUNSUPP, "fragkon_begin: klen %d outside [1,%d]", p->klen, kMaxFragK);
+    Bind bind(ctx);
+    TallyCfg c{};
+    c.mode = kModeFragkon;
+    c.K = p->klen;
+    c.min_len = p->min_len;
+    c.max_len = p->max_len;
+    c.min_mq = (uint32_t)p->min_mq;
+    c.merged_only = p->merged_only ? 1u : 0u;
+    int rc;
+    if ((rc = begin_common(ctx)) != PSSGPU_OK) return rc;
+    const size_t elems = 2ull << (2 * c.K);
+    if (elems != ctx->fk_elems) {
+        cudaFree(ctx->d_fk); ctx->d_fk = nullptr; ctx->fk_elems = 0;
+        CU(cudaMalloc(&ctx->d_fk, elems * sizeof(unsigned long long)));
+        ctx->fk_elems = elems;
+    }
+    CU(cudaMemsetAsync(ctx->d_fk, 0, elems * sizeof(unsigned long long), ctx->stream));
+    ctx->cfg = c;
+    ctx->mode = kModeFragkon;
+    return PSSGPU_OK;
+}
+
+int pssgpu_fragkon_finish(pssgpu_ctx *ctx, uint64_t *fp, uint64_t *tp)
+{
+    if (!ctx || !fp || !tp) return fail(ctx, PSSGPU_EINVAL, "fragkon_finish: null argument");
+    if (ctx->mode != kModeFragkon) return fail(ctx, PSSGPU_EINVAL, "fragkon_finish: no fragkon tally open");
+    if (ctx->carry_len) return fail(ctx, PSSGPU_EINVAL, "fragkon_finish: unterminated line pending (feed with last=1)");
+    Bind bind(ctx);
+    const size_t half = (ctx->fk_elems / 2) * sizeof(uint64_t);
+    CU(cudaMemcpyAsync(fp, ctx->d_fk, half, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(tp, (const char *)ctx->d_fk + half, half, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->d2h_bytes += 2 * half;
+    time_collect(ctx);
+    return PSSGPU_OK;
+}
+
+int pssgpu_fragkon_finish_device(pssgpu_ctx *ctx, void *d_out)
+{
+    if (!ctx || !d_out) return fail(ctx, PSSGPU_EINVAL, "fragkon_finish_device: null argument");
+    if (ctx->mode != kModeFragkon) return fail(ctx, PSSGPU_EINVAL, "fragkon_finish_device: no fragkon tally open");
+    if (ctx->carry_len) return fail(ctx, PSSGPU_EINVAL, "fragkon_finish_device: unterminated line pending");
+    Bind bind(ctx);
+    CU(cudaMemcpyAsync(d_out, ctx->d_fk, ctx->fk_elems * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    time_collect(ctx);
+    return PSSGPU_OK;
+}
+
+// ---- genome-kmer-count ----------------------------------------------------------
+int pssgpu_kmer_spectrum_shard_device(pssgpu_ctx *ctx, int k, int shard, int n_shards, void *d_counts)
+{
+    if (!ctx || !d_counts) return fail(ctx, PSSGPU_EINVAL, "kmer_spectrum: null argument");
+    if (!ctx->have_genome) return fail(ctx, PSSGPU_ENOGENOME, "kmer_spectrum: no genome resident");
+    if (k < 1 || k > kMaxFragK) return fail(ctx, PSSGPU_EUNSUPP, "kmer_spectrum: k %d outside [1,%d]", k, kMaxFragK);
+    if (n_shards < 1 || shard < 0 || shard >= n_shards) return fail(ctx, PSSGPU_EINVAL, "kmer_spectrum: shard %d of %d", shard, n_shards);
+    Bind bind(ctx);
+    const size_t bins = 1ull << (2 * k);
+    CU(cudaMemsetAsync(d_counts, 0, bins * sizeof(uint64_t), ctx->stream));
+    // k-mers are attributed to the group holding their first base; the last
+    // two groups are slack/padding and start no k-mer
+    const uint64_t usable = ctx->n_groups - 2;
+    const uint64_t g0 = usable * (uint64_t)shard / (uint64_t)n_shards;
+    const uint64_t g1 = usable * (uint64_t)(shard + 1) / (uint64_t)n_shards;
+    if (g1 > g0) {
+        const unsigned grid = (unsigned)std::min<uint64_t>((g1 - g0 + 255) / 256, (uint64_t)ctx->sm_count * 8);
+        time_begin(ctx, (g1 - g0) * sizeof(uint64_t));
+        if (k <= kSpectrumSmemK)
+            spectrum_kernel<true><<<grid, 256, 0, ctx->stream>>>(ctx->d_groups, g0, g1, k, (unsigned long long *)d_counts);
+        else
+            spectrum_kernel<false><<<grid, 256, 0, ctx->stream>>>(ctx->d_groups, g0, g1, k, (unsigned long long *)d_counts);
+        time_end(ctx);
+        CU(cudaGetLastError());
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    time_collect(ctx);
+    return PSSGPU_OK;
+}
+
+int pssgpu_kmer_spectrum_shard(pssgpu_ctx *ctx, int k, int shard, int n_shards, uint64_t *counts)
+{
+    if (!ctx || !counts) return fail(ctx, PSSGPU_EINVAL, "kmer_spectrum: null argument");
+    if (k < 1 || k > kMaxFragK) return fail(ctx, PSSGPU_EUNSUPP, "kmer_spectrum: k %d outside [1,%d]", k, kMaxFragK);
+    Bind bind(ctx);
+    const size_t bins = 1ull << (2 * k);
+    void *d = nullptr;
+    CU(cudaMalloc(&d, bins * sizeof(uint64_t)));
+    int rc = pssgpu_kmer_spectrum_shard_device(ctx, k, shard, n_shards, d);
+    if (rc == PSSGPU_OK) {
+        cudaError_t e = cudaMemcpy(counts, d, bins * sizeof(uint64_t), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(ctx, PSSGPU_ECUDA, "kmer_spectrum: D2H: %s", cudaGetErrorString(e));
+        else ctx->d2h_bytes += bins * sizeof(uint64_t);
+    }
+    cudaFree(d);
+    return rc;
+}
+
+int pssgpu_kmer_spectrum(pssgpu_ctx *ctx, int k, uint64_t *counts) { return pssgpu_kmer_spectrum_shard(ctx, k, 0, 1, counts); }
+
+// ---- measurement hooks ------------------------------------------------------------
+int pssgpu_timing_reset(pssgpu_ctx *ctx, int enable)
+{
+    if (!ctx) return PSSGPU_EINVAL;
+    Bind bind(ctx);
+    CU(cudaStreamSynchronize(ctx->stream));
+    time_collect(ctx);
+    ctx->timing = enable != 0;
+    ctx->launches = ctx->bytes_scanned = ctx->h2d_bytes = ctx->d2h_bytes = 0;
+    ctx->kernel_ms = 0.0;
+    return PSSGPU_OK;
+}
+
+int pssgpu_timing_get(pssgpu_ctx *ctx, pssgpu_timing *out)
+{
+    if (!ctx || !out) return PSSGPU_EINVAL;
+    Bind bind(ctx);
+    CU(cudaStreamSynchronize(ctx->stream));
+    time_collect(ctx);
+    out->launches = ctx->launches;
+    out->kernel_ms = ctx->kernel_ms;
+    out->bytes_scanned = ctx->bytes_scanned;
+    out->h2d_bytes = ctx->h2d_bytes;
+    out->d2h_bytes = ctx->d2h_bytes;
+    return PSSGPU_OK;
+}
+
+// ---- test hook -------------------------------------------------------------------------
+int pssgpu_debug_status(pssgpu_ctx *ctx, int enable)
+{
+    if (!ctx) return PSSGPU_EINVAL;
+    Bind bind(ctx);
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (enable && !ctx->d_dbg_n) {
+        ctx->dbg_cap = 8ull << 20;
+        CU(cudaMalloc(&ctx->d_dbg_off, ctx->dbg_cap * sizeof(uint64_t)));
+        CU(cudaMalloc(&ctx->d_dbg_code, ctx->dbg_cap));
+        CU(cudaMalloc(&ctx->d_dbg_n, sizeof(unsigned long long)));
+        CU(cudaMemset(ctx->d_dbg_n, 0, sizeof(unsigned long long)));
+    }
+    ctx->dbg = enable != 0;
+    return PSSGPU_OK;
+}
+
+int pssgpu_debug_fetch(pssgpu_ctx *ctx, uint64_t *offsets, int8_t *codes, uint64_t cap, uint64_t *n)
+{
+    if (!ctx || !n) return PSSGPU_EINVAL;
+    *n = 0;
+    if (!ctx->d_dbg_n) return PSSGPU_OK;
+    Bind bind(ctx);
+    CU(cudaStreamSynchronize(ctx->stream));
+    unsigned long long have = 0;
+    CU(cudaMemcpy(&have, ctx->d_dbg_n, sizeof have, cudaMemcpyDeviceToHost));
+    if (have > ctx->dbg_cap) have = ctx->dbg_cap;
+    const uint64_t take = std::min<uint64_t>(have, cap);
+    if (take && offsets) CU(cudaMemcpy(offsets, ctx->d_dbg_off, take * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (take && codes) CU(cudaMemcpy(codes, ctx->d_dbg_code, take, cudaMemcpyDeviceToHost));
+    *n = take;
+    return PSSGPU_OK;
+}
+
+}  // extern "C"

@@ -421,3 +421,94 @@ def parse_counts_file(text: bytes, R: int):
 
 def tmpdir():
     return tempfile.mkdtemp(prefix="psstest_")
+
+
+# --------------------------------------------------------------------------- host build of the device record logic
+EMUL_SO = os.path.join(ROOT, "tests", "host_emul", "libpssemul.so")
+
+
+def build_emul(force=False):
+    src = os.path.join(ROOT, "tests", "host_emul", "pss_emul.cpp")
+    hdr = os.path.join(ROOT, "pss-bam_b200", "csrc", "pss_record.h")
+    newest = max(os.path.getmtime(src), os.path.getmtime(hdr))
+    if force or not os.path.exists(EMUL_SO) or os.path.getmtime(EMUL_SO) < newest:
+        _run(["g++", "-O2", "-g", "-std=c++17", "-Wno-unknown-pragmas", "-fPIC", "-shared", "-o", EMUL_SO, src])
+    return EMUL_SO
+
+
+class Emul:
+    """pss_record.h compiled for the host (a TEST of the device logic, never a product path)."""
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            build_emul()
+            lib = C.CDLL(EMUL_SO)
+            lib.emul_genome_new.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.c_uint32]
+            lib.emul_genome_new.restype = C.c_void_p
+            lib.emul_genome_free.argtypes = [C.c_void_p]
+            lib.emul_scan11.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
+                                        C.POINTER(C.c_uint32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+            lib.emul_tally.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_uint64, C.c_uint64,
+                                       C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                       C.POINTER(C.c_uint64)]
+            lib.emul_tally.restype = C.c_uint64
+            lib.emul_spectrum.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+            cls._lib = lib
+        return cls._lib
+
+    def __init__(self, contigs):
+        """contigs: list of (id str/bytes, seq bytes) -- e.g. Oracle.contigs()."""
+        lib = self.lib()
+        n = len(contigs)
+        self._ids = [c[0].encode("latin1") if isinstance(c[0], str) else c[0] for c in contigs]
+        self._seqs = [bytes(c[1]) for c in contigs]
+        ids = (C.c_char_p * n)(*self._ids)
+        seqs = (C.c_char_p * n)(*self._seqs)
+        lens = (C.c_uint64 * n)(*[len(s) for s in self._seqs])
+        self.g = lib.emul_genome_new(ids, seqs, lens, n)
+
+    def close(self):
+        if self.g:
+            self.lib().emul_genome_free(self.g)
+            self.g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _tally(self, sam, mode, R, min_len, max_len, min_mq, up, down, merged_only, K, force_slow):
+        lib = self.lib()
+        fwd = np.zeros((R + 2, 16), dtype=np.uint64)
+        rev = np.zeros((R + 2, 16), dtype=np.uint64)
+        nb = 1 << (2 * K) if K else 1
+        fp = np.zeros(nb, dtype=np.uint64)
+        tp = np.zeros(nb, dtype=np.uint64)
+        ptr, n, keep = _as_ptr(sam)
+        cap = _count_lines(sam) + 8
+        status = np.full(cap, 99, dtype=np.int8)
+        fast = C.c_uint64(0)
+        nl = lib.emul_tally(self.g, ptr, n, mode, R, min_len, max_len, min_mq, up, down, merged_only, K, force_slow,
+                            fwd.ctypes.data, rev.ctypes.data, fp.ctypes.data, tp.ctypes.data,
+                            status.ctypes.data, cap, C.byref(fast))
+        del keep
+        return fwd, rev, fp, tp, status[:nl], int(fast.value)
+
+    def pss(self, sam, p: PssParams = PssParams(), force_slow=0):
+        fwd, rev, _, _, st, fast = self._tally(sam, 0, p.region_len, p.min_len, p.max_len, p.min_mq,
+                                               p.up_ctx, p.down_ctx, p.merged_only, 0, force_slow)
+        return fwd, rev, st, fast
+
+    def fragkon(self, sam, p: FkParams = FkParams(), force_slow=0):
+        _, _, fp, tp, st, fast = self._tally(sam, 1, 0, p.min_len, p.max_len, p.min_mq, b"ACGT", b"ACGT",
+                                             p.merged_only, p.klen, force_slow)
+        return fp, tp, st, fast
+
+    def kmer_spectrum(self, k):
+        counts = np.zeros(1 << (2 * k), dtype=np.uint64)
+        self.lib().emul_spectrum(self.g, k, counts.ctypes.data)
+        return counts
