@@ -1,0 +1,381 @@
+#!/usr/bin/env python3
+"""bench.py -- pss-bam PSS tally throughput on B200 (contract: one JSON line on stdout from rank 0).
+
+Workload (BASELINE.json configs[1]): synthetic 3.1 Gb human-scale genome (24 contigs, ~1 % N runs, soft-masked
+stretches) + 200 M variable-length (30-150 bp) reads with indel / soft-clip CIGARs, filtered flags, paired records,
+QUAL '*', unknown contigs and MD/NM tags, read-sharded over 8 GPUs: every GPU holds a full packed genome replica and
+tallies its 25 M-read shard (weak scaling: the per-GPU shard is fixed, N GPUs process N x 25 M reads).
+
+A step = one pass of the hot path over the rank's shard:
+    pssgpu_pss_begin -> pssgpu_feed_device (SAM text resident in HBM) -> pssgpu_pss_finish_device
+    [-> NCCL all-reduce of the 2x17x16 u64 count tables when N > 1] -> tables to the host.
+`value` = reads of all ranks / max-over-ranks device time (CUDA events on the library's stream).
+`e2e`   = same metric through the C ABI with HOST (pinned) SAM text: pssgpu_feed copies it to the device inside the
+          timed region, tables come back to the host.
+`roofline` = algorithmic bytes of the tally kernel / its CUDA-event duration, against the measured HBM copy peak.
+`cpu_baseline` = the unmodified reference binary (oracle/_ref/pss-bam, stock -O0 flags) on a bounded sample.
+
+    python bench.py                      # 1 GPU
+    torchrun --nproc-per-node 8 bench.py --gpus 8
+    python bench.py --impl reference     # the reference's CPU path on this box's host cores
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+HUMAN_CONTIGS = [  # hs37-like lengths, 3.096 Gb in total, every contig < 536 870 911 (fasta-genome-io.h:9)
+    ("chr1", 249250621), ("chr2", 243199373), ("chr3", 198022430), ("chr4", 191154276), ("chr5", 180915260),
+    ("chr6", 171115067), ("chr7", 159138663), ("chr8", 146364022), ("chr9", 141213431), ("chr10", 135534747),
+    ("chr11", 135006516), ("chr12", 133851895), ("chr13", 115169878), ("chr14", 107349540), ("chr15", 102531392),
+    ("chr16", 90354753), ("chr17", 81195210), ("chr18", 78077248), ("chr19", 59128983), ("chr20", 63025520),
+    ("chr21", 48129895), ("chr22", 51304566), ("chrX", 155270560), ("chrY", 59373566),
+]
+GENOME_SEED = 31
+READS_SEED = 2002
+METRIC = "aligned reads/s (PSS tally)"
+UNIT = "reads/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--reads-per-gpu", type=int, default=25_000_000, help="200 M reads / 8 GPUs")
+    ap.add_argument("--genome-scale", type=float, default=1.0, help="shrink the 3.1 Gb genome (developer runs only)")
+    ap.add_argument("--cpu-sample-reads", type=int, default=1_500_000)
+    ap.add_argument("--cpu-genome-mb", type=int, default=100)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def contig_plan(scale):
+    return [(n, max(1000, int(l * scale))) for n, l in HUMAN_CONTIGS]
+
+
+def workload_name(a):
+    s = "configs[1] shard: 3.1 Gb synthetic genome replica + %d of the 200 M variable-length (30-150 bp) reads " \
+        "(200 M / 8 GPUs, read-sharded)" % a.reads_per_gpu
+    if a.genome_scale != 1.0:
+        s += " [genome scaled x%g]" % a.genome_scale
+    return s
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return None
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            return None
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def ref_paths():
+    d = os.path.join(ROOT, "oracle", "_ref")
+    return d, os.path.join(d, "pss-bam"), os.path.join(d, "samtools")
+
+
+def run_reference_sample(n_proc, reads_per_proc, genome_mb, seed, repeats=1):
+    """Time the unmodified reference binary on `n_proc` shards in parallel (one single-threaded process each; the
+    reference has no threads).  Returns (reads_per_s, tally_seconds, load_seconds)."""
+    from pss_testlib import Synth, reads_cfg_config2
+    d, exe, shim = ref_paths()
+    if not (os.path.exists(exe) and os.path.exists(shim)):
+        raise FileNotFoundError("oracle/_ref/pss-bam not built (make -C oracle ref needs /root/reference)")
+    nc = 4
+    g = Synth.genome(GENOME_SEED + 1, [genome_mb * 1_000_000 // nc] * nc, n_frac=0.01, lower_frac=0.03)
+    work = tempfile.mkdtemp(prefix="pssbench_ref_")
+    try:
+        with open(os.path.join(work, "genome.fa"), "wb") as f:
+            f.write(g.fasta_bytes())
+        cfg = reads_cfg_config2(seed=seed)
+        for p in range(n_proc):
+            with open(os.path.join(work, f"shard{p}.sam"), "wb") as f:
+                f.write(Synth.sam(cfg, g, p * reads_per_proc, (p + 1) * reads_per_proc))
+        open(os.path.join(work, "empty.sam"), "wb").close()
+        env = dict(os.environ)
+        env["PATH"] = d + os.pathsep + env.get("PATH", "")
+
+        def run(sams):
+            t0 = time.perf_counter()
+            ps = [subprocess.Popen([exe, "-F", "genome.fa", "-B", s, "-o", f"out{i}"], cwd=work, env=env,
+                                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for i, s in enumerate(sams)]
+            for p in ps:
+                if p.wait() != 0:
+                    raise RuntimeError("reference pss-bam failed")
+            return time.perf_counter() - t0
+
+        load = run(["empty.sam"] * n_proc)                       # FASTA load only (fgetc loop), same concurrency
+        times = [run([f"shard{p}.sam" for p in range(n_proc)]) for _ in range(repeats)]
+        total = min(times)
+        tally = max(total - load, 1e-9)
+        return n_proc * reads_per_proc / tally, tally, load, times
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
+def main_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per = max(50_000, a.cpu_sample_reads // 4)
+    line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "higher_is_better": True, "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic", "config": {"workload": workload_name(a)}, "gpu_launches": 0}
+    try:
+        vals, secs = [], []
+        for it in range(a.warmup + a.steps):
+            v, tally, load, _ = run_reference_sample(cores, per, a.cpu_genome_mb, READS_SEED + it)
+            if it >= a.warmup:
+                vals.append(v)
+                secs.append(tally)
+        value = statistics.mean(vals)
+        sample = (f"unmodified reference oracle/_ref/pss-bam (stock Makefile flags -gdwarf-2 -g, no -O), {cores} "
+                  f"single-threaded processes in parallel, {per} config-2 reads each on a {a.cpu_genome_mb} Mb 4-contig "
+                  f"genome; FASTA load time (same concurrency, empty SAM) subtracted")
+        line.update({"value": value, "ms_per_step": 1e3 * statistics.mean(secs),
+                     "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+                     "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    except Exception as ex:  # the oracle port is the fallback named by the contract
+        line.update({"unavailable": f"{type(ex).__name__}: {ex}"})
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- B200 arm
+def main_b200(a):
+    import torch
+    import torch.distributed as dist
+    from pss_testlib import Synth, reads_cfg_config2
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus:
+        if world == 1 and a.gpus > 1:
+            raise SystemExit("launch with: python -m torch.distributed.run --nproc-per-node %d bench.py --gpus %d" % (a.gpus, a.gpus))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(max(1, cores // max(1, world)))
+
+    pkg = importlib.import_module("pss-bam_b200")
+    ctx = pkg.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.cuda_stream, device=torch.device("cuda", local))
+
+    # ---- synthetic inputs (seeded; every rank builds the same genome and its own read shard)
+    plan = contig_plan(a.genome_scale)
+    t0 = time.perf_counter()
+    g = Synth.genome(GENOME_SEED, [l for _, l in plan], names=[n for n, _ in plan], n_frac=0.01, lower_frac=0.03)
+    ctx.upload_genome(list(zip(g.names, g.seqs)))
+    ginfo = ctx.genome_info()
+    t_genome = time.perf_counter() - t0
+    cfg = reads_cfg_config2(seed=READS_SEED)
+    n_reads = a.reads_per_gpu
+    lo, hi = rank * n_reads, (rank + 1) * n_reads
+    cap = Synth.sam_bound(cfg, lo, hi)
+    host = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+    n_bytes = Synth.sam_into(cfg, g, lo, hi, host.data_ptr(), cap)
+    dev = torch.empty(n_bytes + 64, dtype=torch.uint8, device="cuda")
+    dev[:n_bytes].copy_(host[:n_bytes])
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t0
+    del g.seqs[:]
+
+    R = 15
+    opts = pkg.PssOptions()
+    tables = torch.zeros(2 * (R + 2) * 16, dtype=torch.int64, device="cuda")
+    tables_host = torch.zeros(2 * (R + 2) * 16, dtype=torch.int64).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        ctx.pss_begin(opts)
+        ctx.feed_device(dev.data_ptr(), n_bytes)
+        ctx.pss_finish_device(tables.data_ptr())          # waits for the tally
+        if world > 1:
+            dist.all_reduce(tables)                        # NCCL sum of the count tables over NVLink
+        tables_host.copy_(tables)
+        torch.cuda.synchronize()
+
+    def step_e2e():
+        ctx.pss_begin(opts)
+        ctx.feed_ptr(host.data_ptr(), n_bytes, last=True)  # H2D staging + tally launches, pipelined per 64 MiB
+        ctx.pss_finish_device(tables.data_ptr())
+        if world > 1:
+            dist.all_reduce(tables)
+        tables_host.copy_(tables)
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        w0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - w0
+        ms = max(e0.elapsed_time(e1), 0.0)
+        # the steps also run host-side calls and (N>1) NCCL on torch's stream: take the larger of device and wall time
+        t = torch.tensor([max(ms, wall * 1e3)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(a.warmup):
+        step_resident()
+    ctx.timing_reset(True)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_total = timed(step_resident, a.steps)
+    clocks = sampler.stop() if sampler else None
+    tm = ctx.timing()
+    stats = ctx.stats()
+    ctx.timing_reset(False)
+    check_tables = tables_host.clone()
+
+    e2e = None
+    if not a.no_e2e:
+        e2e_steps = max(1, min(a.steps, 5))
+        step_e2e()
+        ctx.timing_reset(False)
+        ms_e2e = timed(step_e2e, e2e_steps)
+        assert torch.equal(tables_host, check_tables), "host-fed and device-resident tallies differ"
+        tm2 = ctx.timing()
+        e2e = {"value": world * n_reads * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(n_bytes), "d2h_bytes_per_step": int(tables_host.numel() * 8),
+               "ms_per_step": ms_e2e / e2e_steps, "sam_gb_per_s": n_bytes * world * e2e_steps / (ms_e2e * 1e-3) / 1e9,
+               "launches_per_step": int(tm2["launches"] // e2e_steps) if tm2["launches"] else None}
+
+    # ---- gather totals
+    tot = torch.tensor([float(n_bytes), float(stats["counted"]), float(stats["lines"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tot)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    total_bytes, total_counted, total_lines = (float(x) for x in tot.tolist())
+    # with N > 1 the all-reduced tables hold every rank's reads
+    fwd = check_tables[: (R + 2) * 16].view(R + 2, 16)
+    assert int(fwd[1].sum()) <= int(total_counted) * a.steps + 1
+
+    value = world * n_reads * a.steps / (ms_total * 1e-3)
+    launches = int(tm["launches"])
+    kern_ms = tm["kernel_ms"] / max(1, launches)
+    alg_bytes = n_bytes + stats["counted"] * 9          # record bytes + accepted x ceil(2*(R+2)*2 bit / 8)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "tally_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            if tj.get("sam_bytes") == int(n_bytes):
+                traffic = tj.get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic",
+        "config": {"workload": workload_name(a), "reads_per_gpu": n_reads, "sam_bytes_per_gpu": int(n_bytes),
+                   "bytes_per_read": n_bytes / n_reads, "genome_bases": ginfo["n_bases"], "genome_hbm_bytes": ginfo["hbm_bytes"],
+                   "region_len": R, "l2": "input (%.1f GB/GPU) larger than L2, no flush needed" % (n_bytes / 1e9),
+                   "seeds": {"genome": GENOME_SEED, "reads": READS_SEED},
+                   "accepted_fraction": total_counted / max(1.0, total_lines),
+                   "setup_s": {"genome_synth_upload_pack": t_genome, "total": t_setup}},
+        "sam_gb_per_s": total_bytes * a.steps / (ms_total * 1e-3) / 1e9,
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": "tally_kernel<pss>", "kernel_ms": kern_ms,
+                     "algorithmic_bytes_per_launch": int(alg_bytes), "peak_source": peak_src},
+        "clocks": clocks,
+        "e2e": e2e,
+    }
+    if not a.no_cpu_baseline:
+        try:
+            v, tally, load, _ = run_reference_sample(1, a.cpu_sample_reads, a.cpu_genome_mb, READS_SEED)
+            line["cpu_baseline"] = {
+                "value": v, "unit": UNIT, "cores": 1, "kind": "reference",
+                "sample": (f"unmodified reference oracle/_ref/pss-bam (stock flags -gdwarf-2 -g, no -O; single-threaded), "
+                           f"{a.cpu_sample_reads} config-2 reads on a {a.cpu_genome_mb} Mb 4-contig genome, "
+                           f"{tally:.1f} s tally after subtracting {load:.1f} s FASTA load"),
+                "host_cores_available": cores}
+        except Exception as ex:
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference",
+                                    "sample": f"unavailable: {type(ex).__name__}: {ex}"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse_args()
+    if args.impl == "reference":
+        main_reference(args)
+    else:
+        main_b200(args)

@@ -12,7 +12,8 @@
  * index), is checked against something that is structurally close to the
  * reference rather than to itself.
  */
-#define _GNU_SOURCE
+/* no _GNU_SOURCE: with it glibc >= 2.38 routes sscanf to __isoc23_sscanf, whose %i also accepts "0b..." --
+ * the reference (sam-parse.c, no feature macros, -std=gnu17) does not get that variant. */
 #include "oracle_pss.h"
 
 #include <ctype.h>

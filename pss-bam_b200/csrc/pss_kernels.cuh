@@ -159,21 +159,34 @@ constexpr int kPrefix     = 16;                               // bytes before th
 constexpr int kTileSpan   = kPrefix + kTileMain + kTileOver;  // 34832 staged bytes
 constexpr int kThreads    = 256;
 constexpr int kWarps      = kThreads / 32;
-constexpr int kPieces     = ((kTileSpan / 16 + 31) / 32) * 32;    // 16-byte pieces, padded to whole warps (2208)
-constexpr int kWords      = kPieces / 2;                      // 32-bit mask words (1104)
+constexpr int kWords      = (kTileSpan + 31) / 32;                // 32-byte chunks = mask words (1089)
 constexpr int kWordsPerThread = (kWords + kThreads - 1) / kThreads;   // 5
 constexpr int kRecCap     = 1024;                             // records materialised per pass
+constexpr int kCacheContigs = 64;                             // contig table kept in shared memory when it fits
+constexpr int kCacheNames   = 1024;
+constexpr int kCacheSlots   = 128;
+constexpr int kFlushEvery   = 1900;                           // warp iterations between flushes of the 16-bit partial sums
+
+struct ContigCache {
+    uint32_t n;                                               // 0: not cached, use the global table
+    uint32_t hash[kCacheContigs];
+    uint16_t name_off[kCacheContigs], name_len[kCacheContigs];
+    uint64_t base_off[kCacheContigs], len[kCacheContigs];
+    uint8_t  slot[kCacheSlots];                               // open addressing, 0xff = empty
+    char     names[kCacheNames];
+};
 
 struct TallySmem {
-    alignas(128) uint8_t bytes[kPieces * 16];                 // staged SAM text
+    alignas(128) uint8_t bytes[kWords * 32];                  // staged SAM text
     uint32_t le[kWords + 8];                                  // bit i of word w: byte 32w+i is <= 0x20
     uint32_t nl[kWords + 8];                                  //                  byte 32w+i is '\n'
     uint16_t wpre[kWords + 8];                                // newlines before word w
-    uint16_t nlpos[kRecCap + 8];                              // newline positions of this pass
+    uint16_t nlpos[kRecCap + 4];                              // newline positions of this pass
     uint32_t table[2 * 32 * 16];                              // CTA count tables [fwd|rev][row][cell]
     uint32_t stats[8];
     uint32_t warp_sum[kWarps];
     uint32_t n_newlines;
+    ContigCache cc;
     alignas(8) uint64_t bar;
 };
 
@@ -183,6 +196,7 @@ struct TallyArgs {
     uint64_t       stream_off;   // offset of sam[0] within everything fed (debug log only)
     DevGenome      g;
     TallyCfg       cfg;
+    uint32_t       names_bytes;  // total bytes of contig names
     unsigned long long *pss_tables;   // 2*(R+2)*16 u64: fwd then rev
     unsigned long long *fk_hist;      // 2*4^K u64: 5' then 3'
     unsigned long long *stats;        // kStN
@@ -192,28 +206,40 @@ struct TallyArgs {
     uint64_t            dbg_cap;
 };
 
-struct SmemAt {
+struct SmemAt {                  // absolute positions in the staged tile (4-byte aligned base)
     const uint8_t *p;
     __device__ __forceinline__ uint32_t operator()(int i) const { return p[i]; }
+    __device__ __forceinline__ uint32_t word(int i) const { return *reinterpret_cast<const uint32_t *>(p + i); }
+};
+struct SmemRel {                 // positions relative to a record start (any alignment)
+    const uint8_t *p;
+    __device__ __forceinline__ uint32_t operator()(int i) const { return p[i]; }
+    __device__ __forceinline__ uint32_t word(int i) const
+    {
+        return (uint32_t)p[i] | ((uint32_t)p[i + 1] << 8) | ((uint32_t)p[i + 2] << 16) | ((uint32_t)p[i + 3] << 24);
+    }
 };
 struct GlobalAt {
     const uint8_t *p;
     __device__ __forceinline__ uint32_t operator()(int i) const { return __ldg(p + i); }
+    __device__ __forceinline__ uint32_t word(int i) const
+    {
+        return (uint32_t)__ldg(p + i) | ((uint32_t)__ldg(p + i + 1) << 8) | ((uint32_t)__ldg(p + i + 2) << 16) |
+               ((uint32_t)__ldg(p + i + 3) << 24);
+    }
 };
 
-// 0x80 in every byte of w that is <= 0x20
-__device__ __forceinline__ uint32_t le20_flags(uint32_t w)
+// 0x80 in every byte of w that is <= 0x20 / that is '\n'
+__device__ __forceinline__ void classify4(uint32_t w, uint32_t &zle, uint32_t &znl)
 {
-    return ~(((w & 0x7f7f7f7fu) + 0x5f5f5f5fu) | w) & 0x80808080u;
+    zle = ~(((w & 0x7f7f7f7fu) + 0x5f5f5f5fu) | w) & 0x80808080u;
+    const uint32_t y = w ^ 0x0a0a0a0au;
+    znl = ~(((y & 0x7f7f7f7fu) + 0x7f7f7f7fu) | y) & 0x80808080u;
 }
-// 16 flag bytes (0x80 / 0) in four words -> 16-bit mask, via four byte dot products
-__device__ __forceinline__ uint32_t gather16(uint32_t z0, uint32_t z1, uint32_t z2, uint32_t z3)
+// 8 flag bytes (0x80 / 0) in two words -> 8-bit mask << 7, via two byte dot products
+__device__ __forceinline__ uint32_t gather8(uint32_t z0, uint32_t z1)
 {
-    uint32_t a = __dp4a(z0, 0x08040201u, 0u);
-    a = __dp4a(z1, 0x80402010u, a);
-    uint32_t b = __dp4a(z2, 0x08040201u, 0u);
-    b = __dp4a(z3, 0x80402010u, b);
-    return (a >> 7) | (b << 1);
+    return __dp4a(z1, 0x80402010u, __dp4a(z0, 0x08040201u, 0u));
 }
 
 __device__ __forceinline__ void log_outcome(const TallyArgs &A, uint64_t goff, int code)
@@ -232,13 +258,49 @@ __device__ __forceinline__ int stat_slot(int code)
          : code == kParseFail ? kStParseFail : kStUndefined;
 }
 
+// find_seq (fasta-genome-io.c:202-213) against the shared-memory copy of the contig table
+template <class B>
+__device__ __forceinline__ int cache_find(const ContigCache &C, const B &b, int off, int len, uint64_t &base, uint64_t &clen)
+{
+    uint32_t h = kNameHashSeed;
+    for (int i = 0; i < len; i++) h = name_hash_step(h, (uint8_t)b(off + i));
+    uint32_t s = h & (kCacheSlots - 1);
+    int      found = -1;
+    for (;;) {
+        const uint32_t v = C.slot[s];
+        if (v == 0xffu) break;
+        if (C.hash[v] == h && (int)C.name_len[v] == len) {
+            const char *nm = C.names + C.name_off[v];
+            int i = 0;
+            while (i < len && (uint8_t)nm[i] == (uint8_t)b(off + i)) i++;
+            if (i == len) { found = (int)v; break; }
+        }
+        s = (s + 1) & (kCacheSlots - 1);
+    }
+    base = found >= 0 ? C.base_off[found] : 0;
+    clen = found >= 0 ? C.len[found] : 0;
+    return found;
+}
+template <class B>
+__device__ __forceinline__ int lookup_contig(const ContigCache &C, const DevGenome &g, const B &b, int off, int len,
+                                             uint64_t &base, uint64_t &clen)
+{
+    if (C.n) return cache_find(C, b, off, len, base, clen);
+    const int ci = find_contig(g, b, off, len);
+    base = ci >= 0 ? g.contigs[ci].base_off : 0;
+    clen = ci >= 0 ? g.contigs[ci].len : 0;
+    return ci;
+}
+
 // A record the tile could not hold (longer than the look-ahead, or longer than
 // fgets' 200000-byte buffer): walked from global memory by one thread, split
 // the way fgets(buf, MAX_LINE_LEN+1) splits it (pss-bam.c:761-764), counted
 // with shared-memory atomics.  Rare by construction.
 template <int MODE>
-__device__ __noinline__ void long_record(const TallyArgs &A, TallySmem &S, uint64_t gstart)
+__device__ __noinline__ void long_record(const TallyArgs *Ap, TallySmem *Sp, uint64_t gstart)
 {
+    const TallyArgs &A = *Ap;
+    TallySmem       &S = *Sp;
     uint64_t p = gstart;
     while (p < A.len && __ldg(A.sam + p) != '\n') p++;
     uint64_t total = p - gstart + (p < A.len ? 1u : 0u);
@@ -249,9 +311,11 @@ __device__ __noinline__ void long_record(const TallyArgs &A, TallySmem &S, uint6
         RecView r;
         int code = scan11(at, L, r);
         if (code == kCounted) {
+            uint64_t  cb, cl;
+            const int ci = lookup_contig(S.cc, A.g, at, r.rname_off, r.rname_len, cb, cl);
             if (MODE == kModePss) {
                 PssStreams st;
-                code = pss_record(at, r, A.g, A.cfg, st);
+                code = pss_record(at, r, ci, cb, cl, A.g, A.cfg, st);
                 if (code == kCounted) {
                     const int rows = A.cfg.R + 2;
                     for (int j = 0; j < rows; j++) {
@@ -263,7 +327,7 @@ __device__ __noinline__ void long_record(const TallyArgs &A, TallySmem &S, uint6
                 }
             } else {
                 FkHits h;
-                code = fk_record(at, r, A.g, A.cfg, h);
+                code = fk_record(at, r, ci, cb, cl, A.g, A.cfg, h);
                 if (h.add5) atomicAdd(A.fk_hist + h.idx5, 1ull);
                 if (h.add3) atomicAdd(A.fk_hist + (1ull << (2 * A.cfg.K)) + h.idx3, 1ull);
             }
@@ -276,38 +340,61 @@ __device__ __noinline__ void long_record(const TallyArgs &A, TallySmem &S, uint6
     }
 }
 
+// ballot of "(word & mask) != 0" over the full warp: one LOP3-with-predicate + one VOTE
+__device__ __forceinline__ uint32_t ballot_bits(uint32_t word, uint32_t mask)
+{
+    uint32_t r;
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %1, %2;\n\tsetp.ne.u32 p, t, 0;\n\t"
+                 "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t}" : "=r"(r) : "r"(word), "r"(mask));
+    return r;
+}
+
 // The two count tables of one warp-load of records, without atomics: lane l
 // owns cell (l & 15) of table (l >> 4); five ballots per table and row turn
 // "which lanes hit my cell" into a popcount.  acc[] packs two rows per
-// register (16-bit partial sums, flushed once per tile).
+// register (16-bit partial sums).  All 32 lanes must be converged.
 __device__ __forceinline__ void tally_rows(const PssStreams &st, uint32_t (&acc)[16], int rows, uint32_t lane)
 {
     const bool     tb = lane >= 16;
     const uint32_t cell = lane & 15u;
     const uint32_t x0 = (cell & 1u) ? 0u : ~0u, x1 = (cell & 2u) ? 0u : ~0u;
     const uint32_t x2 = (cell & 4u) ? 0u : ~0u, x3 = (cell & 8u) ? 0u : ~0u;
-    const uint32_t full = 0xffffffffu;
+    // "row adds nothing" flags become "row counts" flags so that every ballot is a != 0 test
+    const uint32_t ar[2] = { (uint32_t)st.a_ref, (uint32_t)(st.a_ref >> 32) }, aq[2] = { (uint32_t)st.a_read, (uint32_t)(st.a_read >> 32) };
+    const uint32_t ag[2] = { ~(uint32_t)st.a_bad, ~(uint32_t)(st.a_bad >> 32) };
+    const uint32_t br[2] = { (uint32_t)st.b_ref, (uint32_t)(st.b_ref >> 32) }, bq[2] = { (uint32_t)st.b_read, (uint32_t)(st.b_read >> 32) };
+    const uint32_t bg[2] = { ~(uint32_t)st.b_bad, ~(uint32_t)(st.b_bad >> 32) };
 #pragma unroll
     for (int j = 0; j < 32; j++) {
         if (j >= rows) break;
-        const uint32_t a0 = __ballot_sync(full, (st.a_ref >> (2 * j)) & 1u);
-        const uint32_t a1 = __ballot_sync(full, (st.a_ref >> (2 * j + 1)) & 1u);
-        const uint32_t a2 = __ballot_sync(full, (st.a_read >> (2 * j)) & 1u);
-        const uint32_t a3 = __ballot_sync(full, (st.a_read >> (2 * j + 1)) & 1u);
-        const uint32_t av = __ballot_sync(full, !((st.a_bad >> (2 * j)) & 1u));
-        const uint32_t b0 = __ballot_sync(full, (st.b_ref >> (2 * j)) & 1u);
-        const uint32_t b1 = __ballot_sync(full, (st.b_ref >> (2 * j + 1)) & 1u);
-        const uint32_t b2 = __ballot_sync(full, (st.b_read >> (2 * j)) & 1u);
-        const uint32_t b3 = __ballot_sync(full, (st.b_read >> (2 * j + 1)) & 1u);
-        const uint32_t bv = __ballot_sync(full, !((st.b_bad >> (2 * j)) & 1u));
+        const int      h = j >> 4;
+        const uint32_t m0 = 1u << (2 * (j & 15)), m1 = 2u << (2 * (j & 15));
+        const uint32_t a0 = ballot_bits(ar[h], m0), a1 = ballot_bits(ar[h], m1);
+        const uint32_t a2 = ballot_bits(aq[h], m0), a3 = ballot_bits(aq[h], m1);
+        const uint32_t av = ballot_bits(ag[h], m0);
+        const uint32_t b0 = ballot_bits(br[h], m0), b1 = ballot_bits(br[h], m1);
+        const uint32_t b2 = ballot_bits(bq[h], m0), b3 = ballot_bits(bq[h], m1);
+        const uint32_t bv = ballot_bits(bg[h], m0);
         const uint32_t m = (tb ? bv : av) & ((tb ? b0 : a0) ^ x0) & ((tb ? b1 : a1) ^ x1)
                          & ((tb ? b2 : a2) ^ x2) & ((tb ? b3 : a3) ^ x3);
         acc[j >> 1] += (uint32_t)__popc(m) << (16 * (j & 1));
     }
 }
+__device__ __forceinline__ void flush_acc(uint32_t (&acc)[16], int rows, uint32_t lane, uint32_t *table)
+{
+    const uint32_t tb = lane >> 4, cell = lane & 15u;
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        if (j >= rows) break;
+        const uint32_t v = (acc[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+        if (v) atomicAdd(&table[tb * 512 + j * 16 + cell], v);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc[i] = 0;
+}
 
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 3) tally_kernel(const TallyArgs A)
+__global__ void __launch_bounds__(kThreads, 4) tally_kernel(const __grid_constant__ TallyArgs A)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TallySmem &S = *reinterpret_cast<TallySmem *>(smem_raw);
@@ -318,6 +405,32 @@ __global__ void __launch_bounds__(kThreads, 3) tally_kernel(const TallyArgs A)
     if (tid < 8) S.stats[tid] = 0;
     for (uint32_t i = tid; i < 8; i += kThreads) { S.le[kWords + i] = ~0u; S.nl[kWords + i] = 0u; }
     if (tid == 0) { mbar_init(&S.bar, 1); fence_mbar_init(); }
+    // contig table -> shared memory (24 human chromosomes take < 1 KB)
+    {
+        const bool fits = A.g.n_contigs <= (uint32_t)kCacheContigs && A.names_bytes <= (uint32_t)kCacheNames && A.g.n_contigs > 0;
+        if (fits) {
+            for (uint32_t i = tid; i < (uint32_t)kCacheSlots; i += kThreads) S.cc.slot[i] = 0xffu;
+            for (uint32_t i = tid; i < A.names_bytes; i += kThreads) S.cc.names[i] = A.g.names[i];
+            if (tid < A.g.n_contigs) {
+                const DevContig c = A.g.contigs[tid];
+                uint32_t h = kNameHashSeed;
+                for (uint32_t k = 0; k < c.name_len; k++) h = name_hash_step(h, (uint8_t)A.g.names[c.name_off + k]);
+                S.cc.hash[tid] = h;
+                S.cc.name_off[tid] = (uint16_t)c.name_off; S.cc.name_len[tid] = (uint16_t)c.name_len;
+                S.cc.base_off[tid] = c.base_off; S.cc.len[tid] = c.len;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (fits)
+                for (uint32_t i = 0; i < A.g.n_contigs; i++) {
+                    uint32_t s = S.cc.hash[i] & (kCacheSlots - 1);
+                    while (S.cc.slot[s] != 0xffu) s = (s + 1) & (kCacheSlots - 1);
+                    S.cc.slot[s] = (uint8_t)i;
+                }
+            S.cc.n = fits ? A.g.n_contigs : 0u;
+        }
+    }
     __syncthreads();
 
     const uint64_t n_tiles = (A.len + kTileMain - 1) / kTileMain;
@@ -325,6 +438,7 @@ __global__ void __launch_bounds__(kThreads, 3) tally_kernel(const TallyArgs A)
     const int      rows = A.cfg.R + 2;
     uint32_t       phase = 0;
     uint32_t       acc[16];
+    int            acc_iters = 0;
 #pragma unroll
     for (int i = 0; i < 16; i++) acc[i] = 0;
 
@@ -351,33 +465,31 @@ __global__ void __launch_bounds__(kThreads, 3) tally_kernel(const TallyArgs A)
         phase ^= 1u;
         if (t0 == 0) __syncthreads();
 
-        // ---- phase 1: classify bytes, 16 per thread and step -> le / nl bit masks
-        for (int q = (int)tid; q < kPieces; q += kThreads) {
-            const int   lo = q * 16;
-            const uint4 v = *reinterpret_cast<const uint4 *>(S.bytes + lo);
-            const uint32_t z0 = le20_flags(v.x), z1 = le20_flags(v.y), z2 = le20_flags(v.z), z3 = le20_flags(v.w);
-            uint32_t le16 = gather16(z0, z1, z2, z3);
-            // newline candidates: <= 0x20 with bit 1 set; confirmed below
-            uint32_t nl16 = gather16(z0 & (v.x << 6), z1 & (v.y << 6), z2 & (v.z << 6), z3 & (v.w << 6));
-            if (lo + 16 > data_end) {                                          // tail of the data
+        // ---- phase 1: classify bytes, 32 per thread and step -> one le / nl mask word each
+        for (int w = (int)tid; w < kWords; w += kThreads) {
+            const uint4 v0 = *reinterpret_cast<const uint4 *>(S.bytes + 32 * w);
+            const uint4 v1 = *reinterpret_cast<const uint4 *>(S.bytes + 32 * w + 16);
+            uint32_t zl[8], zn[8];
+            classify4(v0.x, zl[0], zn[0]); classify4(v0.y, zl[1], zn[1]);
+            classify4(v0.z, zl[2], zn[2]); classify4(v0.w, zl[3], zn[3]);
+            classify4(v1.x, zl[4], zn[4]); classify4(v1.y, zl[5], zn[5]);
+            classify4(v1.z, zl[6], zn[6]); classify4(v1.w, zl[7], zn[7]);
+            uint32_t le32 = (gather8(zl[0], zl[1]) >> 7) | (gather8(zl[2], zl[3]) << 1)
+                          | (gather8(zl[4], zl[5]) << 9) | (gather8(zl[6], zl[7]) << 17);
+            uint32_t nl32 = (gather8(zn[0], zn[1]) >> 7) | (gather8(zn[2], zn[3]) << 1)
+                          | (gather8(zn[4], zn[5]) << 9) | (gather8(zn[6], zn[7]) << 17);
+            const int lo = 32 * w;
+            if (lo + 32 > data_end) {                                          // tail of the data (rare)
                 const uint32_t keep = lo >= data_end ? 0u : ((1u << (data_end - lo)) - 1u);
-                le16 &= keep;
-                nl16 &= keep;
+                le32 &= keep;
+                nl32 &= keep;
+                if (sees_end && data_end >= lo && data_end < lo + 32) {        // end of buffer terminates the last line
+                    le32 |= 1u << (data_end - lo);
+                    nl32 |= 1u << (data_end - lo);
+                }
             }
-            uint32_t cand = nl16;
-            while (cand) {
-                const int bit = __ffs((int)cand) - 1;
-                cand &= cand - 1;
-                if (S.bytes[lo + bit] != '\n') nl16 &= ~(1u << bit);
-            }
-            if (sees_end && data_end >= lo && data_end < lo + 16) {            // end of buffer terminates the last line
-                le16 |= 1u << (data_end - lo);
-                nl16 |= 1u << (data_end - lo);
-            }
-            const uint32_t mine = le16 | (nl16 << 16);
-            const uint32_t other = __shfl_xor_sync(full, mine, 1);
-            if (lane & 1u) S.nl[q >> 1] = (other >> 16) | (mine & 0xffff0000u);
-            else           S.le[q >> 1] = (mine & 0xffffu) | (other << 16);
+            S.le[w] = le32;
+            S.nl[w] = nl32;
         }
         __syncthreads();
 
@@ -399,8 +511,10 @@ __global__ void __launch_bounds__(kThreads, 3) tally_kernel(const TallyArgs A)
             if (lane == 31) S.warp_sum[warp] = inc;
             __syncthreads();
             uint32_t base = 0;
-#pragma unroll
-            for (int k = 0; k < kWarps; k++) base += (k < (int)warp) ? S.warp_sum[k] : 0u;
+            if (warp > 0) {                      // sum of the warps below (<= 7 loads, warp uniform)
+                const uint32_t ws = lane < warp ? S.warp_sum[lane] : 0u;
+                base = __reduce_add_sync(full, ws);
+            }
             uint32_t run = base + inc - sum;
 #pragma unroll
             for (int k = 0; k < kWordsPerThread; k++) {
@@ -435,42 +549,49 @@ __global__ void __launch_bounds__(kThreads, 3) tally_kernel(const TallyArgs A)
                 const int i = i0 + (int)lane;
                 int        code = 99;                                   // 99 = no record for this lane
                 uint64_t   goff = 0;
+                int        start = 0, pe = -1;
+                if (i < cnt) {
+                    start = (int)S.nlpos[i] + 1;
+                    if (start >= kPrefix && start < kPrefix + kTileMain && start < data_end) {
+                        goff = t0 + (uint64_t)(start - kPrefix);
+                        if (pass + i + 1 < n_nl) { pe = (int)S.nlpos[i + 1]; code = kNeedSlow; }
+                        else code = 98;                                 // not whole in this tile
+                    }
+                }
+                const SmemAt at{ S.bytes };
+                RecView      r;
+                r.flag = 0; r.pos = 0; r.mapq = 0; r.tlen = 0;
+                r.rname_off = r.cigar_off = r.seq_off = kPrefix; r.rname_len = r.cigar_len = r.seq_len = 0;
+                if (code == kNeedSlow) code = split_fast(at, S.le, start, pe, r);
+                if (code == kNeedSlow) {                                // rare: glibc sscanf rules
+                    RecView      rs;
+                    const SmemRel rel{ S.bytes + start };
+                    code = scan11(rel, pe - start, rs);
+                    r = rs;
+                    r.rname_off += start; r.cigar_off += start; r.seq_off += start;
+                }
                 PssStreams st;
                 st.a_ref = st.a_read = st.b_ref = st.b_read = 0;
                 st.a_bad = st.b_bad = kEvenBits;
-                if (i < cnt) {
-                    const int start = (int)S.nlpos[i] + 1;
-                    if (start >= kPrefix && start < kPrefix + kTileMain && start < data_end) {
-                        goff = t0 + (uint64_t)(start - kPrefix);
-                        if (pass + i + 1 < n_nl) {
-                            const int    pe = (int)S.nlpos[i + 1];
-                            const SmemAt at{ S.bytes };
-                            RecView      r;
-                            code = split_fast(at, S.le, start, pe, r);
-                            if (code == kNeedSlow) {
-                                const SmemAt rel{ S.bytes + start };
-                                code = scan11(rel, pe - start, r);
-                                r.rname_off += start; r.cigar_off += start; r.seq_off += start;
-                            }
-                            if (code == kCounted) {
-                                if (MODE == kModePss) {
-                                    code = pss_record(at, r, A.g, A.cfg, st);
-                                } else {
-                                    FkHits h;
-                                    code = fk_record(at, r, A.g, A.cfg, h);
-                                    if (h.add5) atomicAdd(A.fk_hist + h.idx5, 1ull);
-                                    if (h.add3) atomicAdd(A.fk_hist + (1ull << (2 * A.cfg.K)) + h.idx3, 1ull);
-                                }
-                            }
-                            log_outcome(A, goff, code);
-                        } else {
-                            code = 98;                                  // not whole in this tile
-                        }
+                if (code == kCounted) {
+                    uint64_t  cb, cl;
+                    const int ci = lookup_contig(S.cc, A.g, at, r.rname_off, r.rname_len, cb, cl);
+                    if (MODE == kModePss) {
+                        code = pss_record(at, r, ci, cb, cl, A.g, A.cfg, st);
+                    } else {
+                        FkHits h;
+                        code = fk_record(at, r, ci, cb, cl, A.g, A.cfg, h);
+                        if (h.add5) atomicAdd(A.fk_hist + h.idx5, 1ull);
+                        if (h.add3) atomicAdd(A.fk_hist + (1ull << (2 * A.cfg.K)) + h.idx3, 1ull);
                     }
                 }
+                if (code < 98) log_outcome(A, goff, code);
                 __syncwarp();
-                if (MODE == kModePss) tally_rows(st, acc, rows, lane);
-                if (code == 98) { long_record<MODE>(A, S, goff); code = 99; }
+                if (MODE == kModePss) {
+                    tally_rows(st, acc, rows, lane);
+                    if (++acc_iters >= kFlushEvery) { flush_acc(acc, rows, lane, S.table); acc_iters = 0; }
+                }
+                if (code == 98) { long_record<MODE>(&A, &S, goff); code = 99; }
                 __syncwarp();
                 const uint32_t m_any = __ballot_sync(full, code != 99);
                 if (m_any) {
@@ -489,25 +610,13 @@ __global__ void __launch_bounds__(kThreads, 3) tally_kernel(const TallyArgs A)
                     }
                 }
             }
-            __syncthreads();
+            __syncthreads();             // tile (and nlpos) fully consumed before it is overwritten
         }
-
-        // ---- per-tile flush of the packed 16-bit partial sums
-        if (MODE == kModePss) {
-            const uint32_t tb = lane >> 4, cell = lane & 15u;
-#pragma unroll
-            for (int j = 0; j < 32; j++) {
-                if (j >= rows) break;
-                const uint32_t v = (acc[j >> 1] >> (16 * (j & 1))) & 0xffffu;
-                if (v) atomicAdd(&S.table[tb * 512 + j * 16 + cell], v);
-            }
-#pragma unroll
-            for (int i = 0; i < 16; i++) acc[i] = 0;
-        }
-        __syncthreads();                 // tile fully consumed before the next bulk copy lands
+        if (n_nl == 0) __syncthreads();
     }
 
-    // ---- CTA tables -> global
+    // ---- warp partial sums -> CTA tables -> global
+    if (MODE == kModePss) flush_acc(acc, rows, lane, S.table);
     __syncthreads();
     if (MODE == kModePss) {
         for (uint32_t i = tid; i < 2 * 32 * 16; i += kThreads) {
@@ -518,5 +627,7 @@ __global__ void __launch_bounds__(kThreads, 3) tally_kernel(const TallyArgs A)
     }
     if (tid < kStN && S.stats[tid]) atomicAdd(A.stats + tid, (unsigned long long)S.stats[tid]);
 }
+
+static_assert(sizeof(TallySmem) + 1024 <= 232448 / 4, "four CTAs of the tally kernel must fit one SM");
 
 }  // namespace pssgpu

@@ -303,8 +303,26 @@ PSS_HD_NOINLINE int scan11(const B &b, int L, RecView &r)
 // split_fast: a record [p0, pe) whose terminator sits at pe, located through
 // `le`, the bit mask of bytes <= 0x20 (bit i of le[w] = byte 32w+i).  Accepts
 // only clean records: ten '\t' between eleven non-empty fields, plain decimal
-// numbers.  Everything else is handed to scan11.
+// numbers.  Everything else is handed to scan11 (return kNeedSlow).
+//
+// Written without early exits: on the GPU all lanes of a warp walk their
+// records in lock step and re-converge after every loop; a lane that has seen
+// something unusual just carries `ok = false` to the end.
 // ---------------------------------------------------------------------------
+template <class B>
+PSS_HD uint32_t dec_field(const B &b, int a, int e, int max_digits, bool &ok)
+{
+    ok = ok && (e > a) && (e - a <= max_digits);
+    if (!ok) e = a;
+    uint32_t v = 0;
+    for (; a < e; a++) {
+        const uint32_t d = b(a) - '0';
+        ok = ok && (d <= 9u);
+        v = v * 10 + d;
+    }
+    return v;
+}
+
 template <class B>
 PSS_HD int split_fast(const B &b, const uint32_t *le, int p0, int pe, RecView &r)
 {
@@ -312,20 +330,22 @@ PSS_HD int split_fast(const B &b, const uint32_t *le, int p0, int pe, RecView &r
     int      w = p0 >> 5;
     uint32_t bits = le[w] & (0xffffffffu << (p0 & 31));
     int      prev = p0 - 1;
+    bool     ok = true;
 #pragma unroll
     for (int f = 0; f < 11; f++) {
-        while (bits == 0) bits = le[++w];          // pe's bit is always set
-        const int p = (w << 5) + ffs32(bits) - 1;
+        while (bits == 0) bits = le[++w];          // pe's bit is always set; a sentinel word follows the data
+        int p = (w << 5) + ffs32(bits) - 1;
         bits &= bits - 1;
-        if (p == prev + 1) return kNeedSlow;       // empty field / leading separator
-        if (f < 10) {
-            if (p >= pe) return kNeedSlow;         // fewer than 11 clean fields: let scan11 decide
-            if (b(p) != '\t') return kNeedSlow;
-        }
+        if (p > pe) p = pe;
+        ok = ok && (p > prev + 1);                 // no empty field, no leading separator
+        if (f < 10) ok = ok && (p < pe);           // fewer than 11 clean fields: let scan11 decide
         sep[f] = p;
         prev = p;
     }
-    if (sep[10] < pe && !is_ws(b(sep[10]))) return kNeedSlow;
+    // separators 1..10 must be '\t', the 11th any white space (or the end of the line)
+#pragma unroll
+    for (int f = 0; f < 10; f++) ok = ok && (b(sep[f]) == '\t');
+    ok = ok && (sep[10] == pe || is_ws(b(sep[10])));
 
     const int qname_len = sep[0] - p0;
     r.rname_off = sep[1] + 1; r.rname_len = sep[2] - sep[1] - 1;
@@ -333,50 +353,38 @@ PSS_HD int split_fast(const B &b, const uint32_t *le, int p0, int pe, RecView &r
     const int mrnm_len = sep[6] - sep[5] - 1;
     r.seq_off = sep[8] + 1;   r.seq_len = sep[9] - sep[8] - 1;
     const int qual_len = sep[10] - sep[9] - 1;
-    if ((qname_len | r.rname_len | r.cigar_len | mrnm_len | r.seq_len | qual_len) > kMaxField) return kNeedSlow;
+    ok = ok && ((qname_len | r.rname_len | r.cigar_len | mrnm_len | r.seq_len | qual_len) <= kMaxField);
 
-    // FLAG %u
-    {
-        int a = sep[0] + 1, e = sep[1];
-        if (e - a > 9) return kNeedSlow;
-        uint32_t v = 0;
-        for (; a < e; a++) { uint32_t c = b(a); if (!is_digit(c)) return kNeedSlow; v = v * 10 + (c - '0'); }
-        r.flag = v;
+    r.flag = dec_field(b, sep[0] + 1, sep[1], 9, ok);                       // FLAG %u
+    {                                                                        // POS %lu: up to 18 digits, in two halves
+        const int a = sep[2] + 1, e = sep[3];
+        const int mid = (e - a > 9) ? e - 9 : a;
+        bool okh = true;
+        const uint32_t hi = (mid > a) ? dec_field(b, a, mid, 9, okh) : 0u;
+        const uint32_t lo = dec_field(b, mid, e, 9, ok);
+        ok = ok && okh;
+        r.pos = (uint64_t)hi * 1000000000ull + lo;
     }
-    // POS %lu
-    {
-        int a = sep[2] + 1, e = sep[3];
-        if (e - a > 18) return kNeedSlow;
-        uint64_t v = 0;
-        for (; a < e; a++) { uint32_t c = b(a); if (!is_digit(c)) return kNeedSlow; v = v * 10 + (c - '0'); }
-        r.pos = v;
+    r.mapq = dec_field(b, sep[3] + 1, sep[4], 9, ok);                       // MAPQ %u
+    {                                                                        // MPOS %u: never read, must convert cleanly
+        const int a = sep[6] + 1, e = sep[7];
+        const int mid = (e - a > 9) ? e - 9 : a;
+        bool okh = true;
+        if (mid > a) (void)dec_field(b, a, mid, 9, okh);
+        (void)dec_field(b, mid, e, 9, ok);
+        ok = ok && okh;
     }
-    // MAPQ %u
-    {
-        int a = sep[3] + 1, e = sep[4];
-        if (e - a > 9) return kNeedSlow;
-        uint32_t v = 0;
-        for (; a < e; a++) { uint32_t c = b(a); if (!is_digit(c)) return kNeedSlow; v = v * 10 + (c - '0'); }
-        r.mapq = v;
-    }
-    // MPOS %u: value is never read, it only has to convert cleanly
-    {
-        int a = sep[6] + 1, e = sep[7];
-        if (e - a > 18) return kNeedSlow;
-        for (; a < e; a++) if (!is_digit(b(a))) return kNeedSlow;
-    }
-    // TLEN %i: plain decimal only (a leading 0 would switch glibc to octal/hex)
-    {
-        int a = sep[7] + 1, e = sep[8];
-        bool neg = false;
-        uint32_t c = b(a);
-        if (c == '-' || c == '+') { neg = (c == '-'); a++; }
-        if (a >= e || e - a > 9) return kNeedSlow;
-        if (b(a) == '0' && e - a > 1) return kNeedSlow;
-        uint32_t v = 0;
-        for (; a < e; a++) { c = b(a); if (!is_digit(c)) return kNeedSlow; v = v * 10 + (c - '0'); }
+    {                                                                        // TLEN %i: plain decimal only
+        int a = sep[7] + 1;
+        const int e = sep[8];
+        const uint32_t c = b(a);
+        const bool neg = (c == '-');
+        if (c == '-' || c == '+') a++;
+        ok = ok && !(e - a > 1 && b(a) == '0');    // a leading 0 would switch glibc to octal / hex
+        const uint32_t v = dec_field(b, a, e, 9, ok);
         r.tlen = neg ? -(int32_t)v : (int32_t)v;
     }
+    if (!ok) return kNeedSlow;
     if (r.seq_len != qual_len) return kParseFail;     // sam-parse.c:50,88
     return kCounted;
 }
@@ -468,13 +476,53 @@ PSS_HD bool cigar_is_nM(const B &b, int off, int len, int64_t n)
     return v == n;
 }
 
-// read base -> 2-bit code / validity after toupper (pss-bam.c:425, :203-255)
-PSS_HD uint32_t read_code(uint32_t c, uint32_t &bad)
+// ---------------------------------------------------------------------------
+// read bases -> 2-bit codes, four at a time
+// ---------------------------------------------------------------------------
+PSS_HD uint32_t byte_perm(uint32_t x, uint32_t y, uint32_t sel)
 {
-    c |= 32u;
-    const uint32_t k = (c >> 1) & 3u;            // a->0 c->1 g->3 t->2
-    bad = !(c == 'a' || c == 'c' || c == 'g' || c == 't');
-    return k ^ (k >> 1);                         // a->0 c->1 g->2 t->3
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(x, y, sel);
+#else
+    const uint64_t src = ((uint64_t)y << 32) | x;
+    uint32_t out = 0;
+    for (int i = 0; i < 4; i++) out |= (uint32_t)((src >> (8 * ((sel >> (4 * i)) & 7u))) & 0xffu) << (8 * i);
+    return out;
+#endif
+}
+// four ASCII bases (little endian in w) after toupper (pss-bam.c:425): 8 bits
+// of codes (A=0 C=1 G=2 T=3, base k at bits 2k) and 8 bits with bit 2k set
+// when base k is not one of ACGT (pss-bam.c:253-255 skips those cells).
+PSS_HD void codes_of_word(uint32_t w, uint32_t &codes8, uint32_t &bad8)
+{
+    const uint32_t c = w | 0x20202020u;
+    const uint32_t k = (c >> 1) & 0x03030303u;                 // a->0 c->1 g->3 t->2
+    uint32_t sel = (k | (k >> 4)) & 0x00330033u;
+    sel = (sel | (sel >> 8)) & 0x3333u;                        // one selector nibble per base
+    const uint32_t x = c ^ byte_perm(0x67746361u, 0u, sel);    // "actg"[k]: zero byte <=> a valid base
+    const uint32_t nz = (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
+    const uint32_t code = k ^ ((k >> 1) & 0x01010101u);        // a->0 c->1 g->2 t->3
+    codes8 = (code * 0x01041040u) >> 24;
+    bad8 = ((nz >> 7) * 0x01041040u) >> 24;
+}
+// 4*n_words (<= 32) read bases starting at byte `off`: field k = base k
+template <class B>
+PSS_HD void read_codes(const B &b, int off, int n_words, uint64_t &codes, uint64_t &bad)
+{
+    codes = 0; bad = 0;
+    const int      a0 = off & ~3;
+    const uint32_t sh = 8u * (uint32_t)(off & 3);
+    uint32_t       prev = b.word(a0);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        if (k >= n_words) break;
+        const uint32_t next = b.word(a0 + 4 * k + 4);
+        uint32_t c8, b8;
+        codes_of_word(funnel_r(prev, next, sh), c8, b8);
+        codes |= (uint64_t)c8 << (8 * k);
+        bad   |= (uint64_t)b8 << (8 * k);
+        prev = next;
+    }
 }
 
 // What one record contributes to the two count tables, in table-row order:
@@ -488,50 +536,63 @@ struct PssStreams {
 
 constexpr uint64_t kEvenBits = 0x5555555555555555ull;
 
-// pss-bam.c:390-496 process_aln.  Fills `st` (all-bad unless counted).
+// pss-bam.c:390-496 process_aln, after find_seq (:393) has been resolved by
+// the caller: ci < 0 means "no such contig".  Fills `st` (all-bad unless
+// counted).
 template <class B>
-PSS_HD int pss_record(const B &b, const RecView &r, const DevGenome &g, const TallyCfg &P, PssStreams &st)
+PSS_HD int pss_record(const B &b, const RecView &r, int ci, uint64_t ctg_base, uint64_t ctg_len,
+                      const DevGenome &g, const TallyCfg &P, PssStreams &st)
 {
     st.a_ref = st.a_read = st.b_ref = st.b_read = 0;
     st.a_bad = st.b_bad = kEvenBits;
 
-    const int ci = find_contig(g, b, r.rname_off, r.rname_len);            // :393
-    if (ci < 0) return kNoContig;
-    const DevContig ctg = g.contigs[ci];
-    if (ctg.len == 0) return kUndefined;          // `ref->len-1` wraps (:408) and the window copy reads past the string
+    if (ci < 0) return kNoContig;                                           // :393-396
+    if (ctg_len == 0) return kUndefined;          // `ref->len-1` wraps (:408) and the window copy reads past the string
 
     const bool paired = r.flag & 1u;
     // sam-parse.c:66-68: unpaired -> isize = strlen(seq); pss-bam.c:401: n = abs(isize)
-    int64_t n = paired ? (r.tlen < 0 ? -(int64_t)r.tlen : (int64_t)r.tlen) : (int64_t)r.seq_len;
+    const int64_t n = paired ? (r.tlen < 0 ? -(int64_t)r.tlen : (int64_t)r.tlen) : (int64_t)r.seq_len;
     if (n > kMaxTlen) return kUndefined;          // reference: stack overflow in its VLAs before any filter
     const int     R = P.R;
     const int64_t s = (int64_t)(r.pos - 1);       // :403
     const int64_t e = s + n - 1;                  // :404
 
     if (s - 2 < 0) return kFiltered;                                        // :407
-    if ((uint64_t)(e + 2) > ctg.len - 1) return kFiltered;                  // :408
+    if ((uint64_t)(e + 2) > ctg_len - 1) return kFiltered;                  // :408
     if (r.mapq < P.min_mq) return kFiltered;                                // :409
     if (!((uint64_t)n >= P.min_len && (uint64_t)n <= P.max_len && n >= R)) return kFiltered;   // :96-103
-    if (!cigar_is_nM(b, r.cigar_off, r.cigar_len, n)) return kFiltered;     // :411
     if (r.flag & (4u | 256u | 512u | 1024u | 2048u)) return kFiltered;      // :412-416
     if (P.merged_only && paired) return kFiltered;                          // :417
+
+    // the two windows leave for HBM before the rest of the record is looked at
+    const int W = R + 2;
+    uint64_t lc, lk, rc, rk;
+    load_window(g, ctg_base + (uint64_t)(s - 2), W, lc, lk);                // g[0 .. W)
+    load_window(g, ctg_base + (uint64_t)(e + 2 - (W - 1)), W, rc, rk);      // g[n+3-(W-1) .. n+3]
+
+    if (!cigar_is_nM(b, r.cigar_off, r.cigar_len, n)) return kFiltered;     // :411
     // paired: n comes from TLEN; with a shorter SEQ the reference reads bytes
     // of earlier records that are still in its Saml buffer
     if (paired && (int64_t)r.seq_len < n) return kUndefined;
 
-    const bool rev = r.flag & 16u;
-    bool want_a, want_b;                          // which table(s) this record feeds
-    const uint64_t gb_up = ctg.base_off + (uint64_t)(s - 1);   // g[1]
-    const uint64_t gb_dn = ctg.base_off + (uint64_t)(e + 1);   // g[n+2]
+    // read bases: r[0..R) and, reversed, r[n-1-i]; both moved up two rows
+    const int nw = (R + 3) >> 2;
+    uint64_t  pre, pre_bad, suf, suf_bad;
+    read_codes(b, r.seq_off, nw, pre, pre_bad);
+    read_codes(b, r.seq_off + (int)n - 4 * nw, nw, suf, suf_bad);
+    suf = rev_fields64(suf, 4 * nw);
+    suf_bad = rev_fields64(suf_bad, 4 * nw);
+    const uint64_t m = low_fields_mask(W);
+    pre = (pre << 4) & m;  pre_bad = (pre_bad << 4) & m;
+    suf = (suf << 4) & m;  suf_bad = (suf_bad << 4) & m;
 
-    const int W = R + 2;
-    uint64_t lc, lk, rc, rk;
-    load_window(g, ctg.base_off + (uint64_t)(s - 2), W, lc, lk);            // g[0 .. W)
-    load_window(g, ctg.base_off + (uint64_t)(e + 2 - (W - 1)), W, rc, rk);  // g[n+3-(W-1) .. n+3]
     rc = rev_fields64(rc, W);                                               // row j <-> g[n+3-j]
     rk = rev_fields64(rk, W);
 
     // symbols of the two adjacent context bases (row 1 of each side)
+    const bool     rev = r.flag & 16u;
+    const uint64_t gb_up = ctg_base + (uint64_t)(s - 1);   // g[1]
+    const uint64_t gb_dn = ctg_base + (uint64_t)(e + 1);   // g[n+2]
     const uint32_t sym_up = (uint32_t)((lc >> 2) & 3u) | ((uint32_t)((lk >> 2) & 3u) << 2);
     const uint32_t sym_dn = (uint32_t)((rc >> 2) & 3u) | ((uint32_t)((rk >> 2) & 3u) << 2);
     // molecule orientation: forward read -> 5' context is g[1]; reverse read ->
@@ -539,6 +600,7 @@ PSS_HD int pss_record(const B &b, const RecView &r, const DevGenome &g, const Ta
     const bool up_ok = rev ? ctx_member(g, P, false, sym_dn, true, gb_dn) : ctx_member(g, P, false, sym_up, false, gb_up);
     const bool dn_ok = rev ? ctx_member(g, P, true, sym_up, true, gb_up) : ctx_member(g, P, true, sym_dn, false, gb_dn);
 
+    bool want_a, want_b;                          // which table(s) this record feeds
     if (!paired) {                                                          // :428-447
         if (!(up_ok && dn_ok)) return kFiltered;
         want_a = want_b = true;
@@ -550,16 +612,6 @@ PSS_HD int pss_record(const B &b, const RecView &r, const DevGenome &g, const Ta
         return kFiltered;
     }
 
-    // read bases: prefix r[0..R) in rows 2.., suffix r[n-1-i] in rows 2..
-    uint64_t pre = 0, pre_bad = 0, suf = 0, suf_bad = 0;
-    for (int i = 0; i < R; i++) {
-        uint32_t bad0, bad1;
-        const uint32_t c0 = read_code(b(r.seq_off + i), bad0);
-        const uint32_t c1 = read_code(b(r.seq_off + (int)n - 1 - i), bad1);
-        pre |= (uint64_t)c0 << (2 * i + 4);  pre_bad |= (uint64_t)bad0 << (2 * i + 4);
-        suf |= (uint64_t)c1 << (2 * i + 4);  suf_bad |= (uint64_t)bad1 << (2 * i + 4);
-    }
-    const uint64_t m = low_fields_mask(W);
     // class != 0 -> not one of ACGT -> the cell is skipped (:253-255, :176-188)
     const uint64_t l_bad = ((lk | (lk >> 1)) & kEvenBits) | pre_bad;
     const uint64_t r_bad = ((rk | (rk >> 1)) & kEvenBits) | suf_bad;
@@ -601,14 +653,14 @@ PSS_HD uint32_t kmer_index_fwd(uint32_t lsb_first, int K) { return rev_fields32(
 PSS_HD uint32_t kmer_index_rc(uint32_t lsb_first, int K) { return ~lsb_first & ((1u << (2 * K)) - 1u); }
 
 template <class B>
-PSS_HD int fk_record(const B &b, const RecView &r, const DevGenome &g, const TallyCfg &P, FkHits &h)
+PSS_HD int fk_record(const B &b, const RecView &r, int ci, uint64_t ctg_base, uint64_t ctg_len,
+                     const DevGenome &g, const TallyCfg &P, FkHits &h)
 {
     h.add5 = h.add3 = false;
     h.idx5 = h.idx3 = 0;
-    const int ci = find_contig(g, b, r.rname_off, r.rname_len);            // :124
-    if (ci < 0) return kNoContig;
-    const DevContig ctg = g.contigs[ci];
-    if (ctg.len == 0) return kUndefined;          // `ref->len-1` wraps (:138)
+    if (ci < 0) return kNoContig;                                          // :124-127
+    if (ctg_len == 0) return kUndefined;          // `ref->len-1` wraps (:138)
+    struct { uint64_t base_off, len; } ctg = { ctg_base, ctg_len };
 
     const int      K = P.K;
     const uint64_t ok = (uint64_t)(K / 2), ik = (uint64_t)K - ok;          // :134-135

@@ -46,6 +46,7 @@ struct pssgpu_ctx {
     char      *d_names = nullptr;
     uint32_t  *d_hash = nullptr;
     uint32_t   hash_mask = 0;
+    uint32_t   names_bytes = 0;
     uint64_t  *d_exc_pos = nullptr;
     uint8_t   *d_exc_chr = nullptr;
     uint32_t   n_exc = 0;
@@ -295,6 +296,7 @@ int upload_impl(pssgpu_ctx *ctx, const pssgpu_contig *contigs, uint64_t n, bool 
     cleanup();
 #undef CUX
     ctx->hash_mask = hash_size - 1;
+    ctx->names_bytes = (uint32_t)names.size();
     ctx->n_groups = n_groups;
     ctx->n_bases = total;
     ctx->n_contigs = n;
@@ -329,6 +331,7 @@ int launch_tally(pssgpu_ctx *ctx, const uint8_t *d_sam, size_t len, uint64_t str
     a.sam = d_sam; a.len = len; a.stream_off = stream_off;
     a.g = dev_genome(ctx);
     a.cfg = ctx->cfg;
+    a.names_bytes = ctx->names_bytes;
     a.pss_tables = ctx->d_tables;
     a.fk_hist = ctx->d_fk;
     a.stats = ctx->d_stats;

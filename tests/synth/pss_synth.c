@@ -156,16 +156,18 @@ static size_t one_read(const synth_reads_cfg *C, uint64_t idx,
     mapq         = (uint32_t)rng_below(&r, (uint64_t)C->max_mapq + 1);
 
     if (L < (uint64_t)n + 64) {            /* contig too short for this read: shrink */
-        n = L > 80 ? (uint32_t)(L - 64) : 8;
-        if (n < 1) n = 1;
+        n = L > 80 ? (uint32_t)(L - 64) : (L > 12 ? (uint32_t)(L - 8) : (uint32_t)(L > 1 ? L - 1 : 1));
     }
     if (kind_edge) {
         /* place so that the +-2 context falls on / over an edge */
         uint64_t k = rng_below(&r, 6);            /* 0..5 */
         if (rng_unit(&r) < 0.5) start = k;        /* pos = 1..6: pos 1,2 rejected, 3+ accepted */
         else                    start = L - n - k;  /* k = 0,1: e+2 > len-1 rejected; k >= 2 accepted */
-    } else {
+        if (start + n > L) start = L - n;         /* tiny contigs */
+    } else if (L >= (uint64_t)n + 64) {
         start = 32 + rng_below(&r, L - n - 64);
+    } else {
+        start = rng_below(&r, L - n + 1);         /* tiny contig: anywhere, edges included */
     }
 
     /* reference window, upper-cased like the loader does */
