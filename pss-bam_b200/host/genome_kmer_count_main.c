@@ -1,0 +1,52 @@
+/* genome-kmer-count on a B200: command line and stdout of the reference
+ * program (genome-kmer-count.c:23-66); the per-base insert loop
+ * (genome-kmer-count.c:56-58, :68-79) is the GPU spectrum kernel behind
+ * include/pssgpu.h.
+ *
+ *   genome-kmer-count -f genome.fa [-k 4]
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+#include "pss_host.h"
+#include "pss_tables.h"
+
+static void help(void)
+{
+    fputs("genome-kmer-count -f <fasta genome file>\n"
+          "                  -k <kmer size; default = 4>\n"
+          "This program reports the number of observed number\n"
+          "of all possible kmers of the given length in the\n"
+          "input genome.\n", stdout);
+    exit(0);
+}
+
+int main(int argc, char *argv[])
+{
+    const char *fa_in = NULL;
+    int k = 4, ich;
+    while ((ich = getopt(argc, argv, "f:k:")) != -1) {
+        switch (ich) {
+        case 'f': fa_in = optarg; break;
+        case 'k': k = atoi(optarg); break;
+        default:  help();
+        }
+    }
+    if (!fa_in || !*fa_in) help();
+
+    pssgpu_ctx *gpu = pss_open_device();
+    Genome *genome = init_genome(fa_in);
+    if (!genome) { fprintf(stderr, "ERROR: cannot read %s\n", fa_in); return 1; }
+    if (pss_upload_genome(gpu, genome) != PSSGPU_OK) pss_die(gpu, "genome upload");
+    if (k < 1 || k > 14) { fprintf(stderr, "ERROR: k must be in [1,14] on this build\n"); return 1; }
+
+    const size_t bins = (size_t)1 << (2 * k);
+    uint64_t *counts = (uint64_t *)calloc(bins, sizeof *counts);
+    if (pssgpu_kmer_spectrum(gpu, k, counts) != PSSGPU_OK) pss_die(gpu, "kmer_spectrum");
+    pss_write_spectrum(stdout, genome->n_seqs, k, counts);
+    free(counts);
+    pssgpu_destroy(gpu);
+    exit(0);
+}

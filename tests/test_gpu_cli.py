@@ -1,0 +1,70 @@
+"""The three host programs (pss-bam_b200/bin, C host + libpssgpu.so) against the reference's golden outputs:
+same command lines, byte-identical files / stdout."""
+import json
+import os
+import subprocess
+
+import pytest
+
+from pss_testlib import REF_DIR, tmpdir
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden", "v1")
+MAN = json.load(open(os.path.join(GOLD, "manifest.json")))
+BIN = os.path.join(ROOT, "pss-bam_b200", "bin")
+SHIM = os.path.join(ROOT, "oracle", "samtools_shim.sh")
+
+
+@pytest.fixture(scope="module")
+def env():
+    import importlib
+    importlib.import_module("pss-bam_b200").build_library()
+    subprocess.run(["make", "-C", os.path.join(ROOT, "pss-bam_b200", "host")], check=True, capture_output=True)
+    d = tmpdir()
+    shim = os.path.join(d, "samtools")            # `samtools view` stand-in (samtools is not in the image)
+    with open(SHIM) as f, open(shim, "w") as o:
+        o.write(f.read())
+    os.chmod(shim, 0o755)
+    e = dict(os.environ)
+    e["PATH"] = d + os.pathsep + e.get("PATH", "")
+    for fn in [MAN["fasta"], *MAN["sams"].values()]:
+        os.symlink(os.path.join(GOLD, fn), os.path.join(d, fn))
+    return d, e
+
+
+def _gold(name):
+    return open(os.path.join(GOLD, name), "rb").read()
+
+
+@pytest.mark.parametrize("case", MAN["pss"], ids=lambda c: c["sam"] + "".join(c["args"]))
+def test_pss_bam_cli(env, case):
+    d, e = env
+    r = subprocess.run([os.path.join(BIN, "pss-bam"), "-F", "genome.fa", "-B", case["sam"] + ".sam", "-o", "out", *case["args"]],
+                       cwd=d, env=e, capture_output=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert open(os.path.join(d, "out.pss.counts.txt"), "rb").read() == _gold(case["counts"])
+    assert open(os.path.join(d, "out.pss.rates.txt"), "rb").read() == _gold(case["rates"])
+
+
+@pytest.mark.parametrize("case", MAN["fragkon"], ids=lambda c: c["sam"] + "".join(c["args"]))
+def test_fragkon_cli(env, case):
+    d, e = env
+    r = subprocess.run([os.path.join(BIN, "fragkon"), "-F", "genome.fa", "-B", case["sam"] + ".sam", *case["args"]],
+                       cwd=d, env=e, capture_output=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = r.stdout
+    if case["sparse"]:
+        lines = out.split(b"\n")
+        out = b"\n".join(lines[:4] + [ln for ln in lines[4:] if ln and not ln.endswith(b"\t0\t0")]) + b"\n"
+    assert out == _gold(case["out"])
+
+
+@pytest.mark.parametrize("case", MAN["gkc"], ids=lambda c: f"k{c['k']}")
+def test_genome_kmer_count_cli(env, case):
+    d, e = env
+    r = subprocess.run([os.path.join(BIN, "genome-kmer-count"), "-f", "genome.fa", "-k", str(case["k"])],
+                       cwd=d, env=e, capture_output=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout == _gold(case["out"])
