@@ -153,6 +153,9 @@ __global__ void __launch_bounds__(256) spectrum_kernel(const uint64_t *__restric
 // ===========================================================================
 // K1-K4  SAM tile scan + per-record tally
 // ===========================================================================
+#ifndef PSS_TALLY_CTAS_PER_SM
+#define PSS_TALLY_CTAS_PER_SM 4
+#endif
 constexpr int kTileMain   = 32768;                            // bytes of SAM a CTA owns per tile
 constexpr int kTileOver   = 2048;                             // look-ahead so the last owned record is whole
 constexpr int kPrefix     = 16;                               // bytes before the tile (is byte -1 a '\n'?)
@@ -170,10 +173,16 @@ constexpr int kFlushEvery   = 1900;                           // warp iterations
 struct ContigCache {
     uint32_t n;                                               // 0: not cached, use the global table
     uint32_t hash[kCacheContigs];
-    uint16_t name_off[kCacheContigs], name_len[kCacheContigs];
+    uint16_t name_w0[kCacheContigs], name_len[kCacheContigs]; // first word of the name in names32 / length in bytes
     uint64_t base_off[kCacheContigs], len[kCacheContigs];
     uint8_t  slot[kCacheSlots];                               // open addressing, 0xff = empty
-    char     names[kCacheNames];
+    uint32_t names32[kCacheNames / 4 + kCacheContigs];        // names as zero-padded little-endian words
+};
+
+struct TallyShared {                                          // per-CTA state both tally kernels keep
+    uint32_t table[2 * 32 * 16];                              // CTA count tables [fwd|rev][row][cell]
+    uint32_t stats[8];
+    ContigCache cc;
 };
 
 struct TallySmem {
@@ -182,11 +191,9 @@ struct TallySmem {
     uint32_t nl[kWords + 8];                                  //                  byte 32w+i is '\n'
     uint16_t wpre[kWords + 8];                                // newlines before word w
     uint16_t nlpos[kRecCap + 4];                              // newline positions of this pass
-    uint32_t table[2 * 32 * 16];                              // CTA count tables [fwd|rev][row][cell]
-    uint32_t stats[8];
+    TallyShared sh;
     uint32_t warp_sum[kWarps];
     uint32_t n_newlines;
-    ContigCache cc;
     alignas(8) uint64_t bar;
 };
 
@@ -208,19 +215,22 @@ struct TallyArgs {
 
 struct SmemAt {                  // absolute positions in the staged tile (4-byte aligned base)
     const uint8_t *p;
+    __device__ __forceinline__ int lo() const { return 0; }
     __device__ __forceinline__ uint32_t operator()(int i) const { return p[i]; }
     __device__ __forceinline__ uint32_t word(int i) const { return *reinterpret_cast<const uint32_t *>(p + i); }
 };
-struct SmemRel {                 // positions relative to a record start (any alignment)
+struct SmemRel {                 // positions relative to a record start (any alignment); records start at >= kPrefix
     const uint8_t *p;
+    __device__ __forceinline__ int lo() const { return -kPrefix; }
     __device__ __forceinline__ uint32_t operator()(int i) const { return p[i]; }
     __device__ __forceinline__ uint32_t word(int i) const
     {
         return (uint32_t)p[i] | ((uint32_t)p[i + 1] << 8) | ((uint32_t)p[i + 2] << 16) | ((uint32_t)p[i + 3] << 24);
     }
 };
-struct GlobalAt {
+struct GlobalAt {                // positions relative to p; nothing before p is touched
     const uint8_t *p;
+    __device__ __forceinline__ int lo() const { return 0; }
     __device__ __forceinline__ uint32_t operator()(int i) const { return __ldg(p + i); }
     __device__ __forceinline__ uint32_t word(int i) const
     {
@@ -258,27 +268,74 @@ __device__ __forceinline__ int stat_slot(int code)
          : code == kParseFail ? kStParseFail : kStUndefined;
 }
 
-// find_seq (fasta-genome-io.c:202-213) against the shared-memory copy of the contig table
+// k-th 4-byte word of the field [off, off+len), zero padded at the end
+template <class B>
+__device__ __forceinline__ uint32_t field_word(const B &b, int off, int len, int k)
+{
+    uint32_t  w = word_at(b, off + 4 * k);
+    const int rem = len - 4 * k;
+    if (rem < 4) w &= rem <= 0 ? 0u : ((1u << (8 * rem)) - 1u);
+    return w;
+}
+template <class B>
+__device__ __forceinline__ uint32_t name_hash_words(const B &b, int off, int len)
+{
+    // every name hashes at least its first two (zero padded) words: no loop for names of up to 8 bytes
+    uint32_t  h = kNameHashSeed ^ (uint32_t)len;
+    const int nw = (len + 3) >> 2;
+    h = (h ^ field_word(b, off, len, 0)) * 0x9E3779B1u;  h ^= h >> 15;
+    h = (h ^ field_word(b, off, len, 1)) * 0x9E3779B1u;  h ^= h >> 15;
+    for (int k = 2; k < nw; k++) {
+        h = (h ^ field_word(b, off, len, k)) * 0x9E3779B1u;
+        h ^= h >> 15;
+    }
+    return h;
+}
+// find_seq (fasta-genome-io.c:202-213) against the shared-memory copy of the
+// contig table: hash and comparison run on whole words of RNAME.  The first
+// two probes are straight-line code (with 128 slots for <= 64 names a third
+// probe is rare), so the lanes of a warp do not drift apart here.
+template <class B>
+__device__ __forceinline__ bool cache_name_equal(const ContigCache &C, uint32_t v, const B &b, int off, int len,
+                                                  uint32_t w0, uint32_t w1)
+{
+    const uint32_t *nm = C.names32 + C.name_w0[v];
+    bool eq = (int)C.name_len[v] == len;
+    if (len > 0) eq = eq && (nm[0] == w0);
+    if (len > 4) eq = eq && (nm[1] == w1);
+    if (len > 8) {                                    // long names: the remaining words
+        const int nw = (len + 3) >> 2;
+        for (int k = 2; eq && k < nw; k++) eq = (nm[k] == field_word(b, off, len, k));
+    }
+    return eq;
+}
 template <class B>
 __device__ __forceinline__ int cache_find(const ContigCache &C, const B &b, int off, int len, uint64_t &base, uint64_t &clen)
 {
-    uint32_t h = kNameHashSeed;
-    for (int i = 0; i < len; i++) h = name_hash_step(h, (uint8_t)b(off + i));
+    const uint32_t h = name_hash_words(b, off, len);
+    const uint32_t w0 = field_word(b, off, len, 0), w1 = field_word(b, off, len, 1);
     uint32_t s = h & (kCacheSlots - 1);
     int      found = -1;
-    for (;;) {
+    bool     open = true;                             // still probing
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
         const uint32_t v = C.slot[s];
-        if (v == 0xffu) break;
-        if (C.hash[v] == h && (int)C.name_len[v] == len) {
-            const char *nm = C.names + C.name_off[v];
-            int i = 0;
-            while (i < len && (uint8_t)nm[i] == (uint8_t)b(off + i)) i++;
-            if (i == len) { found = (int)v; break; }
-        }
+        const bool occupied = (v != 0xffu);
+        const uint32_t vv = occupied ? v : 0u;
+        const bool hit = open && occupied && C.hash[vv] == h && cache_name_equal(C, vv, b, off, len, w0, w1);
+        if (hit) found = (int)vv;
+        open = open && occupied && !hit;
         s = (s + 1) & (kCacheSlots - 1);
     }
-    base = found >= 0 ? C.base_off[found] : 0;
-    clen = found >= 0 ? C.len[found] : 0;
+    while (open) {                                    // rare: a third or later probe
+        const uint32_t v = C.slot[s];
+        if (v == 0xffu) break;
+        if (C.hash[v] == h && cache_name_equal(C, v, b, off, len, w0, w1)) { found = (int)v; break; }
+        s = (s + 1) & (kCacheSlots - 1);
+    }
+    base = C.base_off[found < 0 ? 0 : found];
+    clen = C.len[found < 0 ? 0 : found];
+    if (found < 0) { base = 0; clen = 0; }
     return found;
 }
 template <class B>
@@ -297,10 +354,10 @@ __device__ __forceinline__ int lookup_contig(const ContigCache &C, const DevGeno
 // the way fgets(buf, MAX_LINE_LEN+1) splits it (pss-bam.c:761-764), counted
 // with shared-memory atomics.  Rare by construction.
 template <int MODE>
-__device__ __noinline__ void long_record(const TallyArgs *Ap, TallySmem *Sp, uint64_t gstart)
+__device__ __noinline__ void long_record(const TallyArgs *Ap, TallyShared *Sp, uint64_t gstart)
 {
     const TallyArgs &A = *Ap;
-    TallySmem       &S = *Sp;
+    TallyShared     &S = *Sp;
     uint64_t p = gstart;
     while (p < A.len && __ldg(A.sam + p) != '\n') p++;
     uint64_t total = p - gstart + (p < A.len ? 1u : 0u);
@@ -315,7 +372,7 @@ __device__ __noinline__ void long_record(const TallyArgs *Ap, TallySmem *Sp, uin
             const int ci = lookup_contig(S.cc, A.g, at, r.rname_off, r.rname_len, cb, cl);
             if (MODE == kModePss) {
                 PssStreams st;
-                code = pss_record(at, r, ci, cb, cl, A.g, A.cfg, st);
+                code = pss_record(at, r, true, ci, cb, cl, A.g, A.cfg, st);
                 if (code == kCounted) {
                     const int rows = A.cfg.R + 2;
                     for (int j = 0; j < rows; j++) {
@@ -327,7 +384,7 @@ __device__ __noinline__ void long_record(const TallyArgs *Ap, TallySmem *Sp, uin
                 }
             } else {
                 FkHits h;
-                code = fk_record(at, r, ci, cb, cl, A.g, A.cfg, h);
+                code = fk_record(at, r, true, ci, cb, cl, A.g, A.cfg, h);
                 if (h.add5) atomicAdd(A.fk_hist + h.idx5, 1ull);
                 if (h.add3) atomicAdd(A.fk_hist + (1ull << (2 * A.cfg.K)) + h.idx3, 1ull);
             }
@@ -393,48 +450,231 @@ __device__ __forceinline__ void flush_acc(uint32_t (&acc)[16], int rows, uint32_
     for (int i = 0; i < 16; i++) acc[i] = 0;
 }
 
+// ---------------------------------------------------------------------------
+// building blocks shared by the two tally kernels
+// ---------------------------------------------------------------------------
+// zero the CTA tables and mirror the contig table into shared memory (24 human
+// chromosomes take < 1 KB).  Called by every thread of the CTA.
+__device__ __forceinline__ void cta_prologue(TallyShared &T, const TallyArgs &A, uint32_t tid, uint32_t nthreads)
+{
+    for (uint32_t i = tid; i < 2 * 32 * 16; i += nthreads) T.table[i] = 0;
+    if (tid < 8) T.stats[tid] = 0;
+    const bool fits = A.g.n_contigs <= (uint32_t)kCacheContigs && A.names_bytes <= (uint32_t)kCacheNames && A.g.n_contigs > 0;
+    if (fits) {
+        for (uint32_t i = tid; i < (uint32_t)kCacheSlots; i += nthreads) T.cc.slot[i] = 0xffu;
+        if (tid == 0) {                          // word offsets of the padded names
+            uint32_t w = 0;
+            for (uint32_t i = 0; i < A.g.n_contigs; i++) {
+                T.cc.name_w0[i] = (uint16_t)w;
+                w += (A.g.contigs[i].name_len + 3u) >> 2;
+            }
+        }
+    }
+    __syncthreads();
+    if (fits && tid < A.g.n_contigs) {
+        const DevContig c = A.g.contigs[tid];
+        const GlobalAt  nm{ reinterpret_cast<const uint8_t *>(A.g.names) };
+        const int       nw = (int)((c.name_len + 3u) >> 2);
+        for (int k = 0; k < nw; k++) T.cc.names32[T.cc.name_w0[tid] + k] = field_word(nm, (int)c.name_off, (int)c.name_len, k);
+        T.cc.hash[tid] = name_hash_words(nm, (int)c.name_off, (int)c.name_len);
+        T.cc.name_len[tid] = (uint16_t)c.name_len;
+        T.cc.base_off[tid] = c.base_off; T.cc.len[tid] = c.len;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (fits)
+            for (uint32_t i = 0; i < A.g.n_contigs; i++) {
+                uint32_t s = T.cc.hash[i] & (kCacheSlots - 1);
+                while (T.cc.slot[s] != 0xffu) s = (s + 1) & (kCacheSlots - 1);
+                T.cc.slot[s] = (uint8_t)i;
+            }
+        T.cc.n = fits ? A.g.n_contigs : 0u;
+    }
+    __syncthreads();
+}
+// CTA tables -> global (after a __syncthreads)
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 4) tally_kernel(const __grid_constant__ TallyArgs A)
+__device__ __forceinline__ void cta_epilogue(const TallyShared &T, const TallyArgs &A, uint32_t tid, uint32_t nthreads, int rows)
+{
+    if (MODE == kModePss) {
+        for (uint32_t i = tid; i < 2 * 32 * 16; i += nthreads) {
+            const uint32_t v = T.table[i];
+            const uint32_t tb = i >> 9, row = (i >> 4) & 31u, cell = i & 15u;
+            if (v && (int)row < rows) atomicAdd(A.pss_tables + (size_t)tb * rows * 16 + row * 16 + cell, (unsigned long long)v);
+        }
+    }
+    if (tid < kStN && T.stats[tid]) atomicAdd(A.stats + tid, (unsigned long long)T.stats[tid]);
+}
+
+// geometry of one tile: smem position p <-> global offset t0 - kPrefix + p
+struct TileGeo {
+    uint64_t t0;
+    int      data_end;      // first smem position past the data
+    bool     sees_end;      // the staged span reaches the end of the buffer
+};
+__device__ __forceinline__ TileGeo tile_geo(const TallyArgs &A, uint64_t tile)
+{
+    TileGeo g;
+    g.t0 = tile * kTileMain;
+    const uint64_t avail = A.len - g.t0;                                       // > 0
+    g.sees_end = avail <= (uint64_t)(kTileMain + kTileOver);
+    g.data_end = kPrefix + (g.sees_end ? (int)avail : kTileMain + kTileOver);
+    return g;
+}
+// one bulk async copy of the tile (plus 16 bytes before it) into `bytes`, completion on `bar`
+__device__ __forceinline__ void stage_tile(const TallyArgs &A, const TileGeo &g, uint8_t *bytes, uint64_t *bar)
+{
+    fence_proxy_async();
+    const uint64_t len16 = (A.len + 15) & ~15ull;
+    const uint64_t src = g.t0 ? g.t0 - kPrefix : 0;
+    uint8_t       *dst = bytes + (g.t0 ? 0 : kPrefix);
+    uint64_t       nb = len16 - src;
+    const uint64_t cap = (uint64_t)kTileSpan - (g.t0 ? 0 : kPrefix);
+    if (nb > cap) nb = cap;
+    mbar_expect_tx(bar, (uint32_t)nb);
+    bulk_g2s(dst, A.sam + src, (uint32_t)nb, bar);
+}
+// phase 1: classify bytes, 32 per thread and step -> one le / nl mask word each
+__device__ __forceinline__ void classify_tile(const uint8_t *bytes, uint32_t *le, uint32_t *nl, const TileGeo &g,
+                                              int first, int stride)
+{
+    for (int w = first; w < kWords; w += stride) {
+        const uint4 v0 = *reinterpret_cast<const uint4 *>(bytes + 32 * w);
+        const uint4 v1 = *reinterpret_cast<const uint4 *>(bytes + 32 * w + 16);
+        uint32_t zl[8], zn[8];
+        classify4(v0.x, zl[0], zn[0]); classify4(v0.y, zl[1], zn[1]);
+        classify4(v0.z, zl[2], zn[2]); classify4(v0.w, zl[3], zn[3]);
+        classify4(v1.x, zl[4], zn[4]); classify4(v1.y, zl[5], zn[5]);
+        classify4(v1.z, zl[6], zn[6]); classify4(v1.w, zl[7], zn[7]);
+        uint32_t le32 = (gather8(zl[0], zl[1]) >> 7) | (gather8(zl[2], zl[3]) << 1)
+                      | (gather8(zl[4], zl[5]) << 9) | (gather8(zl[6], zl[7]) << 17);
+        uint32_t nl32 = (gather8(zn[0], zn[1]) >> 7) | (gather8(zn[2], zn[3]) << 1)
+                      | (gather8(zn[4], zn[5]) << 9) | (gather8(zn[6], zn[7]) << 17);
+        const int lo = 32 * w;
+        if (lo + 32 > g.data_end) {                                            // tail of the data (rare)
+            const uint32_t keep = lo >= g.data_end ? 0u : ((1u << (g.data_end - lo)) - 1u);
+            le32 &= keep;
+            nl32 &= keep;
+            if (g.sees_end && g.data_end >= lo && g.data_end < lo + 32) {      // end of buffer terminates the last line
+                le32 |= 1u << (g.data_end - lo);
+                nl32 |= 1u << (g.data_end - lo);
+            }
+        }
+        le[w] = le32;
+        nl[w] = nl32;
+    }
+}
+// newline positions with ordinal in [pass, pass + kRecCap] -> nlpos[]; this thread's words are [w0, w0 + n)
+__device__ __forceinline__ void list_newlines(const uint32_t *nl, const uint16_t *wpre, uint16_t *nlpos, int pass, int w0, int n)
+{
+    for (int k = 0; k < n; k++) {
+        if (w0 + k >= kWords) break;
+        uint32_t bits = nl[w0 + k];
+        int      ord = (int)wpre[w0 + k] - pass;
+        while (bits) {
+            const int bit = __ffs((int)bits) - 1;
+            bits &= bits - 1;
+            if (ord >= 0 && ord <= kRecCap) nlpos[ord] = (uint16_t)((w0 + k) * 32 + bit);
+            ord++;
+        }
+    }
+}
+
+// One warp-load of records: record i runs from newline i (exclusive) to
+// newline i+1 of the pass' list.  Parses, filters, gathers, tallies, counts
+// outcomes.  All 32 lanes of the warp must call it together.
+template <int MODE>
+__device__ __forceinline__ void process_batch(const TallyArgs &A, TallyShared &T, const uint8_t *bytes, const uint32_t *le,
+                                              const uint16_t *nlpos, int i0, int cnt, int pass, int n_nl, const TileGeo &g,
+                                              uint32_t lane, uint32_t (&acc)[16], int &acc_iters, int rows)
+{
+    const uint32_t full = 0xffffffffu;
+    const int      i = i0 + (int)lane;
+    int            code = 99;                                           // 99 = no record for this lane
+    uint64_t       goff = 0;
+    int            start = 0, pe = -1;
+    if (i < cnt) {
+        start = (int)nlpos[i] + 1;
+        if (start >= kPrefix && start < kPrefix + kTileMain && start < g.data_end) {
+            goff = g.t0 + (uint64_t)(start - kPrefix);
+            if (pass + i + 1 < n_nl) { pe = (int)nlpos[i + 1]; code = kNeedSlow; }
+            else code = 98;                                             // not whole in this tile
+        }
+    }
+    const SmemAt at{ bytes };
+    RecView      r;
+    r.flag = 0; r.pos = 0; r.mapq = 0; r.tlen = 0;
+    r.rname_off = r.cigar_off = r.seq_off = kPrefix; r.rname_len = r.cigar_len = r.seq_len = 0;
+    if (code == kNeedSlow) code = split_fast(at, le, start, pe, r);
+    if (code == kNeedSlow) {                                            // rare: glibc sscanf rules
+        RecView       rs;
+        const SmemRel rel{ bytes + start };
+        code = scan11(rel, pe - start, rs);
+        r = rs;
+        r.rname_off += start; r.cigar_off += start; r.seq_off += start;
+    }
+    // From here on every lane runs the same straight-line code; lanes whose
+    // record did not parse (or that have none) carry valid == false.
+    const bool valid = (code == kCounted);
+    uint64_t   cb, cl;
+    const int  ci = lookup_contig(T.cc, A.g, at, r.rname_off, valid ? r.rname_len : 0, cb, cl);
+    PssStreams st;
+    if (MODE == kModePss) {
+        const int rc = pss_record(at, r, valid, ci, cb, cl, A.g, A.cfg, st);
+        if (valid) code = rc;
+    } else {
+        FkHits    h;
+        const int rc = fk_record(at, r, valid, ci, cb, cl, A.g, A.cfg, h);
+        if (valid) code = rc;
+        if (h.add5) atomicAdd(A.fk_hist + h.idx5, 1ull);
+        if (h.add3) atomicAdd(A.fk_hist + (1ull << (2 * A.cfg.K)) + h.idx3, 1ull);
+    }
+    if (code < 98) log_outcome(A, goff, code);
+    __syncwarp();
+    if (MODE == kModePss) {
+        tally_rows(st, acc, rows, lane);
+        if (++acc_iters >= kFlushEvery) { flush_acc(acc, rows, lane, T.table); acc_iters = 0; }
+    }
+    if (code == 98) { long_record<MODE>(&A, &T, goff); code = 99; }
+    __syncwarp();
+    const uint32_t m_any = __ballot_sync(full, code != 99);
+    if (m_any) {
+        const uint32_t m0 = __ballot_sync(full, code == kCounted);
+        const uint32_t m1 = __ballot_sync(full, code == kNoContig);
+        const uint32_t m2 = __ballot_sync(full, code == kFiltered);
+        const uint32_t m3 = __ballot_sync(full, code == kParseFail);
+        const uint32_t m4 = __ballot_sync(full, code == kUndefined);
+        if (lane == 0) {
+            atomicAdd(&T.stats[kStLines], (uint32_t)__popc(m_any));
+            if (m0) atomicAdd(&T.stats[kStCounted], (uint32_t)__popc(m0));
+            if (m1) atomicAdd(&T.stats[kStNoContig], (uint32_t)__popc(m1));
+            if (m2) atomicAdd(&T.stats[kStFiltered], (uint32_t)__popc(m2));
+            if (m3) atomicAdd(&T.stats[kStParseFail], (uint32_t)__popc(m3));
+            if (m4) atomicAdd(&T.stats[kStUndefined], (uint32_t)__popc(m4));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// tally kernel: one tile at a time per CTA, phases separated by block barriers; four CTAs per SM overlap
+// each other's staging, scan and record phases.  (A producer/consumer variant with scan warps and record warps
+// handing tiles over through mbarriers was measured and dropped: the record phase is bound by the latency of one
+// warp-load of records times the number of such loads resident per SM, which shared memory caps at about 20 either
+// way -- profiles/r1_ncu_tally_pipeline_experiment.txt.)
+// ---------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, PSS_TALLY_CTAS_PER_SM) tally_kernel(const __grid_constant__ TallyArgs A)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TallySmem &S = *reinterpret_cast<TallySmem *>(smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t full = 0xffffffffu;
 
-    for (uint32_t i = tid; i < 2 * 32 * 16; i += kThreads) S.table[i] = 0;
-    if (tid < 8) S.stats[tid] = 0;
     for (uint32_t i = tid; i < 8; i += kThreads) { S.le[kWords + i] = ~0u; S.nl[kWords + i] = 0u; }
     if (tid == 0) { mbar_init(&S.bar, 1); fence_mbar_init(); }
-    // contig table -> shared memory (24 human chromosomes take < 1 KB)
-    {
-        const bool fits = A.g.n_contigs <= (uint32_t)kCacheContigs && A.names_bytes <= (uint32_t)kCacheNames && A.g.n_contigs > 0;
-        if (fits) {
-            for (uint32_t i = tid; i < (uint32_t)kCacheSlots; i += kThreads) S.cc.slot[i] = 0xffu;
-            for (uint32_t i = tid; i < A.names_bytes; i += kThreads) S.cc.names[i] = A.g.names[i];
-            if (tid < A.g.n_contigs) {
-                const DevContig c = A.g.contigs[tid];
-                uint32_t h = kNameHashSeed;
-                for (uint32_t k = 0; k < c.name_len; k++) h = name_hash_step(h, (uint8_t)A.g.names[c.name_off + k]);
-                S.cc.hash[tid] = h;
-                S.cc.name_off[tid] = (uint16_t)c.name_off; S.cc.name_len[tid] = (uint16_t)c.name_len;
-                S.cc.base_off[tid] = c.base_off; S.cc.len[tid] = c.len;
-            }
-        }
-        __syncthreads();
-        if (tid == 0) {
-            if (fits)
-                for (uint32_t i = 0; i < A.g.n_contigs; i++) {
-                    uint32_t s = S.cc.hash[i] & (kCacheSlots - 1);
-                    while (S.cc.slot[s] != 0xffu) s = (s + 1) & (kCacheSlots - 1);
-                    S.cc.slot[s] = (uint8_t)i;
-                }
-            S.cc.n = fits ? A.g.n_contigs : 0u;
-        }
-    }
-    __syncthreads();
+    cta_prologue(S.sh, A, tid, kThreads);
 
     const uint64_t n_tiles = (A.len + kTileMain - 1) / kTileMain;
-    const uint64_t len16 = (A.len + 15) & ~15ull;
     const int      rows = A.cfg.R + 2;
     uint32_t       phase = 0;
     uint32_t       acc[16];
@@ -443,57 +683,17 @@ __global__ void __launch_bounds__(kThreads, 4) tally_kernel(const __grid_constan
     for (int i = 0; i < 16; i++) acc[i] = 0;
 
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint64_t t0 = tile * kTileMain;
-        // smem position p <-> global offset t0 - kPrefix + p
-        const uint64_t avail = A.len - t0;                                     // > 0
-        const bool     sees_end = avail <= (uint64_t)(kTileMain + kTileOver);
-        const int      data_end = kPrefix + (sees_end ? (int)avail : kTileMain + kTileOver);
-
-        // ---- stage the tile: one bulk async copy, completion on the mbarrier
-        if (tid == 0) {
-            fence_proxy_async();
-            const uint64_t src = t0 ? t0 - kPrefix : 0;
-            uint8_t       *dst = S.bytes + (t0 ? 0 : kPrefix);
-            uint64_t       nb = len16 - src;
-            const uint64_t cap = (uint64_t)kTileSpan - (t0 ? 0 : kPrefix);
-            if (nb > cap) nb = cap;
-            mbar_expect_tx(&S.bar, (uint32_t)nb);
-            bulk_g2s(dst, A.sam + src, (uint32_t)nb, &S.bar);
-        }
-        if (t0 == 0 && tid < kPrefix) S.bytes[tid] = '\n';                     // "byte -1" of the stream
+        const TileGeo g = tile_geo(A, tile);
+        if (tid == 0) stage_tile(A, g, S.bytes, &S.bar);
+        if (g.t0 == 0 && tid < kPrefix) S.bytes[tid] = '\n';                   // "byte -1" of the stream
         mbar_wait(&S.bar, phase);
         phase ^= 1u;
-        if (t0 == 0) __syncthreads();
+        if (g.t0 == 0) __syncthreads();
 
-        // ---- phase 1: classify bytes, 32 per thread and step -> one le / nl mask word each
-        for (int w = (int)tid; w < kWords; w += kThreads) {
-            const uint4 v0 = *reinterpret_cast<const uint4 *>(S.bytes + 32 * w);
-            const uint4 v1 = *reinterpret_cast<const uint4 *>(S.bytes + 32 * w + 16);
-            uint32_t zl[8], zn[8];
-            classify4(v0.x, zl[0], zn[0]); classify4(v0.y, zl[1], zn[1]);
-            classify4(v0.z, zl[2], zn[2]); classify4(v0.w, zl[3], zn[3]);
-            classify4(v1.x, zl[4], zn[4]); classify4(v1.y, zl[5], zn[5]);
-            classify4(v1.z, zl[6], zn[6]); classify4(v1.w, zl[7], zn[7]);
-            uint32_t le32 = (gather8(zl[0], zl[1]) >> 7) | (gather8(zl[2], zl[3]) << 1)
-                          | (gather8(zl[4], zl[5]) << 9) | (gather8(zl[6], zl[7]) << 17);
-            uint32_t nl32 = (gather8(zn[0], zn[1]) >> 7) | (gather8(zn[2], zn[3]) << 1)
-                          | (gather8(zn[4], zn[5]) << 9) | (gather8(zn[6], zn[7]) << 17);
-            const int lo = 32 * w;
-            if (lo + 32 > data_end) {                                          // tail of the data (rare)
-                const uint32_t keep = lo >= data_end ? 0u : ((1u << (data_end - lo)) - 1u);
-                le32 &= keep;
-                nl32 &= keep;
-                if (sees_end && data_end >= lo && data_end < lo + 32) {        // end of buffer terminates the last line
-                    le32 |= 1u << (data_end - lo);
-                    nl32 |= 1u << (data_end - lo);
-                }
-            }
-            S.le[w] = le32;
-            S.nl[w] = nl32;
-        }
+        classify_tile(S.bytes, S.le, S.nl, g, (int)tid, kThreads);
         __syncthreads();
 
-        // ---- phase 1b: newlines before each mask word (block scan)
+        // newlines before each mask word (block scan)
         {
             const int w0 = (int)tid * kWordsPerThread;
             uint32_t  c[kWordsPerThread], sum = 0;
@@ -526,108 +726,22 @@ __global__ void __launch_bounds__(kThreads, 4) tally_kernel(const __grid_constan
         __syncthreads();
         const int n_nl = (int)S.n_newlines;
 
-        // ---- phase 2: records.  Record i runs from newline i (exclusive) to newline i+1.
         for (int pass = 0; pass < n_nl; pass += kRecCap) {
-            {
-                const int w0 = (int)tid * kWordsPerThread;
-#pragma unroll
-                for (int k = 0; k < kWordsPerThread; k++) {
-                    if (w0 + k >= kWords) break;
-                    uint32_t bits = S.nl[w0 + k];
-                    int      ord = (int)S.wpre[w0 + k] - pass;
-                    while (bits) {
-                        const int bit = __ffs((int)bits) - 1;
-                        bits &= bits - 1;
-                        if (ord >= 0 && ord <= kRecCap) S.nlpos[ord] = (uint16_t)((w0 + k) * 32 + bit);
-                        ord++;
-                    }
-                }
-            }
+            list_newlines(S.nl, S.wpre, S.nlpos, pass, (int)tid * kWordsPerThread, kWordsPerThread);
             __syncthreads();
             const int cnt = (n_nl - pass) < kRecCap ? (n_nl - pass) : kRecCap;
-            for (int i0 = (int)warp * 32; i0 < cnt; i0 += kThreads) {
-                const int i = i0 + (int)lane;
-                int        code = 99;                                   // 99 = no record for this lane
-                uint64_t   goff = 0;
-                int        start = 0, pe = -1;
-                if (i < cnt) {
-                    start = (int)S.nlpos[i] + 1;
-                    if (start >= kPrefix && start < kPrefix + kTileMain && start < data_end) {
-                        goff = t0 + (uint64_t)(start - kPrefix);
-                        if (pass + i + 1 < n_nl) { pe = (int)S.nlpos[i + 1]; code = kNeedSlow; }
-                        else code = 98;                                 // not whole in this tile
-                    }
-                }
-                const SmemAt at{ S.bytes };
-                RecView      r;
-                r.flag = 0; r.pos = 0; r.mapq = 0; r.tlen = 0;
-                r.rname_off = r.cigar_off = r.seq_off = kPrefix; r.rname_len = r.cigar_len = r.seq_len = 0;
-                if (code == kNeedSlow) code = split_fast(at, S.le, start, pe, r);
-                if (code == kNeedSlow) {                                // rare: glibc sscanf rules
-                    RecView      rs;
-                    const SmemRel rel{ S.bytes + start };
-                    code = scan11(rel, pe - start, rs);
-                    r = rs;
-                    r.rname_off += start; r.cigar_off += start; r.seq_off += start;
-                }
-                PssStreams st;
-                st.a_ref = st.a_read = st.b_ref = st.b_read = 0;
-                st.a_bad = st.b_bad = kEvenBits;
-                if (code == kCounted) {
-                    uint64_t  cb, cl;
-                    const int ci = lookup_contig(S.cc, A.g, at, r.rname_off, r.rname_len, cb, cl);
-                    if (MODE == kModePss) {
-                        code = pss_record(at, r, ci, cb, cl, A.g, A.cfg, st);
-                    } else {
-                        FkHits h;
-                        code = fk_record(at, r, ci, cb, cl, A.g, A.cfg, h);
-                        if (h.add5) atomicAdd(A.fk_hist + h.idx5, 1ull);
-                        if (h.add3) atomicAdd(A.fk_hist + (1ull << (2 * A.cfg.K)) + h.idx3, 1ull);
-                    }
-                }
-                if (code < 98) log_outcome(A, goff, code);
-                __syncwarp();
-                if (MODE == kModePss) {
-                    tally_rows(st, acc, rows, lane);
-                    if (++acc_iters >= kFlushEvery) { flush_acc(acc, rows, lane, S.table); acc_iters = 0; }
-                }
-                if (code == 98) { long_record<MODE>(&A, &S, goff); code = 99; }
-                __syncwarp();
-                const uint32_t m_any = __ballot_sync(full, code != 99);
-                if (m_any) {
-                    const uint32_t m0 = __ballot_sync(full, code == kCounted);
-                    const uint32_t m1 = __ballot_sync(full, code == kNoContig);
-                    const uint32_t m2 = __ballot_sync(full, code == kFiltered);
-                    const uint32_t m3 = __ballot_sync(full, code == kParseFail);
-                    const uint32_t m4 = __ballot_sync(full, code == kUndefined);
-                    if (lane == 0) {
-                        atomicAdd(&S.stats[kStLines], (uint32_t)__popc(m_any));
-                        if (m0) atomicAdd(&S.stats[kStCounted], (uint32_t)__popc(m0));
-                        if (m1) atomicAdd(&S.stats[kStNoContig], (uint32_t)__popc(m1));
-                        if (m2) atomicAdd(&S.stats[kStFiltered], (uint32_t)__popc(m2));
-                        if (m3) atomicAdd(&S.stats[kStParseFail], (uint32_t)__popc(m3));
-                        if (m4) atomicAdd(&S.stats[kStUndefined], (uint32_t)__popc(m4));
-                    }
-                }
-            }
+            for (int i0 = (int)warp * 32; i0 < cnt; i0 += kThreads)
+                process_batch<MODE>(A, S.sh, S.bytes, S.le, S.nlpos, i0, cnt, pass, n_nl, g, lane, acc, acc_iters, rows);
             __syncthreads();             // tile (and nlpos) fully consumed before it is overwritten
         }
         if (n_nl == 0) __syncthreads();
     }
 
-    // ---- warp partial sums -> CTA tables -> global
-    if (MODE == kModePss) flush_acc(acc, rows, lane, S.table);
+    if (MODE == kModePss) flush_acc(acc, rows, lane, S.sh.table);
     __syncthreads();
-    if (MODE == kModePss) {
-        for (uint32_t i = tid; i < 2 * 32 * 16; i += kThreads) {
-            const uint32_t v = S.table[i];
-            const uint32_t tb = i >> 9, row = (i >> 4) & 31u, cell = i & 15u;
-            if (v && (int)row < rows) atomicAdd(A.pss_tables + (size_t)tb * rows * 16 + row * 16 + cell, (unsigned long long)v);
-        }
-    }
-    if (tid < kStN && S.stats[tid]) atomicAdd(A.stats + tid, (unsigned long long)S.stats[tid]);
+    cta_epilogue<MODE>(S.sh, A, tid, kThreads, rows);
 }
 
-static_assert(sizeof(TallySmem) + 1024 <= 232448 / 4, "four CTAs of the tally kernel must fit one SM");
+static_assert(sizeof(TallySmem) + 1024 <= 232448 / 4, "four CTAs of tally kernel A must fit one SM");
 
 }  // namespace pssgpu

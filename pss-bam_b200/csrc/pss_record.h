@@ -309,18 +309,64 @@ PSS_HD_NOINLINE int scan11(const B &b, int L, RecView &r)
 // records in lock step and re-converge after every loop; a lane that has seen
 // something unusual just carries `ok = false` to the end.
 // ---------------------------------------------------------------------------
+// ---- decimal fields without byte loops -------------------------------------
+// The digits of a field [a, e) are fetched as whole words ending at e (two or
+// four aligned loads that do not depend on each other), bytes left of the
+// field are replaced by '0', and the value comes out of a few multiply-adds.
+// Compared with a load-test-multiply loop per digit this keeps the lanes of a
+// warp in lock step and removes a chain of dependent shared-memory loads.
 template <class B>
-PSS_HD uint32_t dec_field(const B &b, int a, int e, int max_digits, bool &ok)
+PSS_HD uint32_t word_at(const B &b, int p)            // bytes [p, p+4), any alignment, p >= 0
 {
-    ok = ok && (e > a) && (e - a <= max_digits);
-    if (!ok) e = a;
+    const int a = p & ~3;
+    return funnel_r(b.word(a), b.word(a + 4), 8u * (uint32_t)(p & 3));
+}
+PSS_HD bool all_digits4(uint32_t t) { return (((t + 0x76767676u) | t) & 0x80808080u) == 0u; }   // t = word ^ "0000"
+PSS_HD uint32_t value4(uint32_t t)                    // four digit values, most significant in the low byte
+{
+    t = t * 10u + (t >> 8);
+    return (t & 0xffu) * 100u + ((t >> 16) & 0xffu);
+}
+PSS_HD uint32_t keep_tail(uint32_t w, int drop)       // first `drop` (0..4) bytes -> '0'
+{
+    const uint32_t m = drop >= 4 ? 0u : (0xffffffffu << (8 * drop));
+    return (w & m) | (0x30303030u & ~m);
+}
+template <class B>
+PSS_HD uint32_t dec_loop(const B &b, int a, int e, bool &ok)      // only for the first bytes of the whole input
+{
     uint32_t v = 0;
-    for (; a < e; a++) {
-        const uint32_t d = b(a) - '0';
-        ok = ok && (d <= 9u);
-        v = v * 10 + d;
-    }
+    for (int i = a; i < e; i++) { const uint32_t d = b(i) - '0'; ok = ok && (d <= 9u); v = v * 10u + d; }
     return v;
+}
+// value of the 1..4 digit field [a, e); anything else clears ok
+template <class B>
+PSS_HD uint32_t dec4(const B &b, int a, int e, bool &ok)
+{
+    int L = e - a;
+    ok = ok && (L >= 1) && (L <= 4);
+    if (!ok) L = 1;
+    if (e - 4 < b.lo()) return dec_loop(b, e - L, e, ok);
+    const uint32_t t = keep_tail(word_at(b, e - 4), 4 - L) ^ 0x30303030u;
+    ok = ok && all_digits4(t);
+    return value4(t);
+}
+// value of the 1..9 digit field [a, e); anything else clears ok
+template <class B>
+PSS_HD uint32_t dec9(const B &b, int a, int e, bool &ok)
+{
+    int L = e - a;
+    ok = ok && (L >= 1) && (L <= 9);
+    if (!ok) L = 1;
+    if (e - 12 < b.lo()) return dec_loop(b, e - L, e, ok);
+    const int      p = e - 12, a0 = p & ~3, drop = 12 - L;          // drop in 3..11
+    const uint32_t sh = 8u * (uint32_t)(p & 3);
+    const uint32_t x0 = b.word(a0), x1 = b.word(a0 + 4), x2 = b.word(a0 + 8), x3 = b.word(a0 + 12);
+    const uint32_t t0 = keep_tail(funnel_r(x0, x1, sh), drop) ^ 0x30303030u;
+    const uint32_t t1 = keep_tail(funnel_r(x1, x2, sh), drop - 4 < 0 ? 0 : drop - 4) ^ 0x30303030u;
+    const uint32_t t2 = keep_tail(funnel_r(x2, x3, sh), drop - 8 < 0 ? 0 : drop - 8) ^ 0x30303030u;
+    ok = ok && all_digits4(t0) && all_digits4(t1) && all_digits4(t2);
+    return (value4(t0) * 10000u + value4(t1)) * 10000u + value4(t2);
 }
 
 template <class B>
@@ -355,33 +401,20 @@ PSS_HD int split_fast(const B &b, const uint32_t *le, int p0, int pe, RecView &r
     const int qual_len = sep[10] - sep[9] - 1;
     ok = ok && ((qname_len | r.rname_len | r.cigar_len | mrnm_len | r.seq_len | qual_len) <= kMaxField);
 
-    r.flag = dec_field(b, sep[0] + 1, sep[1], 9, ok);                       // FLAG %u
-    {                                                                        // POS %lu: up to 18 digits, in two halves
-        const int a = sep[2] + 1, e = sep[3];
-        const int mid = (e - a > 9) ? e - 9 : a;
-        bool okh = true;
-        const uint32_t hi = (mid > a) ? dec_field(b, a, mid, 9, okh) : 0u;
-        const uint32_t lo = dec_field(b, mid, e, 9, ok);
-        ok = ok && okh;
-        r.pos = (uint64_t)hi * 1000000000ull + lo;
-    }
-    r.mapq = dec_field(b, sep[3] + 1, sep[4], 9, ok);                       // MAPQ %u
-    {                                                                        // MPOS %u: never read, must convert cleanly
-        const int a = sep[6] + 1, e = sep[7];
-        const int mid = (e - a > 9) ? e - 9 : a;
-        bool okh = true;
-        if (mid > a) (void)dec_field(b, a, mid, 9, okh);
-        (void)dec_field(b, mid, e, 9, ok);
-        ok = ok && okh;
-    }
-    {                                                                        // TLEN %i: plain decimal only
+    // plain decimal numbers of at most nine digits; anything else (signs on
+    // unsigned fields, 0x.., leading-zero TLEN, longer numbers) goes to scan11
+    r.flag = dec4(b, sep[0] + 1, sep[1], ok);                               // FLAG %u (more than 4 digits: scan11)
+    r.pos = dec9(b, sep[2] + 1, sep[3], ok);                                // POS  %lu
+    r.mapq = dec4(b, sep[3] + 1, sep[4], ok);                               // MAPQ %u
+    (void)dec9(b, sep[6] + 1, sep[7], ok);                                  // MPOS %u: never read, must convert cleanly
+    {                                                                        // TLEN %i
         int a = sep[7] + 1;
         const int e = sep[8];
         const uint32_t c = b(a);
         const bool neg = (c == '-');
         if (c == '-' || c == '+') a++;
         ok = ok && !(e - a > 1 && b(a) == '0');    // a leading 0 would switch glibc to octal / hex
-        const uint32_t v = dec_field(b, a, e, 9, ok);
+        const uint32_t v = dec9(b, a, e, ok);
         r.tlen = neg ? -(int32_t)v : (int32_t)v;
     }
     if (!ok) return kNeedSlow;
@@ -448,10 +481,11 @@ PSS_HD uint8_t other_char(const DevGenome &g, uint64_t gb)
 // strchr(UP_CTX|DOWN_CTX, c) != NULL for the genome symbol at gb, after the
 // optional complement of a reverse-strand read (pss-bam.c:60-79 leaves
 // non-ACGT bytes as they are).
-PSS_HD bool ctx_member(const DevGenome &g, const TallyCfg &P, bool down, uint32_t sym, bool complement, uint64_t gb)
+PSS_HD bool ctx_member(const DevGenome &g, const TallyCfg &P, bool down, uint32_t sym, bool complement, uint64_t gb, bool live)
 {
     if (sym < 4u && complement) sym ^= 3u;
-    if (sym != kSymOther) return (((down ? P.down_mask : P.up_mask) >> sym) & 1u) != 0u;
+    const uint32_t mask = down ? P.down_mask : P.up_mask;
+    if (sym != kSymOther || !live) return ((mask >> (sym & 15u)) & 1u) != 0u;     // bit 15 is never set
     if (!(down ? P.down_other : P.up_other)) return false;
     const uint8_t c = other_char(g, gb);
     const char *s = down ? P.down_ctx : P.up_ctx;
@@ -464,16 +498,12 @@ PSS_HD bool ctx_member(const DevGenome &g, const TallyCfg &P, bool down, uint32_
 template <class B>
 PSS_HD bool cigar_is_nM(const B &b, int off, int len, int64_t n)
 {
-    if (len < 2 || len > 11 || n < 0) return false;
-    if (b(off + len - 1) != 'M') return false;
-    if (b(off) == '0' && len != 2) return false;
-    int64_t v = 0;
-    for (int i = 0; i < len - 1; i++) {
-        uint32_t c = b(off + i);
-        if (!is_digit(c)) return false;
-        v = v * 10 + (c - '0');
-    }
-    return v == n;
+    bool ok = (len >= 2) && (len <= 10) && (n >= 0);
+    if (!ok) len = 2;
+    ok = ok && (b(off + len - 1) == 'M') && !(b(off) == '0' && len != 2);
+    // read lengths have at most four digits; longer numbers can only matter for paired records with a huge TLEN
+    const uint32_t v = (len <= 5) ? dec4(b, off, off + len - 1, ok) : dec9(b, off, off + len - 1, ok);
+    return ok && (int64_t)v == n;
 }
 
 // ---------------------------------------------------------------------------
@@ -539,47 +569,55 @@ constexpr uint64_t kEvenBits = 0x5555555555555555ull;
 // pss-bam.c:390-496 process_aln, after find_seq (:393) has been resolved by
 // the caller: ci < 0 means "no such contig".  Fills `st` (all-bad unless
 // counted).
+//
+// Written as straight-line predicated code: a record that fails a filter
+// keeps walking with `live == false` and harmless addresses instead of
+// returning, so that the 32 lanes of a warp stay converged through the window
+// gathers and the read decoding (a lane that drops out costs nothing, a warp
+// that splits executes everything twice).  `valid` = the record parsed; lanes
+// without a record pass valid == false and the RecView defaults.
 template <class B>
-PSS_HD int pss_record(const B &b, const RecView &r, int ci, uint64_t ctg_base, uint64_t ctg_len,
+PSS_HD int pss_record(const B &b, const RecView &r, bool valid, int ci, uint64_t ctg_base, uint64_t ctg_len,
                       const DevGenome &g, const TallyCfg &P, PssStreams &st)
 {
-    st.a_ref = st.a_read = st.b_ref = st.b_read = 0;
-    st.a_bad = st.b_bad = kEvenBits;
-
-    if (ci < 0) return kNoContig;                                           // :393-396
-    if (ctg_len == 0) return kUndefined;          // `ref->len-1` wraps (:408) and the window copy reads past the string
+    int  code = kCounted;
+    bool live = valid;
+#define PSS_DROP(cond, c) do { if (live && (cond)) { code = (c); live = false; } } while (0)
+    PSS_DROP(ci < 0, kNoContig);                                            // :393-396
+    PSS_DROP(ctg_len == 0, kUndefined);           // `ref->len-1` wraps (:408) and the window copy reads past the string
 
     const bool paired = r.flag & 1u;
     // sam-parse.c:66-68: unpaired -> isize = strlen(seq); pss-bam.c:401: n = abs(isize)
     const int64_t n = paired ? (r.tlen < 0 ? -(int64_t)r.tlen : (int64_t)r.tlen) : (int64_t)r.seq_len;
-    if (n > kMaxTlen) return kUndefined;          // reference: stack overflow in its VLAs before any filter
+    PSS_DROP(n > kMaxTlen, kUndefined);           // reference: stack overflow in its VLAs before any filter
     const int     R = P.R;
     const int64_t s = (int64_t)(r.pos - 1);       // :403
     const int64_t e = s + n - 1;                  // :404
 
-    if (s - 2 < 0) return kFiltered;                                        // :407
-    if ((uint64_t)(e + 2) > ctg_len - 1) return kFiltered;                  // :408
-    if (r.mapq < P.min_mq) return kFiltered;                                // :409
-    if (!((uint64_t)n >= P.min_len && (uint64_t)n <= P.max_len && n >= R)) return kFiltered;   // :96-103
-    if (r.flag & (4u | 256u | 512u | 1024u | 2048u)) return kFiltered;      // :412-416
-    if (P.merged_only && paired) return kFiltered;                          // :417
+    PSS_DROP(s - 2 < 0, kFiltered);                                         // :407
+    PSS_DROP((uint64_t)(e + 2) > ctg_len - 1, kFiltered);                   // :408
+    PSS_DROP(r.mapq < P.min_mq, kFiltered);                                 // :409
+    PSS_DROP(!((uint64_t)n >= P.min_len && (uint64_t)n <= P.max_len && n >= R), kFiltered);   // :96-103
+    PSS_DROP(r.flag & (4u | 256u | 512u | 1024u | 2048u), kFiltered);       // :412-416
+    PSS_DROP(P.merged_only && paired, kFiltered);                           // :417
 
     // the two windows leave for HBM before the rest of the record is looked at
     const int W = R + 2;
     uint64_t lc, lk, rc, rk;
-    load_window(g, ctg_base + (uint64_t)(s - 2), W, lc, lk);                // g[0 .. W)
-    load_window(g, ctg_base + (uint64_t)(e + 2 - (W - 1)), W, rc, rk);      // g[n+3-(W-1) .. n+3]
+    load_window(g, live ? ctg_base + (uint64_t)(s - 2) : (uint64_t)kPadBases, W, lc, lk);             // g[0 .. W)
+    load_window(g, live ? ctg_base + (uint64_t)(e + 2 - (W - 1)) : (uint64_t)kPadBases, W, rc, rk);   // g[n+3-(W-1) .. n+3]
 
-    if (!cigar_is_nM(b, r.cigar_off, r.cigar_len, n)) return kFiltered;     // :411
+    PSS_DROP(!cigar_is_nM(b, r.cigar_off, r.cigar_len, n), kFiltered);      // :411
     // paired: n comes from TLEN; with a shorter SEQ the reference reads bytes
     // of earlier records that are still in its Saml buffer
-    if (paired && (int64_t)r.seq_len < n) return kUndefined;
+    PSS_DROP(paired && (int64_t)r.seq_len < n, kUndefined);
 
     // read bases: r[0..R) and, reversed, r[n-1-i]; both moved up two rows
     const int nw = (R + 3) >> 2;
+    const int nn = live ? (int)n : 4 * nw;
     uint64_t  pre, pre_bad, suf, suf_bad;
     read_codes(b, r.seq_off, nw, pre, pre_bad);
-    read_codes(b, r.seq_off + (int)n - 4 * nw, nw, suf, suf_bad);
+    read_codes(b, r.seq_off + nn - 4 * nw, nw, suf, suf_bad);
     suf = rev_fields64(suf, 4 * nw);
     suf_bad = rev_fields64(suf_bad, 4 * nw);
     const uint64_t m = low_fields_mask(W);
@@ -593,39 +631,35 @@ PSS_HD int pss_record(const B &b, const RecView &r, int ci, uint64_t ctg_base, u
     const bool     rev = r.flag & 16u;
     const uint64_t gb_up = ctg_base + (uint64_t)(s - 1);   // g[1]
     const uint64_t gb_dn = ctg_base + (uint64_t)(e + 1);   // g[n+2]
-    const uint32_t sym_up = (uint32_t)((lc >> 2) & 3u) | ((uint32_t)((lk >> 2) & 3u) << 2);
-    const uint32_t sym_dn = (uint32_t)((rc >> 2) & 3u) | ((uint32_t)((rk >> 2) & 3u) << 2);
+    const uint32_t sym_l = (uint32_t)((lc >> 2) & 3u) | ((uint32_t)((lk >> 2) & 3u) << 2);
+    const uint32_t sym_r = (uint32_t)((rc >> 2) & 3u) | ((uint32_t)((rk >> 2) & 3u) << 2);
     // molecule orientation: forward read -> 5' context is g[1]; reverse read ->
     // 5' context is comp(g[n+2]) (pss-bam.c:430-436)
-    const bool up_ok = rev ? ctx_member(g, P, false, sym_dn, true, gb_dn) : ctx_member(g, P, false, sym_up, false, gb_up);
-    const bool dn_ok = rev ? ctx_member(g, P, true, sym_up, true, gb_up) : ctx_member(g, P, true, sym_dn, false, gb_dn);
+    const bool up_ok = ctx_member(g, P, false, rev ? sym_r : sym_l, rev, rev ? gb_dn : gb_up, live);
+    const bool dn_ok = ctx_member(g, P, true, rev ? sym_l : sym_r, rev, rev ? gb_up : gb_dn, live);
 
-    bool want_a, want_b;                          // which table(s) this record feeds
-    if (!paired) {                                                          // :428-447
-        if (!(up_ok && dn_ok)) return kFiltered;
-        want_a = want_b = true;
-    } else if ((r.flag & 2u) && !(r.flag & 8u)) {                           // :450-452
-        if ((r.flag & 64u) && up_ok)       { want_a = true;  want_b = false; }   // :460 / :482
-        else if ((r.flag & 128u) && dn_ok) { want_a = false; want_b = true;  }   // :471 / :488
-        else return kFiltered;
-    } else {
-        return kFiltered;
-    }
+    // which table(s) this record feeds: unpaired :428-447, paired :450-493
+    const bool pp = (r.flag & 2u) && !(r.flag & 8u);
+    const bool sel_a = pp && (r.flag & 64u) && up_ok;                       // :460 / :482
+    const bool sel_b = pp && !sel_a && (r.flag & 128u) && dn_ok;            // :471 / :488
+    const bool want_a = paired ? sel_a : (up_ok && dn_ok);
+    const bool want_b = paired ? sel_b : (up_ok && dn_ok);
+    PSS_DROP(!(want_a || want_b), kFiltered);
+#undef PSS_DROP
 
     // class != 0 -> not one of ACGT -> the cell is skipped (:253-255, :176-188)
     const uint64_t l_bad = ((lk | (lk >> 1)) & kEvenBits) | pre_bad;
     const uint64_t r_bad = ((rk | (rk >> 1)) & kEvenBits) | suf_bad;
     const uint64_t l_read = (lc & 0xfull) | pre;      // rows 0,1: diagonal cell of the context base
     const uint64_t r_read = (rc & 0xfull) | suf;
-
-    if (!rev) {
-        st.a_ref = lc; st.a_read = l_read; st.a_bad = want_a ? l_bad : kEvenBits;
-        st.b_ref = rc; st.b_read = r_read; st.b_bad = want_b ? r_bad : kEvenBits;
-    } else {                                      // complement = flip both code bits
-        st.a_ref = ~rc & m; st.a_read = ~r_read & m; st.a_bad = want_a ? r_bad : kEvenBits;
-        st.b_ref = ~lc & m; st.b_read = ~l_read & m; st.b_bad = want_b ? l_bad : kEvenBits;
-    }
-    return kCounted;
+    const uint64_t flip = rev ? m : 0ull;             // complement = flip both code bits
+    st.a_ref  = (rev ? rc : lc) ^ flip;
+    st.a_read = (rev ? r_read : l_read) ^ flip;
+    st.a_bad  = (live && want_a) ? (rev ? r_bad : l_bad) : kEvenBits;
+    st.b_ref  = (rev ? lc : rc) ^ flip;
+    st.b_read = (rev ? l_read : r_read) ^ flip;
+    st.b_bad  = (live && want_b) ? (rev ? l_bad : r_bad) : kEvenBits;
+    return code;
 }
 
 // ---------------------------------------------------------------------------
@@ -653,14 +687,14 @@ PSS_HD uint32_t kmer_index_fwd(uint32_t lsb_first, int K) { return rev_fields32(
 PSS_HD uint32_t kmer_index_rc(uint32_t lsb_first, int K) { return ~lsb_first & ((1u << (2 * K)) - 1u); }
 
 template <class B>
-PSS_HD int fk_record(const B &b, const RecView &r, int ci, uint64_t ctg_base, uint64_t ctg_len,
+PSS_HD int fk_record(const B &b, const RecView &r, bool valid, int ci, uint64_t ctg_base, uint64_t ctg_len,
                      const DevGenome &g, const TallyCfg &P, FkHits &h)
 {
-    h.add5 = h.add3 = false;
-    h.idx5 = h.idx3 = 0;
-    if (ci < 0) return kNoContig;                                          // :124-127
-    if (ctg_len == 0) return kUndefined;          // `ref->len-1` wraps (:138)
-    struct { uint64_t base_off, len; } ctg = { ctg_base, ctg_len };
+    int  code = kFiltered;
+    bool live = valid;
+#define PSS_DROP(cond, c) do { if (live && (cond)) { code = (c); live = false; } } while (0)
+    PSS_DROP(ci < 0, kNoContig);                                           // :124-127
+    PSS_DROP(ctg_len == 0, kUndefined);           // `ref->len-1` wraps (:138)
 
     const int      K = P.K;
     const uint64_t ok = (uint64_t)(K / 2), ik = (uint64_t)K - ok;          // :134-135
@@ -668,46 +702,43 @@ PSS_HD int fk_record(const B &b, const RecView &r, int ci, uint64_t ctg_base, ui
     const uint64_t s = r.pos - 1;                                           // :129, unsigned: POS 0 wraps
     const uint64_t e = s + n - 1;
     // `aln_start-(KLEN/2) >= 0` is an unsigned tautology (:137)
-    if (!(e + ok <= ctg.len - 1)) return kFiltered;                        // :138
-    if (!(r.mapq >= P.min_mq)) return kFiltered;                           // :139
-    if (!(n >= P.min_len && n <= P.max_len)) return kFiltered;             // :52-58
-    if (!cigar_is_nM(b, r.cigar_off, r.cigar_len, (int64_t)n)) return kFiltered;   // :141
-    if (r.flag & (4u | 256u | 512u | 1024u | 2048u)) return kFiltered;     // :142-146
+    PSS_DROP(!(e + ok <= ctg_len - 1), kFiltered);                         // :138
+    PSS_DROP(!(r.mapq >= P.min_mq), kFiltered);                            // :139
+    PSS_DROP(!(n >= P.min_len && n <= P.max_len), kFiltered);              // :52-58
+    PSS_DROP(r.flag & (4u | 256u | 512u | 1024u | 2048u), kFiltered);      // :142-146
 
+    // Window starts.  Forward: 5' G[s-ok, +K), 3' G[s+n-ik, +K) (:176-177).
+    // Reverse: sub = G[s-ok, s-ok+n+K) copied with strncpy (:156), 5' =
+    // RC(sub)[0,K) = RC(G[s-ok+n, +K)) (:164), 3' = RC(sub)[ok+n-ik, +K) =
+    // RC(G[s-ok+(ik-ok), +K)) (:167).  Left of the contig the reference reads
+    // the allocator's header, whose last byte is 0: such a window never
+    // validates (the packed genome has "other" symbols there), and for reverse
+    // reads the strncpy stops at that 0 and zero-fills, so s < ok kills both.
     const bool    rev = r.flag & 16u;
     const int64_t ss = (int64_t)s;                // -1 when POS was 0
-    bool     v5, v3;
+    const int64_t o5 = rev ? ss - (int64_t)ok + (int64_t)n : ss - (int64_t)ok;
+    const int64_t o3 = rev ? ss - (int64_t)ok + (int64_t)(ik - ok) : ss + (int64_t)n - (int64_t)ik;
     uint32_t w5, w3;
-    if (!rev) {
-        // 5' window G[s-ok, s-ok+K), 3' window G[s+n-ik, s+n-ik+K)  (:176-177).
-        // Left of the contig the reference reads the allocator's header,
-        // whose last byte is 0 -> such a window never validates; the packed
-        // genome has "other" symbols there.
-        v5 = load_kmer(g, ctg.base_off + (uint64_t)(ss - (int64_t)ok), K, w5);
-        v3 = load_kmer(g, ctg.base_off + (uint64_t)(ss + (int64_t)n - (int64_t)ik), K, w3);
-        h.idx5 = kmer_index_fwd(w5, K);
-        h.idx3 = kmer_index_fwd(w3, K);
-    } else {
-        // sub = G[s-ok, s-ok+n+K) copied with strncpy (:156): a terminator
-        // left of the contig zero-fills everything after it, so s < ok kills
-        // both k-mers.  5' = RC(sub)[0,K) = RC(G[s-ok+n, +K)) (:164);
-        // 3' = RC(sub)[ok+n-ik, +K) = RC(G[s-ok+(ik-ok), +K)) (:167).
-        v5 = load_kmer(g, ctg.base_off + (uint64_t)(ss - (int64_t)ok + (int64_t)n), K, w5);
-        v3 = load_kmer(g, ctg.base_off + (uint64_t)(ss - (int64_t)ok + (int64_t)(ik - ok)), K, w3);
-        if (ss < (int64_t)ok) v5 = v3 = false;
-        h.idx5 = kmer_index_rc(w5, K);
-        h.idx3 = kmer_index_rc(w3, K);
-    }
+    bool v5 = load_kmer(g, live ? ctg_base + (uint64_t)o5 : (uint64_t)kPadBases, K, w5);
+    bool v3 = load_kmer(g, live ? ctg_base + (uint64_t)o3 : (uint64_t)kPadBases, K, w3);
+    if (rev && ss < (int64_t)ok) v5 = v3 = false;
+    h.idx5 = rev ? kmer_index_rc(w5, K) : kmer_index_fwd(w5, K);
+    h.idx3 = rev ? kmer_index_rc(w3, K) : kmer_index_fwd(w3, K);
 
-    if (!(r.flag & 1u)) {                                                   // :149-184
-        h.add5 = v5; h.add3 = v3;                // both ends attempted independently
-        return (v5 && v3) ? kCounted : kFiltered;
+    PSS_DROP(!cigar_is_nM(b, r.cigar_off, r.cigar_len, (int64_t)n), kFiltered);   // :141
+#undef PSS_DROP
+
+    const bool paired = r.flag & 1u;
+    const bool pp = !P.merged_only && (r.flag & 2u) && !(r.flag & 8u);     // :187-190
+    const bool use5 = paired ? (pp && (r.flag & 64u)) : true;              // unpaired: both ends, independently (:149-184)
+    const bool use3 = paired ? (pp && !(r.flag & 64u) && (r.flag & 128u)) : true;
+    h.add5 = live && use5 && v5;
+    h.add3 = live && use3 && v3;
+    if (live) {
+        if (!paired) code = (v5 && v3) ? kCounted : kFiltered;
+        else         code = ((use5 && v5) || (use3 && v3)) ? kCounted : kFiltered;
     }
-    if (!P.merged_only && (r.flag & 2u) && !(r.flag & 8u)) {                // :187-190
-        if (r.flag & 64u)  { h.add5 = v5; return v5 ? kCounted : kFiltered; }
-        if (r.flag & 128u) { h.add3 = v3; return v3 ? kCounted : kFiltered; }
-    }
-    return kFiltered;
+    return code;
 }
 
 }  // namespace pssgpu

@@ -288,7 +288,7 @@ int upload_impl(pssgpu_ctx *ctx, const pssgpu_contig *contigs, uint64_t n, bool 
         ctx->n_exc = (uint32_t)exc_n;
     }
     CUX(cudaMalloc(&ctx->d_contigs, std::max<size_t>(1, n) * sizeof(DevContig)));
-    CUX(cudaMalloc(&ctx->d_names, std::max<size_t>(1, names.size())));
+    CUX(cudaMalloc(&ctx->d_names, names.size() + 16));      // + slack: names are also read as whole words
     CUX(cudaMalloc(&ctx->d_hash, hash_size * sizeof(uint32_t)));
     if (n) CUX(cudaMemcpy(ctx->d_contigs, tab.data(), n * sizeof(DevContig), cudaMemcpyHostToDevice));
     if (!names.empty()) CUX(cudaMemcpy(ctx->d_names, names.data(), names.size(), cudaMemcpyHostToDevice));
@@ -340,9 +340,9 @@ int launch_tally(pssgpu_ctx *ctx, const uint8_t *d_sam, size_t len, uint64_t str
     a.dbg_n = ctx->dbg ? ctx->d_dbg_n : nullptr;
     a.dbg_cap = ctx->dbg_cap;
     const uint64_t n_tiles = (len + kTileMain - 1) / kTileMain;
+    time_begin(ctx, len);
     const int      max_grid = MODE == kModePss ? ctx->tally_grid_pss : ctx->tally_grid_fk;
     const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)max_grid);
-    time_begin(ctx, len);
     tally_kernel<MODE><<<grid, kThreads, sizeof(TallySmem), ctx->stream>>>(a);
     time_end(ctx);
     CU(cudaGetLastError());
@@ -414,6 +414,7 @@ int pssgpu_init(int device, pssgpu_ctx **out)
     }
     c->tally_grid_pss = c->sm_count * occ_p;
     c->tally_grid_fk = c->sm_count * occ_f;
+
     *out = c;
     return PSSGPU_OK;
 }

@@ -40,6 +40,7 @@ struct HostGenome {
 
 struct At {
     const uint8_t *p;
+    int lo() const { return 0; }
     uint32_t operator()(int i) const { return p[i]; }
     uint32_t word(int i) const { return (uint32_t)p[i] | ((uint32_t)p[i + 1] << 8) | ((uint32_t)p[i + 2] << 16) | ((uint32_t)p[i + 3] << 24); }
 };
@@ -164,7 +165,7 @@ uint64_t emul_tally(void *gp, const char *sam, uint64_t len, int mode,
                 const uint64_t cb = ci >= 0 ? g.contigs[ci].base_off : 0, cl = ci >= 0 ? g.contigs[ci].len : 0;
                 if (mode == kModePss) {
                     PssStreams st;
-                    code = pss_record(at, r, ci, cb, cl, g, P, st);
+                    code = pss_record(at, r, true, ci, cb, cl, g, P, st);
                     if (code == kCounted) {
                         for (int j = 0; j < R + 2; j++) {
                             if (!((st.a_bad >> (2 * j)) & 1u)) fwd[j * 16 + ((st.a_read >> (2 * j)) & 3u) * 4 + ((st.a_ref >> (2 * j)) & 3u)]++;
@@ -173,7 +174,7 @@ uint64_t emul_tally(void *gp, const char *sam, uint64_t len, int mode,
                     }
                 } else {
                     FkHits h;
-                    code = fk_record(at, r, ci, cb, cl, g, P, h);
+                    code = fk_record(at, r, true, ci, cb, cl, g, P, h);
                     if (h.add5) fp[h.idx5]++;
                     if (h.add3) tp[h.idx3]++;
                 }
