@@ -214,12 +214,14 @@ struct TallyArgs {
 };
 
 struct SmemAt {                  // absolute positions in the staged tile (4-byte aligned base)
+    static constexpr int kLookBack = kPrefix;       // every record starts at >= kPrefix: 12 bytes back is always inside
     const uint8_t *p;
     __device__ __forceinline__ int lo() const { return 0; }
     __device__ __forceinline__ uint32_t operator()(int i) const { return p[i]; }
     __device__ __forceinline__ uint32_t word(int i) const { return *reinterpret_cast<const uint32_t *>(p + i); }
 };
 struct SmemRel {                 // positions relative to a record start (any alignment); records start at >= kPrefix
+    static constexpr int kLookBack = kPrefix;
     const uint8_t *p;
     __device__ __forceinline__ int lo() const { return -kPrefix; }
     __device__ __forceinline__ uint32_t operator()(int i) const { return p[i]; }
@@ -229,6 +231,7 @@ struct SmemRel {                 // positions relative to a record start (any al
     }
 };
 struct GlobalAt {                // positions relative to p; nothing before p is touched
+    static constexpr int kLookBack = 0;
     const uint8_t *p;
     __device__ __forceinline__ int lo() const { return 0; }
     __device__ __forceinline__ uint32_t operator()(int i) const { return __ldg(p + i); }

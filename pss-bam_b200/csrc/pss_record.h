@@ -346,7 +346,7 @@ PSS_HD uint32_t dec4(const B &b, int a, int e, bool &ok)
     int L = e - a;
     ok = ok && (L >= 1) && (L <= 4);
     if (!ok) L = 1;
-    if (e - 4 < b.lo()) return dec_loop(b, e - L, e, ok);
+    if (B::kLookBack < 4 && e - 4 < b.lo()) return dec_loop(b, e - L, e, ok);
     const uint32_t t = keep_tail(word_at(b, e - 4), 4 - L) ^ 0x30303030u;
     ok = ok && all_digits4(t);
     return value4(t);
@@ -358,7 +358,7 @@ PSS_HD uint32_t dec9(const B &b, int a, int e, bool &ok)
     int L = e - a;
     ok = ok && (L >= 1) && (L <= 9);
     if (!ok) L = 1;
-    if (e - 12 < b.lo()) return dec_loop(b, e - L, e, ok);
+    if (B::kLookBack < 12 && e - 12 < b.lo()) return dec_loop(b, e - L, e, ok);
     const int      p = e - 12, a0 = p & ~3, drop = 12 - L;          // drop in 3..11
     const uint32_t sh = 8u * (uint32_t)(p & 3);
     const uint32_t x0 = b.word(a0), x1 = b.word(a0 + 4), x2 = b.word(a0 + 8), x3 = b.word(a0 + 12);
@@ -379,7 +379,12 @@ PSS_HD int split_fast(const B &b, const uint32_t *le, int p0, int pe, RecView &r
     bool     ok = true;
 #pragma unroll
     for (int f = 0; f < 11; f++) {
-        while (bits == 0) bits = le[++w];          // pe's bit is always set; a sentinel word follows the data
+        while (bits == 0) {                         // pe's bit is always set; 8 sentinel words follow the data
+            const uint32_t b1 = le[w + 1], b2 = le[w + 2], b3 = le[w + 3], b4 = le[w + 4];   // independent loads
+            const int      k = b1 ? 1 : b2 ? 2 : b3 ? 3 : 4;
+            bits = b1 ? b1 : b2 ? b2 : b3 ? b3 : b4;
+            w += k;
+        }
         int p = (w << 5) + ffs32(bits) - 1;
         bits &= bits - 1;
         if (p > pe) p = pe;

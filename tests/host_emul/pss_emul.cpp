@@ -39,6 +39,7 @@ struct HostGenome {
 };
 
 struct At {
+    static constexpr int kLookBack = 0;
     const uint8_t *p;
     int lo() const { return 0; }
     uint32_t operator()(int i) const { return p[i]; }
@@ -131,7 +132,7 @@ uint64_t emul_tally(void *gp, const char *sam, uint64_t len, int mode,
     fill_ctx(down ? down : "ACGT", &P.down_mask, &P.down_other, P.down_ctx);
 
     // separator mask the way the tile scan builds it (+ virtual terminator at len)
-    std::vector<uint32_t> le((len + 32) / 32 + 4, 0);
+    std::vector<uint32_t> le((len + 32) / 32 + 12, 0);
     for (uint64_t i = 0; i < len; i++)
         if ((uint8_t)sam[i] <= 0x20) le[i >> 5] |= 1u << (i & 31);
     le[len >> 5] |= 1u << (len & 31);
