@@ -153,14 +153,21 @@ __global__ void __launch_bounds__(256) spectrum_kernel(const uint64_t *__restric
 // ===========================================================================
 // K1-K4  SAM tile scan + per-record tally
 // ===========================================================================
+// tuning knobs (defaults = the measured best; other values are only used by tuning builds)
 #ifndef PSS_TALLY_CTAS_PER_SM
 #define PSS_TALLY_CTAS_PER_SM 4
 #endif
-constexpr int kTileMain   = 32768;                            // bytes of SAM a CTA owns per tile
+#ifndef PSS_TILE_MAIN
+#define PSS_TILE_MAIN 32768
+#endif
+#ifndef PSS_TALLY_THREADS
+#define PSS_TALLY_THREADS 256
+#endif
+constexpr int kTileMain   = PSS_TILE_MAIN;                            // bytes of SAM a CTA owns per tile
 constexpr int kTileOver   = 2048;                             // look-ahead so the last owned record is whole
 constexpr int kPrefix     = 16;                               // bytes before the tile (is byte -1 a '\n'?)
 constexpr int kTileSpan   = kPrefix + kTileMain + kTileOver;  // 34832 staged bytes
-constexpr int kThreads    = 256;
+constexpr int kThreads    = PSS_TALLY_THREADS;
 constexpr int kWarps      = kThreads / 32;
 constexpr int kWords      = (kTileSpan + 31) / 32;                // 32-byte chunks = mask words (1089)
 constexpr int kWordsPerThread = (kWords + kThreads - 1) / kThreads;   // 5
@@ -745,6 +752,7 @@ __global__ void __launch_bounds__(kThreads, PSS_TALLY_CTAS_PER_SM) tally_kernel(
     cta_epilogue<MODE>(S.sh, A, tid, kThreads, rows);
 }
 
-static_assert(sizeof(TallySmem) + 1024 <= 232448 / 4, "four CTAs of tally kernel A must fit one SM");
+static_assert(sizeof(TallySmem) + 1024 <= 232448 / PSS_TALLY_CTAS_PER_SM, "the CTAs of the tally kernel must fit one SM");
+static_assert(kTileSpan < 65536 && kTileSpan % 16 == 0, "newline positions are kept as u16; bulk copies move 16-byte units");
 
 }  // namespace pssgpu

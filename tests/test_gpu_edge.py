@@ -1,0 +1,189 @@
+"""GPU parity on the paths the bulk tests do not reach: records longer than a tile's look-ahead, lines longer than
+fgets' buffer, tiles with more newlines than one pass holds, the global contig table (> 64 contigs), long contig
+names, exotic -U/-D bytes (exception list), device-resident input, error codes."""
+import importlib
+import random
+
+import numpy as np
+import pytest
+
+from pss_testlib import FkParams, Oracle, PssParams, Synth, reads_cfg_config1, reads_cfg_config2
+from test_record_logic import _mutate
+
+pytestmark = pytest.mark.gpu
+pkg = importlib.import_module("pss-bam_b200")
+
+
+def _opts(p):
+    return pkg.PssOptions(p.region_len, p.min_len, p.max_len, p.min_mq, p.up_ctx, p.down_ctx, p.merged_only)
+
+
+def _line_offsets(sam):
+    """fgets view of the stream: a line ends after '\\n' or after 200000 bytes."""
+    offs, i, n = [], 0, len(sam)
+    while i < n:
+        offs.append(i)
+        j = sam.find(b"\n", i, i + 200000)
+        i = (j + 1) if j >= 0 else min(n, i + 200000)
+    return np.array(offs, dtype=np.uint64)
+
+
+def _check(ctx, ora, sam, p=PssParams(), fk=None):
+    f, r, st, status = ora.pss(sam, p, want_status=True)
+    ctx.debug_status(True)
+    gf, gr = ctx.pss(sam, _opts(p))
+    gst = ctx.stats()
+    off, code = ctx.debug_fetch()
+    ctx.debug_status(False)
+    assert np.array_equal(off, _line_offsets(sam))
+    bad = np.flatnonzero(code != status)
+    assert bad.size == 0, (bad[:5], code[bad[:5]], status[bad[:5]])
+    assert gst == st
+    assert np.array_equal(gf, f) and np.array_equal(gr, r)
+    if fk is not None:
+        fp, tp, fst = ora.fragkon(sam, fk)
+        gfp, gtp = ctx.fragkon(sam, pkg.FragkonOptions(fk.klen, fk.min_len, fk.max_len, fk.min_mq, fk.merged_only))
+        assert ctx.stats() == fst
+        assert np.array_equal(gfp, fp) and np.array_equal(gtp, tp)
+
+
+@pytest.fixture(scope="module")
+def small():
+    g = Synth.genome(61, [80000, 50000, 3000], names=["chr1", "chr2", "chrM"], n_frac=0.01, lower_frac=0.05)
+    g.seqs[1][500:520] = np.frombuffer(b"RYKMSWBDHVNrykmswbdh", dtype=np.uint8)
+    g.seqs[1][600:604] = np.frombuffer(b"*-.X", dtype=np.uint8)
+    ora = Oracle(fasta=g.fasta_bytes())
+    ctx = pkg.Context(0)
+    ctx.upload_genome(ora.contigs())
+    yield g, ora, ctx
+    ctx.close()
+
+
+def test_long_records_and_overlong_lines(small):
+    g, ora, ctx = small
+    good = Synth.sam(reads_cfg_config1(seed=5), g, 0, 400).split(b"\n")[:-1]
+    lines = []
+    for i, ln in enumerate(good):
+        lines.append(ln)
+        if i % 40 == 7:
+            lines.append(ln + b"\tXX:Z:" + b"t" * (2500 + 97 * i))          # good record, longer than the look-ahead
+        if i % 97 == 11:
+            lines.append(b"x" * 199999)                                     # exactly fgets' buffer with its newline
+            lines.append(b"y" * 200000)                                     # splits into two lines
+            lines.append(b"z" * 199990 + b" " + ln + b"\t" + b"t" * 250000)  # tail chunk of a 450 KB line parses
+    _check(ctx, ora, b"\n".join(lines) + b"\n", fk=FkParams(klen=6))
+    _check(ctx, ora, b"\n".join(lines))                                     # no final newline
+
+
+def test_more_newlines_than_one_pass(small):
+    g, ora, ctx = small
+    good = Synth.sam(reads_cfg_config2(seed=6, min_len=20, max_len=60), g, 0, 3000).split(b"\n")[:-1]
+    rng = random.Random(3)
+    lines = []
+    for ln in good:
+        lines.append(ln)
+        lines.extend([b""] * rng.choice([0, 0, 3, 40]))                     # bursts of empty lines
+        if rng.random() < 0.05:
+            lines.extend([b"a\tb"] * 700)                                   # > 1024 short lines per 32 KiB tile
+    _check(ctx, ora, b"\n".join(lines) + b"\n", fk=FkParams(klen=5))
+    _check(ctx, ora, b"\n" * 100000 + good[0] + b"\n")
+
+
+def test_malformed_lines(small):
+    g, ora, ctx = small
+    for seed in (21, 22):
+        rng = random.Random(seed)
+        good = Synth.sam(reads_cfg_config2(seed=seed, min_len=20, max_len=70), g, 0, 4000).split(b"\n")[:-1]
+        lines = [_mutate(rng, ln) if rng.random() < 0.7 else ln for ln in good]
+        _check(ctx, ora, b"\n".join(lines) + b"\n", fk=FkParams(klen=7))
+
+
+def test_exotic_context_bytes(small):
+    g, ora, ctx = small
+    sam = Synth.sam(reads_cfg_config1(seed=9, read_len=40), g, 0, 200).split(b"\n")[:-1]
+    # reads placed right next to the IUPAC / exotic bytes of chr2 so that their context base is one of them
+    seq = g.seqs[1].tobytes().upper()
+    extra = []
+    for pos0 in range(470, 640):
+        rd = seq[pos0:pos0 + 30].replace(b"*", b"A").replace(b"-", b"A").replace(b".", b"A")
+        for flag in (0, 16):
+            extra.append(b"\t".join([b"e%d" % pos0, str(flag).encode(), b"chr2", str(pos0 + 1).encode(), b"30", b"30M", b"*",
+                                     b"0", b"0", rd, b"I" * 30]))
+    data = b"\n".join(sam + extra) + b"\n"
+    for p in (PssParams(), PssParams(up_ctx=b"ACGTN", down_ctx=b"ACGTRYKM"), PssParams(up_ctx=b"*-.X", down_ctx=b"ACGT*"),
+              PssParams(up_ctx=b"ACGT-", down_ctx=b"."), PssParams(up_ctx=b"acgt", down_ctx=b"ACGT")):
+        _check(ctx, ora, data, p)
+
+
+def test_many_contigs_and_long_names():
+    names = [f"scaffold_{i:05d}_with_a_rather_long_name" for i in range(150)] + ["x", "chrUn_" + "y" * 200]
+    lens = [900 + 7 * i for i in range(150)] + [5000, 4000]
+    g = Synth.genome(71, lens, names=names, n_frac=0.01)
+    ora = Oracle(fasta=g.fasta_bytes())
+    ctx = pkg.Context(0)
+    ctx.upload_genome(ora.contigs()[::-1])                      # any order
+    sam = Synth.sam(reads_cfg_config2(seed=72, min_len=20, max_len=60), g, 0, 20000)
+    _check(ctx, ora, sam, fk=FkParams(klen=8))
+    for k in (2, 9):
+        assert np.array_equal(ctx.kmer_spectrum(k), ora.kmer_spectrum(k))
+    ctx.close()
+    # <= 64 contigs but names longer than 16 bytes: shared-memory table with multi-word names
+    g2 = Synth.genome(73, [3000] * 20, names=[f"contig_number_{i}_of_the_assembly" for i in range(20)])
+    ora2 = Oracle(fasta=g2.fasta_bytes())
+    ctx2 = pkg.Context(0)
+    ctx2.upload_genome(ora2.contigs())
+    _check(ctx2, ora2, Synth.sam(reads_cfg_config2(seed=74, min_len=20, max_len=60), g2, 0, 10000))
+    ctx2.close()
+
+
+def test_device_resident_input_and_reuse(small):
+    import torch
+    g, ora, ctx = small
+    sam = Synth.sam(reads_cfg_config2(seed=11, min_len=20, max_len=90), g, 0, 30000)
+    f, r, st = ora.pss(sam, PssParams())
+    dev = torch.frombuffer(bytearray(sam), dtype=torch.uint8).cuda()
+    tab = torch.zeros(2 * 17 * 16, dtype=torch.int64, device="cuda")
+    for _ in range(2):                                           # begin/feed/finish twice on one context
+        ctx.pss_begin(pkg.PssOptions())
+        ctx.feed_device(dev.data_ptr(), len(sam))
+        ctx.pss_finish_device(tab.data_ptr())
+        got = tab.cpu().numpy().astype(np.uint64).reshape(2, 17, 16)
+        assert np.array_equal(got[0], f) and np.array_equal(got[1], r)
+    gf, gr = ctx.pss_finish()                                    # finish may be repeated
+    assert np.array_equal(gf, f)
+    ctx.feed(sam, last=True)                                     # and the tally stays open
+    gf, gr = ctx.pss_finish()
+    assert np.array_equal(gf, 2 * f) and np.array_equal(gr, 2 * r)
+    # genome uploaded from device memory
+    ctx2 = pkg.Context(0)
+    keep = [torch.frombuffer(bytearray(s), dtype=torch.uint8).cuda() for _, s in ora.contigs()]
+    ctx2.upload_genome_device([(cid, t.data_ptr(), t.numel()) for (cid, _), t in zip(ora.contigs(), keep)])
+    gf2, gr2 = ctx2.pss(sam)
+    assert np.array_equal(gf2, f) and np.array_equal(gr2, r)
+    ctx2.close()
+
+
+def test_error_codes(small):
+    g, ora, ctx = small
+    with pytest.raises(pkg.PssGpuError) as e:
+        ctx.pss_begin(pkg.PssOptions(region_len=31))
+    assert e.value.code == -5
+    with pytest.raises(pkg.PssGpuError):
+        ctx.fragkon_begin(pkg.FragkonOptions(klen=15))
+    with pytest.raises(pkg.PssGpuError):
+        ctx.kmer_spectrum(0)
+    fresh = pkg.Context(0)
+    with pytest.raises(pkg.PssGpuError) as e:
+        fresh.pss_begin(pkg.PssOptions())
+    assert e.value.code == -4                                    # no genome resident
+    with pytest.raises(pkg.PssGpuError):
+        fresh.upload_genome([("a", b"ACGT"), ("a", b"GGGG")])    # duplicate ids
+    with pytest.raises(pkg.PssGpuError):
+        fresh.upload_genome([("a", b"AC\x00GT")])                # NUL byte
+    fresh.close()
+    ctx.pss_begin(pkg.PssOptions())
+    ctx.feed(b"r1\t0\tchr1\t100\t30\t3")                         # unterminated line pending
+    with pytest.raises(pkg.PssGpuError):
+        ctx.pss_finish()
+    ctx.feed(b"", last=True)
+    ctx.pss_finish()
