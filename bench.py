@@ -212,7 +212,7 @@ def main_b200(a):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cores = os.cpu_count() or 1
-    os.environ["OMP_NUM_THREADS"] = str(max(1, cores // max(1, world)))
+    Synth.set_threads(max(1, cores // max(1, world)))      # torchrun exports OMP_NUM_THREADS=1
 
     pkg = importlib.import_module("pss-bam_b200")
     ctx = pkg.Context(local)

@@ -1,0 +1,2 @@
+set -x
+timeout 900 python -m pytest tests/test_gpu_edge.py -x -q -m gpu 2>&1 | tail -30

@@ -116,8 +116,14 @@ class Synth:
             lib.synth_sam.restype = C.c_size_t
             lib.synth_fasta_record.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, C.c_uint32, C.c_char_p]
             lib.synth_fasta_record.restype = C.c_size_t
+            lib.synth_set_threads.argtypes = [C.c_int]
+            lib.synth_set_threads.restype = None
             cls._lib = lib
         return cls._lib
+
+    @classmethod
+    def set_threads(cls, n: int):
+        cls.lib().synth_set_threads(int(n))
 
     @classmethod
     def genome(cls, seed, contig_lens, names=None, n_frac=0.0, lower_frac=0.0) -> SynthGenome:

@@ -42,6 +42,16 @@ typedef struct synth_reads_cfg {
     uint32_t with_tags;             /* append NM:i / MD:Z                         */
 } synth_reads_cfg;
 
+/* Thread count for the generators (torchrun exports OMP_NUM_THREADS=1 to every rank). */
+void synth_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* ---- counter based RNG -------------------------------------------------- */
 static inline uint64_t mix64(uint64_t z)
 {
