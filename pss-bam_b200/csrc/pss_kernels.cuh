@@ -420,7 +420,8 @@ __device__ __forceinline__ uint32_t ballot_bits(uint32_t word, uint32_t mask)
 // owns cell (l & 15) of table (l >> 4); five ballots per table and row turn
 // "which lanes hit my cell" into a popcount.  acc[] packs two rows per
 // register (16-bit partial sums).  All 32 lanes must be converged.
-__device__ __forceinline__ void tally_rows(const PssStreams &st, uint32_t (&acc)[16], int rows, uint32_t lane)
+template <int NACC>
+__device__ __forceinline__ void tally_rows(const PssStreams &st, uint32_t (&acc)[NACC], int rows, uint32_t lane)
 {
     const bool     tb = lane >= 16;
     const uint32_t cell = lane & 15u;
@@ -432,7 +433,7 @@ __device__ __forceinline__ void tally_rows(const PssStreams &st, uint32_t (&acc)
     const uint32_t br[2] = { (uint32_t)st.b_ref, (uint32_t)(st.b_ref >> 32) }, bq[2] = { (uint32_t)st.b_read, (uint32_t)(st.b_read >> 32) };
     const uint32_t bg[2] = { ~(uint32_t)st.b_bad, ~(uint32_t)(st.b_bad >> 32) };
 #pragma unroll
-    for (int j = 0; j < 32; j++) {
+    for (int j = 0; j < 2 * NACC; j++) {
         if (j >= rows) break;
         const int      h = j >> 4;
         const uint32_t m0 = 1u << (2 * (j & 15)), m1 = 2u << (2 * (j & 15));
@@ -447,17 +448,18 @@ __device__ __forceinline__ void tally_rows(const PssStreams &st, uint32_t (&acc)
         acc[j >> 1] += (uint32_t)__popc(m) << (16 * (j & 1));
     }
 }
-__device__ __forceinline__ void flush_acc(uint32_t (&acc)[16], int rows, uint32_t lane, uint32_t *table)
+template <int NACC>
+__device__ __forceinline__ void flush_acc(uint32_t (&acc)[NACC], int rows, uint32_t lane, uint32_t *table)
 {
     const uint32_t tb = lane >> 4, cell = lane & 15u;
 #pragma unroll
-    for (int j = 0; j < 32; j++) {
+    for (int j = 0; j < 2 * NACC; j++) {
         if (j >= rows) break;
         const uint32_t v = (acc[j >> 1] >> (16 * (j & 1))) & 0xffffu;
         if (v) atomicAdd(&table[tb * 512 + j * 16 + cell], v);
     }
 #pragma unroll
-    for (int i = 0; i < 16; i++) acc[i] = 0;
+    for (int i = 0; i < NACC; i++) acc[i] = 0;
 }
 
 // ---------------------------------------------------------------------------
@@ -593,10 +595,10 @@ __device__ __forceinline__ void list_newlines(const uint32_t *nl, const uint16_t
 // One warp-load of records: record i runs from newline i (exclusive) to
 // newline i+1 of the pass' list.  Parses, filters, gathers, tallies, counts
 // outcomes.  All 32 lanes of the warp must call it together.
-template <int MODE>
+template <int MODE, int NACC>
 __device__ __forceinline__ void process_batch(const TallyArgs &A, TallyShared &T, const uint8_t *bytes, const uint32_t *le,
                                               const uint16_t *nlpos, int i0, int cnt, int pass, int n_nl, const TileGeo &g,
-                                              uint32_t lane, uint32_t (&acc)[16], int &acc_iters, int rows)
+                                              uint32_t lane, uint32_t (&acc)[NACC], int &acc_iters, int rows)
 {
     const uint32_t full = 0xffffffffu;
     const int      i = i0 + (int)lane;
@@ -626,6 +628,10 @@ __device__ __forceinline__ void process_batch(const TallyArgs &A, TallyShared &T
     // From here on every lane runs the same straight-line code; lanes whose
     // record did not parse (or that have none) carry valid == false.
     const bool valid = (code == kCounted);
+    if (!valid) {                     // a failed parse leaves arbitrary offsets behind: park them on safe bytes
+        r.flag = 0; r.pos = 0; r.mapq = 0; r.tlen = 0;
+        r.rname_off = r.cigar_off = r.seq_off = kPrefix; r.rname_len = r.cigar_len = r.seq_len = 0;
+    }
     uint64_t   cb, cl;
     const int  ci = lookup_contig(T.cc, A.g, at, r.rname_off, valid ? r.rname_len : 0, cb, cl);
     PssStreams st;
@@ -672,7 +678,8 @@ __device__ __forceinline__ void process_batch(const TallyArgs &A, TallyShared &T
 // warp-load of records times the number of such loads resident per SM, which shared memory caps at about 20 either
 // way -- profiles/r1_ncu_tally_pipeline_experiment.txt.)
 // ---------------------------------------------------------------------------
-template <int MODE>
+// NACC = registers of packed partial sums per lane: 9 cover -r <= 16 (the default is 15), 16 cover -r <= 30
+template <int MODE, int NACC>
 __global__ void __launch_bounds__(kThreads, PSS_TALLY_CTAS_PER_SM) tally_kernel(const __grid_constant__ TallyArgs A)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -687,29 +694,33 @@ __global__ void __launch_bounds__(kThreads, PSS_TALLY_CTAS_PER_SM) tally_kernel(
     const uint64_t n_tiles = (A.len + kTileMain - 1) / kTileMain;
     const int      rows = A.cfg.R + 2;
     uint32_t       phase = 0;
-    uint32_t       acc[16];
+    uint32_t       acc[NACC];
     int            acc_iters = 0;
 #pragma unroll
-    for (int i = 0; i < 16; i++) acc[i] = 0;
+    for (int i = 0; i < NACC; i++) acc[i] = 0;
 
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const TileGeo g = tile_geo(A, tile);
         if (tid == 0) stage_tile(A, g, S.bytes, &S.bar);
         if (g.t0 == 0 && tid < kPrefix) S.bytes[tid] = '\n';                   // "byte -1" of the stream
-        mbar_wait(&S.bar, phase);
+        // one warp sleeps on the mbarrier; the others wait at the block barrier without spending issue slots,
+        // then take their own (immediately successful) acquire of the completed phase
+        if (warp == 0) mbar_wait(&S.bar, phase);
+        __syncthreads();
+        if (warp != 0) mbar_wait(&S.bar, phase);
         phase ^= 1u;
-        if (g.t0 == 0) __syncthreads();
 
         classify_tile(S.bytes, S.le, S.nl, g, (int)tid, kThreads);
         __syncthreads();
 
-        // newlines before each mask word (block scan)
+        // newlines before each mask word (block scan), and -- fused -- the position list of the first pass
         {
             const int w0 = (int)tid * kWordsPerThread;
-            uint32_t  c[kWordsPerThread], sum = 0;
+            uint32_t  nlw[kWordsPerThread], c[kWordsPerThread], sum = 0;
 #pragma unroll
             for (int k = 0; k < kWordsPerThread; k++) {
-                c[k] = (w0 + k < kWords) ? (uint32_t)__popc(S.nl[w0 + k]) : 0u;
+                nlw[k] = (w0 + k < kWords) ? S.nl[w0 + k] : 0u;
+                c[k] = (uint32_t)__popc(nlw[k]);
                 sum += c[k];
             }
             uint32_t inc = sum;
@@ -728,7 +739,19 @@ __global__ void __launch_bounds__(kThreads, PSS_TALLY_CTAS_PER_SM) tally_kernel(
             uint32_t run = base + inc - sum;
 #pragma unroll
             for (int k = 0; k < kWordsPerThread; k++) {
-                if (w0 + k < kWords) S.wpre[w0 + k] = (uint16_t)run;
+                if (w0 + k < kWords) S.wpre[w0 + k] = (uint16_t)run;         // only read again by later passes
+                // a 32-byte chunk rarely holds more than one newline: the first one is stored without a branch
+                const uint32_t bits = nlw[k];
+                if (bits != 0u && run <= (uint32_t)kRecCap) S.nlpos[run] = (uint16_t)((w0 + k) * 32 + __ffs((int)bits) - 1);
+                uint32_t rest = bits & (bits - 1u);
+                if (__any_sync(full, rest != 0u)) {
+                    uint32_t ord = run + 1;
+                    while (rest) {
+                        if (ord <= (uint32_t)kRecCap) S.nlpos[ord] = (uint16_t)((w0 + k) * 32 + __ffs((int)rest) - 1);
+                        rest &= rest - 1u;
+                        ord++;
+                    }
+                }
                 run += c[k];
             }
             if (tid == kThreads - 1) S.n_newlines = run;
@@ -737,11 +760,13 @@ __global__ void __launch_bounds__(kThreads, PSS_TALLY_CTAS_PER_SM) tally_kernel(
         const int n_nl = (int)S.n_newlines;
 
         for (int pass = 0; pass < n_nl; pass += kRecCap) {
-            list_newlines(S.nl, S.wpre, S.nlpos, pass, (int)tid * kWordsPerThread, kWordsPerThread);
-            __syncthreads();
+            if (pass > 0) {                      // rare: more than kRecCap newlines in one tile
+                list_newlines(S.nl, S.wpre, S.nlpos, pass, (int)tid * kWordsPerThread, kWordsPerThread);
+                __syncthreads();
+            }
             const int cnt = (n_nl - pass) < kRecCap ? (n_nl - pass) : kRecCap;
             for (int i0 = (int)warp * 32; i0 < cnt; i0 += kThreads)
-                process_batch<MODE>(A, S.sh, S.bytes, S.le, S.nlpos, i0, cnt, pass, n_nl, g, lane, acc, acc_iters, rows);
+                process_batch<MODE, NACC>(A, S.sh, S.bytes, S.le, S.nlpos, i0, cnt, pass, n_nl, g, lane, acc, acc_iters, rows);
             __syncthreads();             // tile (and nlpos) fully consumed before it is overwritten
         }
         if (n_nl == 0) __syncthreads();

@@ -377,22 +377,53 @@ PSS_HD int split_fast(const B &b, const uint32_t *le, int p0, int pe, RecView &r
     uint32_t bits = le[w] & (0xffffffffu << (p0 & 31));
     int      prev = p0 - 1;
     bool     ok = true;
+    // next separator at or after the cursor (w, bits); empty mask words are skipped four at a time with
+    // independent loads.  pe's bit is always set and 8 all-ones sentinel words follow the data.
+#define PSS_NEXT_SEP(f)                                                                         \
+    do {                                                                                        \
+        while (bits == 0) {                                                                     \
+            const uint32_t b1 = le[w + 1], b2 = le[w + 2], b3 = le[w + 3], b4 = le[w + 4];      \
+            const int      k = b1 ? 1 : b2 ? 2 : b3 ? 3 : 4;                                    \
+            bits = b1 ? b1 : b2 ? b2 : b3 ? b3 : b4;                                            \
+            w += k;                                                                             \
+        }                                                                                       \
+        int p = (w << 5) + ffs32(bits) - 1;                                                     \
+        bits &= bits - 1;                                                                       \
+        if (p > pe) p = pe;                                                                     \
+        ok = ok && (p > prev + 1);                 /* no empty field, no leading separator */   \
+        if ((f) < 10) ok = ok && (p < pe);         /* fewer than 11 clean fields: scan11 decides */ \
+        sep[f] = p;                                                                             \
+        prev = p;                                                                               \
+    } while (0)
+    PSS_NEXT_SEP(0);                                // end of QNAME
+    {
+        // FLAG .. TLEN are short: their eight separators normally sit within the next 64..96 bytes, so they
+        // are picked out of three mask words held in registers -- straight-line, no loads, no loops.  (A
+        // per-field skip loop would run for a handful of lanes at a time: fields end at random word offsets.)
+        uint32_t m0 = bits, m1 = le[w + 1], m2 = le[w + 2];
 #pragma unroll
-    for (int f = 0; f < 11; f++) {
-        while (bits == 0) {                         // pe's bit is always set; 8 sentinel words follow the data
-            const uint32_t b1 = le[w + 1], b2 = le[w + 2], b3 = le[w + 3], b4 = le[w + 4];   // independent loads
-            const int      k = b1 ? 1 : b2 ? 2 : b3 ? 3 : 4;
-            bits = b1 ? b1 : b2 ? b2 : b3 ? b3 : b4;
-            w += k;
+        for (int f = 1; f <= 8; f++) {
+            const bool     z0 = (m0 == 0u), z1 = (m1 == 0u);
+            const uint32_t x = z0 ? (z1 ? m2 : m1) : m0;
+            const int      base = z0 ? (z1 ? 64 : 32) : 0;
+            ok = ok && (x != 0u);                   // window exhausted: unusually long fields, let scan11 decide
+            int p = (w << 5) + base + ffs32(x) - 1;
+            if (p > pe || x == 0u) p = pe;
+            const uint32_t y = x & (x - 1u);
+            m0 = z0 ? m0 : y;
+            m1 = (z0 && !z1) ? y : m1;
+            m2 = (z0 && z1) ? y : m2;
+            ok = ok && (p > prev + 1) && (p < pe);
+            sep[f] = p;
+            prev = p;
         }
-        int p = (w << 5) + ffs32(bits) - 1;
-        bits &= bits - 1;
-        if (p > pe) p = pe;
-        ok = ok && (p > prev + 1);                 // no empty field, no leading separator
-        if (f < 10) ok = ok && (p < pe);           // fewer than 11 clean fields: let scan11 decide
-        sep[f] = p;
-        prev = p;
+        const bool z0 = (m0 == 0u), z1 = (m1 == 0u);    // cursor for the two long fields
+        bits = z0 ? (z1 ? m2 : m1) : m0;
+        w += z0 ? (z1 ? 2 : 1) : 0;
     }
+    PSS_NEXT_SEP(9);                                // end of SEQ
+    PSS_NEXT_SEP(10);                               // end of QUAL
+#undef PSS_NEXT_SEP
     // separators 1..10 must be '\t', the 11th any white space (or the end of the line)
 #pragma unroll
     for (int f = 0; f < 10; f++) ok = ok && (b(sep[f]) == '\t');

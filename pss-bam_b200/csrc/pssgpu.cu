@@ -343,7 +343,8 @@ int launch_tally(pssgpu_ctx *ctx, const uint8_t *d_sam, size_t len, uint64_t str
     time_begin(ctx, len);
     const int      max_grid = MODE == kModePss ? ctx->tally_grid_pss : ctx->tally_grid_fk;
     const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)max_grid);
-    tally_kernel<MODE><<<grid, kThreads, sizeof(TallySmem), ctx->stream>>>(a);
+    if (MODE == kModeFragkon || ctx->cfg.R + 2 <= 18) tally_kernel<MODE, 9><<<grid, kThreads, sizeof(TallySmem), ctx->stream>>>(a);
+    else tally_kernel<MODE, 16><<<grid, kThreads, sizeof(TallySmem), ctx->stream>>>(a);
     time_end(ctx);
     CU(cudaGetLastError());
     return PSSGPU_OK;
@@ -400,11 +401,12 @@ int pssgpu_init(int device, pssgpu_ctx **out)
     c->sm_count = prop.multiProcessorCount;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tally_kernel<kModePss>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TallySmem));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tally_kernel<kModeFragkon>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TallySmem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tally_kernel<kModePss, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TallySmem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tally_kernel<kModePss, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TallySmem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tally_kernel<kModeFragkon, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TallySmem));
     int occ_p = 0, occ_f = 0;
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, tally_kernel<kModePss>, kThreads, sizeof(TallySmem));
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, tally_kernel<kModeFragkon>, kThreads, sizeof(TallySmem));
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, tally_kernel<kModePss, 16>, kThreads, sizeof(TallySmem));
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, tally_kernel<kModeFragkon, 9>, kThreads, sizeof(TallySmem));
     if (e != cudaSuccess || occ_p < 1 || occ_f < 1) {
         fail(nullptr, PSSGPU_ECUDA, "pssgpu_init: %s (occupancy %d/%d)", cudaGetErrorString(e), occ_p, occ_f);
         if (c->stream) cudaStreamDestroy(c->stream);
