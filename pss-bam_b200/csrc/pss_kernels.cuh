@@ -113,9 +113,11 @@ __global__ void __launch_bounds__(256) pack_kernel(PackArgs A)
 // contigs (genome-kmer-count.c:56-58) -- are skipped (kmer.c:94-96,207-208).
 constexpr int kSpectrumSmemK = 6;     // 4^6 u32 bins = 16 KB privatised per CTA
 
-template <bool SMEM>
+// CT = counter type of the global table: unsigned int while the genome has fewer than 2^32 positions (no bin can
+// overflow; 4^12 bins are then 64 MiB and stay in L2), unsigned long long otherwise.
+template <bool SMEM, typename CT>
 __global__ void __launch_bounds__(256) spectrum_kernel(const uint64_t *__restrict__ groups, uint64_t g_begin, uint64_t g_end,
-                                                       int K, unsigned long long *__restrict__ counts)
+                                                       int K, CT *__restrict__ counts)
 {
     __shared__ uint32_t s_hist[SMEM ? (1 << (2 * kSpectrumSmemK)) : 1];
     const uint32_t n_bins = 1u << (2 * K);
@@ -138,16 +140,21 @@ __global__ void __launch_bounds__(256) spectrum_kernel(const uint64_t *__restric
             const uint32_t w = (uint32_t)(codes >> (2 * o)) & kmask;
             const uint32_t idx = rev_fields32(w) >> (32 - 2 * K);
             if (SMEM) atomicAdd(&s_hist[idx], 1u);
-            else      atomicAdd(counts + idx, 1ull);
+            else      atomicAdd(counts + idx, (CT)1);
         }
     }
     if (SMEM) {
         __syncthreads();
         for (uint32_t i = threadIdx.x; i < n_bins; i += blockDim.x) {
             const uint32_t v = s_hist[i];
-            if (v) atomicAdd(counts + i, (unsigned long long)v);
+            if (v) atomicAdd(counts + i, (CT)v);
         }
     }
+}
+// u32 spectrum -> u64 output
+__global__ void __launch_bounds__(256) widen_kernel(const unsigned int *__restrict__ in, unsigned long long *__restrict__ out, uint64_t n)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) out[i] = in[i];
 }
 
 // ===========================================================================
@@ -253,8 +260,9 @@ struct GlobalAt {                // positions relative to p; nothing before p is
 __device__ __forceinline__ void classify4(uint32_t w, uint32_t &zle, uint32_t &znl)
 {
     zle = ~(((w & 0x7f7f7f7fu) + 0x5f5f5f5fu) | w) & 0x80808080u;
-    const uint32_t y = w ^ 0x0a0a0a0au;
-    znl = ~(((y & 0x7f7f7f7fu) + 0x7f7f7f7fu) | y) & 0x80808080u;
+    // among the flagged bytes (all <= 0x20, so bits 6 and 7 are clear) '\n' is the one whose low six bits equal 0x0a
+    const uint32_t y = (w ^ 0x0a0a0a0au) & 0x3f3f3f3fu;
+    znl = zle & ~(y + 0x7f7f7f7fu);
 }
 // 8 flag bytes (0x80 / 0) in two words -> 8-bit mask << 7, via two byte dot products
 __device__ __forceinline__ uint32_t gather8(uint32_t z0, uint32_t z1)

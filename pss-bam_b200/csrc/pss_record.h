@@ -351,6 +351,22 @@ PSS_HD uint32_t dec4(const B &b, int a, int e, bool &ok)
     ok = ok && all_digits4(t);
     return value4(t);
 }
+// [a, e) must be 1..9 decimal digits (value not needed); anything else clears ok
+template <class B>
+PSS_HD void digits9(const B &b, int a, int e, bool &ok)
+{
+    int L = e - a;
+    ok = ok && (L >= 1) && (L <= 9);
+    if (!ok) L = 1;
+    if (B::kLookBack < 12 && e - 12 < b.lo()) { (void)dec_loop(b, e - L, e, ok); return; }
+    const int      p = e - 12, a0 = p & ~3, drop = 12 - L;
+    const uint32_t sh = 8u * (uint32_t)(p & 3);
+    const uint32_t x0 = b.word(a0), x1 = b.word(a0 + 4), x2 = b.word(a0 + 8), x3 = b.word(a0 + 12);
+    const uint32_t t0 = keep_tail(funnel_r(x0, x1, sh), drop) ^ 0x30303030u;
+    const uint32_t t1 = keep_tail(funnel_r(x1, x2, sh), drop - 4 < 0 ? 0 : drop - 4) ^ 0x30303030u;
+    const uint32_t t2 = keep_tail(funnel_r(x2, x3, sh), drop - 8 < 0 ? 0 : drop - 8) ^ 0x30303030u;
+    ok = ok && all_digits4(t0) && all_digits4(t1) && all_digits4(t2);
+}
 // value of the 1..9 digit field [a, e); anything else clears ok
 template <class B>
 PSS_HD uint32_t dec9(const B &b, int a, int e, bool &ok)
@@ -442,7 +458,7 @@ PSS_HD int split_fast(const B &b, const uint32_t *le, int p0, int pe, RecView &r
     r.flag = dec4(b, sep[0] + 1, sep[1], ok);                               // FLAG %u (more than 4 digits: scan11)
     r.pos = dec9(b, sep[2] + 1, sep[3], ok);                                // POS  %lu
     r.mapq = dec4(b, sep[3] + 1, sep[4], ok);                               // MAPQ %u
-    (void)dec9(b, sep[6] + 1, sep[7], ok);                                  // MPOS %u: never read, must convert cleanly
+    digits9(b, sep[6] + 1, sep[7], ok);                                     // MPOS %u: never read, must convert cleanly
     {                                                                        // TLEN %i
         int a = sep[7] + 1;
         const int e = sep[8];
@@ -450,7 +466,7 @@ PSS_HD int split_fast(const B &b, const uint32_t *le, int p0, int pe, RecView &r
         const bool neg = (c == '-');
         if (c == '-' || c == '+') a++;
         ok = ok && !(e - a > 1 && b(a) == '0');    // a leading 0 would switch glibc to octal / hex
-        const uint32_t v = dec9(b, a, e, ok);
+        const uint32_t v = dec4(b, a, e, ok);      // |TLEN| >= 10000 is left to scan11
         r.tlen = neg ? -(int32_t)v : (int32_t)v;
     }
     if (!ok) return kNeedSlow;

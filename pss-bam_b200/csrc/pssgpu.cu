@@ -698,23 +698,42 @@ int pssgpu_kmer_spectrum_shard_device(pssgpu_ctx *ctx, int k, int shard, int n_s
     if (n_shards < 1 || shard < 0 || shard >= n_shards) return fail(ctx, PSSGPU_EINVAL, "kmer_spectrum: shard %d of %d", shard, n_shards);
     Bind bind(ctx);
     const size_t bins = 1ull << (2 * k);
-    CU(cudaMemsetAsync(d_counts, 0, bins * sizeof(uint64_t), ctx->stream));
     // k-mers are attributed to the group holding their first base; the last
     // two groups are slack/padding and start no k-mer
     const uint64_t usable = ctx->n_groups - 2;
     const uint64_t g0 = usable * (uint64_t)shard / (uint64_t)n_shards;
     const uint64_t g1 = usable * (uint64_t)(shard + 1) / (uint64_t)n_shards;
-    if (g1 > g0) {
-        const unsigned grid = (unsigned)std::min<uint64_t>((g1 - g0 + 255) / 256, (uint64_t)ctx->sm_count * 8);
-        time_begin(ctx, (g1 - g0) * sizeof(uint64_t));
-        if (k <= kSpectrumSmemK)
-            spectrum_kernel<true><<<grid, 256, 0, ctx->stream>>>(ctx->d_groups, g0, g1, k, (unsigned long long *)d_counts);
-        else
-            spectrum_kernel<false><<<grid, 256, 0, ctx->stream>>>(ctx->d_groups, g0, g1, k, (unsigned long long *)d_counts);
-        time_end(ctx);
-        CU(cudaGetLastError());
+    const unsigned grid = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (g1 - g0 + 255) / 256), (uint64_t)ctx->sm_count * 8);
+    // 32-bit bins while no bin can overflow them (fewer than 2^32 positions in the shard)
+    const bool narrow = (g1 - g0) * 16 < 0xffffffffull;
+    unsigned int *d_narrow = nullptr;
+    if (narrow) {
+        CU(cudaMalloc(&d_narrow, bins * sizeof(unsigned int)));
+        cudaError_t e = cudaMemsetAsync(d_narrow, 0, bins * sizeof(unsigned int), ctx->stream);
+        if (e != cudaSuccess) { cudaFree(d_narrow); return fail(ctx, PSSGPU_ECUDA, "kmer_spectrum: %s", cudaGetErrorString(e)); }
+    } else {
+        CU(cudaMemsetAsync(d_counts, 0, bins * sizeof(uint64_t), ctx->stream));
     }
-    CU(cudaStreamSynchronize(ctx->stream));
+    time_begin(ctx, (g1 - g0) * sizeof(uint64_t));
+    if (g1 > g0) {
+        if (narrow) {
+            if (k <= kSpectrumSmemK) spectrum_kernel<true, unsigned int><<<grid, 256, 0, ctx->stream>>>(ctx->d_groups, g0, g1, k, d_narrow);
+            else spectrum_kernel<false, unsigned int><<<grid, 256, 0, ctx->stream>>>(ctx->d_groups, g0, g1, k, d_narrow);
+        } else {
+            if (k <= kSpectrumSmemK) spectrum_kernel<true, unsigned long long><<<grid, 256, 0, ctx->stream>>>(ctx->d_groups, g0, g1, k, (unsigned long long *)d_counts);
+            else spectrum_kernel<false, unsigned long long><<<grid, 256, 0, ctx->stream>>>(ctx->d_groups, g0, g1, k, (unsigned long long *)d_counts);
+        }
+    }
+    if (narrow) {
+        const unsigned wgrid = (unsigned)std::min<uint64_t>((bins + 255) / 256, (uint64_t)ctx->sm_count * 8);
+        widen_kernel<<<wgrid, 256, 0, ctx->stream>>>(d_narrow, (unsigned long long *)d_counts, bins);
+    }
+    time_end(ctx);
+    cudaError_t le = cudaGetLastError();
+    cudaError_t se = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_narrow);
+    if (le != cudaSuccess || se != cudaSuccess)
+        return fail(ctx, PSSGPU_ECUDA, "kmer_spectrum: %s", cudaGetErrorString(le != cudaSuccess ? le : se));
     time_collect(ctx);
     return PSSGPU_OK;
 }
