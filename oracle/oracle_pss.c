@@ -105,6 +105,27 @@ ora_genome *ora_genome_parse(const char *text, size_t len)
     return g;
 }
 
+/* Same genome from contigs already split out of their FASTA text (used for
+ * multi-gigabase test genomes, where formatting and re-parsing FASTA text
+ * would only cost time): bytes are upper-cased like read_fasta does
+ * (fasta-genome-io.c:127) and the contigs sorted by id (:236). */
+ora_genome *ora_genome_from_contigs(const char *const *ids, const char *const *seqs, const size_t *lens, size_t n)
+{
+    ora_genome *g = (ora_genome *)calloc(1, sizeof *g);
+    size_t      i, k;
+    g->ctg = (ora_contig *)malloc((n ? n : 1) * sizeof *g->ctg);
+    g->n = n;
+    for (i = 0; i < n; i++) {
+        g->ctg[i].id = strdup(ids[i]);
+        g->ctg[i].seq = (char *)malloc(lens[i] + 1);
+        for (k = 0; k < lens[i]; k++) g->ctg[i].seq[k] = (char)toupper((unsigned char)seqs[i][k]);
+        g->ctg[i].seq[lens[i]] = '\0';
+        g->ctg[i].len = lens[i];
+    }
+    qsort(g->ctg, g->n, sizeof *g->ctg, contig_cmp);
+    return g;
+}
+
 /* fasta-genome-io.c:6-15 is_gz: name ends in ".gz" */
 static int name_is_gz(const char *fn)
 {

@@ -39,6 +39,8 @@ typedef struct ora_genome {
 ora_genome *ora_genome_load(const char *fasta_path);
 /* Same parse over an in-memory FASTA text. */
 ora_genome *ora_genome_parse(const char *text, size_t len);
+/* Same from contigs already split out of their FASTA text (upper-cases, sorts). */
+ora_genome *ora_genome_from_contigs(const char *const *ids, const char *const *seqs, const size_t *lens, size_t n);
 void        ora_genome_free(ora_genome *g);
 /* fasta-genome-io.c:202-213 find_seq; returns index or -1 */
 long        ora_find_contig(const ora_genome *g, const char *id);

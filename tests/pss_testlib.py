@@ -235,6 +235,8 @@ class Oracle:
             lib.ora_genome_load.argtypes = [C.c_char_p]
             lib.ora_genome_load.restype = C.POINTER(_OraGenome)
             lib.ora_genome_free.argtypes = [C.POINTER(_OraGenome)]
+            lib.ora_genome_from_contigs.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_size_t]
+            lib.ora_genome_from_contigs.restype = C.POINTER(_OraGenome)
             lib.ora_pss_tally.argtypes = [C.POINTER(_OraGenome), C.c_void_p, C.c_size_t, C.POINTER(_OraPssParams),
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(_OraStats)]
             lib.ora_pss_tally.restype = C.c_uint64
@@ -249,9 +251,16 @@ class Oracle:
             cls._lib = lib
         return cls._lib
 
-    def __init__(self, fasta: bytes | None = None, fasta_path: str | None = None):
+    def __init__(self, fasta: bytes | None = None, fasta_path: str | None = None, contigs=None):
+        """fasta: FASTA text; fasta_path: file; contigs: list of (name, np.uint8 array) -- no FASTA round trip."""
         lib = self.lib()
-        if fasta is not None:
+        if contigs is not None:
+            n = len(contigs)
+            ids = (C.c_char_p * n)(*[c[0].encode() for c in contigs])
+            seqs = (C.c_void_p * n)(*[c[1].ctypes.data for c in contigs])
+            lens = (C.c_size_t * n)(*[len(c[1]) for c in contigs])
+            self.g = lib.ora_genome_from_contigs(ids, seqs, lens, n)
+        elif fasta is not None:
             self.g = lib.ora_genome_parse(fasta, len(fasta))
         else:
             self.g = lib.ora_genome_load(fasta_path.encode())
