@@ -73,9 +73,12 @@ static int next_record(blockreader *r, Seq *seq)
     seq->id[i] = '\0';
     while ((c = br_peek(r)) >= 0 && c != '\n') br_skip(r);   /* rest of the header line */
 
-    /* sequence: whole blocks at a time */
+    /* sequence: a line at a time.  The common line (bases only, then '\n') is found with memchr and copied
+     * with a branch-free upper-casing loop the compiler vectorises; lines holding anything else (blanks, '\r',
+     * a '>' in the middle, the 0xFF end marker) take the byte loop. */
     for (;;) {
-        size_t k, lim;
+        size_t avail, seg, k;
+        const unsigned char *p, *nl;
         c = br_peek(r);
         if (c < 0 || c == '>') break;
         if (s.n >= MAX_SEQ_LEN) {                          /* truncate like the reference, then resynchronise */
@@ -83,15 +86,33 @@ static int next_record(blockreader *r, Seq *seq)
             while ((c = br_peek(r)) >= 0 && c != '>') br_skip(r);
             break;
         }
-        lim = r->have - r->at;
-        if (lim > MAX_SEQ_LEN - s.n) lim = MAX_SEQ_LEN - s.n;
-        sb_reserve(&s, lim);
-        for (k = 0; k < lim; k++) {
-            unsigned char b = r->buf[r->at + k];
-            if (b == '>' || b == 0xFF) break;
-            if (!isspace(b)) s.p[s.n++] = (char)toupper(b);
+        p = r->buf + r->at;
+        avail = r->have - r->at;
+        if (avail > MAX_SEQ_LEN - s.n) avail = MAX_SEQ_LEN - s.n;
+        nl = (const unsigned char *)memchr(p, '\n', avail);
+        seg = nl ? (size_t)(nl - p) : avail;
+        sb_reserve(&s, seg);
+        {
+            unsigned odd = 0;                              /* any byte that is not plain sequence? */
+            char *out = s.p + s.n;
+            for (k = 0; k < seg; k++) {
+                const unsigned char ch = p[k];
+                odd |= (unsigned)(ch <= ' ') | (unsigned)(ch == '>') | (unsigned)(ch == 0xFF);
+                out[k] = (char)(ch - (((unsigned char)(ch - 'a') < 26u) << 5));
+            }
+            if (!odd) {
+                s.n += seg;
+                r->at += seg + (nl ? 1 : 0);               /* the newline itself is white space: dropped */
+                continue;
+            }
+        }
+        for (k = 0; k < seg; k++) {                        /* rare line: byte by byte, stop at '>' / 0xFF */
+            const unsigned char ch = p[k];
+            if (ch == '>' || ch == 0xFF) break;
+            if (!isspace(ch)) s.p[s.n++] = (char)toupper(ch);
         }
         r->at += k;
+        if (k == seg && nl) r->at++;
     }
     sb_reserve(&s, 0);
     s.p[s.n] = '\0';
