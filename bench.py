@@ -320,6 +320,14 @@ def main_b200(a):
         ctx.feed_device(dev.data_ptr(), n_bytes)
         ctx.sync()
         fk_ms = ctx.timing()["kernel_ms"]
+        ctx.both_begin(opts, fko)                             # pss-bam + fragkon from one scan (configs[4] workflow)
+        ctx.feed_device(dev.data_ptr(), n_bytes)
+        ctx.sync()
+        ctx.both_begin(opts, fko)
+        ctx.timing_reset(True)
+        ctx.feed_device(dev.data_ptr(), n_bytes)
+        ctx.sync()
+        both_ms = ctx.timing()["kernel_ms"]
         spec = {}
         counts = torch.zeros(1 << 24, dtype=torch.int64, device="cuda")
         for k in (8, 12):
@@ -330,6 +338,8 @@ def main_b200(a):
         ctx.timing_reset(False)
         other = {"fragkon_k8": {"reads_per_s_per_gpu": n_reads / (fk_ms * 1e-3), "sam_gb_per_s_per_gpu": n_bytes / (fk_ms * 1e-3) / 1e9,
                                 "kernel_ms": fk_ms},
+                 "pss_and_fragkon_fused": {"reads_per_s_per_gpu": n_reads / (both_ms * 1e-3), "kernel_ms": both_ms,
+                                           "vs_two_passes": (tm["kernel_ms"] / max(1, int(tm["launches"])) + fk_ms) / both_ms},
                  "genome_kmer_count": {f"k{k}": {"kernel_ms": ms, "gbase_per_s_per_gpu": ginfo["n_bases"] / (ms * 1e-3) / 1e9,
                                                  "bound": "L2 atomics (not HBM)"} for k, ms in spec.items()}}
         del counts

@@ -147,6 +147,7 @@ int pssgpu_pss_finish_device(pssgpu_ctx *ctx, void *d_tables);
 
 int pssgpu_get_stats(pssgpu_ctx *ctx, pssgpu_stats *out);
 
+
 /* ---- fragkon ----------------------------------------------------------------
  * Options of fragkon.c:14-18. */
 typedef struct pssgpu_fragkon_params {
@@ -165,6 +166,16 @@ int  pssgpu_fragkon_begin(pssgpu_ctx *ctx, const pssgpu_fragkon_params *p);
  * (kmer.c:102-104) is applied by the table writer. */
 int  pssgpu_fragkon_finish(pssgpu_ctx *ctx, uint64_t *fp, uint64_t *tp);
 int  pssgpu_fragkon_finish_device(pssgpu_ctx *ctx, void *d_tables /* 2*4^k u64: 5' then 3' */);
+
+/* ---- both tallies from one scan of the text --------------------------------------
+ * pss-bam and fragkon read the same SAM stream with the same parser and differ
+ * only in filters and in what they count (pss-bam.c:390-496 vs fragkon.c:122-216);
+ * running both over one `samtools view` pipe is the usual workflow.  After
+ * pssgpu_both_begin every fed byte updates both table sets; read them with
+ * pssgpu_pss_finish* and pssgpu_fragkon_finish*.  pssgpu_get_stats reports
+ * pss-bam's outcomes, pssgpu_get_fragkon_stats fragkon's. */
+int pssgpu_both_begin(pssgpu_ctx *ctx, const pssgpu_pss_params *pss, const pssgpu_fragkon_params *fragkon);
+int pssgpu_get_fragkon_stats(pssgpu_ctx *ctx, pssgpu_stats *out);
 
 /* ---- genome-kmer-count ---------------------------------------------------------
  * Whole-genome forward-strand k-mer spectrum over every contig

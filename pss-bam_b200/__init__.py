@@ -82,7 +82,7 @@ ABI_SYMBOLS = (
     "pssgpu_cuda_stream", "pssgpu_host_alloc", "pssgpu_host_free",
     "pssgpu_genome_upload", "pssgpu_genome_upload_device", "pssgpu_genome_info",
     "pssgpu_pss_default_params", "pssgpu_pss_begin", "pssgpu_feed", "pssgpu_feed_device", "pssgpu_sync",
-    "pssgpu_pss_finish", "pssgpu_pss_finish_device", "pssgpu_get_stats",
+    "pssgpu_pss_finish", "pssgpu_pss_finish_device", "pssgpu_get_stats", "pssgpu_both_begin", "pssgpu_get_fragkon_stats",
     "pssgpu_fragkon_default_params", "pssgpu_fragkon_begin", "pssgpu_fragkon_finish", "pssgpu_fragkon_finish_device",
     "pssgpu_kmer_spectrum", "pssgpu_kmer_spectrum_shard", "pssgpu_kmer_spectrum_shard_device",
     "pssgpu_timing_reset", "pssgpu_timing_get", "pssgpu_debug_status", "pssgpu_debug_fetch",
@@ -126,6 +126,8 @@ def load_library():
     lib.pssgpu_pss_finish.argtypes = [P, P, P]
     lib.pssgpu_pss_finish_device.argtypes = [P, P]
     lib.pssgpu_get_stats.argtypes = [P, C.POINTER(_Stats)]
+    lib.pssgpu_get_fragkon_stats.argtypes = [P, C.POINTER(_Stats)]
+    lib.pssgpu_both_begin.argtypes = [P, C.POINTER(_PssParams), C.POINTER(_FkParams)]
     lib.pssgpu_fragkon_default_params.argtypes = [C.POINTER(_FkParams)]
     lib.pssgpu_fragkon_default_params.restype = None
     lib.pssgpu_fragkon_begin.argtypes = [P, C.POINTER(_FkParams)]
@@ -247,6 +249,19 @@ class Context:
         p = _FkParams(o.klen, o.min_len, o.max_len, o.min_mq, o.merged_only)
         self._ck(self.lib.pssgpu_fragkon_begin(self.h, C.byref(p)))
         self._mode, self._K = "fragkon", o.klen
+
+    def both_begin(self, o: PssOptions = PssOptions(), f: FragkonOptions = FragkonOptions()):
+        """pss-bam and fragkon tallies from one scan of the text."""
+        self._up, self._down = bytes(o.up_ctx), bytes(o.down_ctx)
+        p = _PssParams(o.region_len, o.min_len, o.max_len, o.min_mq, self._up, self._down, o.merged_only)
+        q = _FkParams(f.klen, f.min_len, f.max_len, f.min_mq, f.merged_only)
+        self._ck(self.lib.pssgpu_both_begin(self.h, C.byref(p), C.byref(q)))
+        self._mode, self._R, self._K = "both", o.region_len, f.klen
+
+    def fragkon_stats(self):
+        s = _Stats()
+        self._ck(self.lib.pssgpu_get_fragkon_stats(self.h, C.byref(s)))
+        return {k: int(getattr(s, k)) for k, _ in _Stats._fields_}
 
     def feed(self, sam, last: bool = False):
         addr, n, keep = _host_view(sam)

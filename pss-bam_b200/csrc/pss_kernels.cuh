@@ -193,9 +193,10 @@ struct ContigCache {
     uint32_t names32[kCacheNames / 4 + kCacheContigs];        // names as zero-padded little-endian words
 };
 
-struct TallyShared {                                          // per-CTA state both tally kernels keep
+struct TallyShared {                                          // per-CTA tables, outcome counters, contig table
     uint32_t table[2 * 32 * 16];                              // CTA count tables [fwd|rev][row][cell]
-    uint32_t stats[8];
+    uint32_t stats[8];                                        // outcomes (pss-bam's in the fused mode)
+    uint32_t stats_fk[8];                                     // fragkon's outcomes in the fused mode
     ContigCache cc;
 };
 
@@ -216,11 +217,13 @@ struct TallyArgs {
     uint64_t       len;
     uint64_t       stream_off;   // offset of sam[0] within everything fed (debug log only)
     DevGenome      g;
-    TallyCfg       cfg;
+    TallyCfg       cfg;          // pss-bam options (fragkon's when only fragkon runs)
+    TallyCfg       cfg_fk;       // fragkon options of the fused mode
     uint32_t       names_bytes;  // total bytes of contig names
     unsigned long long *pss_tables;   // 2*(R+2)*16 u64: fwd then rev
     unsigned long long *fk_hist;      // 2*4^K u64: 5' then 3'
     unsigned long long *stats;        // kStN
+    unsigned long long *stats_fk;     // kStN, fused mode only
     uint64_t           *dbg_off;      // debug log (may be null)
     int8_t             *dbg_code;
     unsigned long long *dbg_n;
@@ -388,7 +391,16 @@ __device__ __noinline__ void long_record(const TallyArgs *Ap, TallyShared *Sp, u
         if (code == kCounted) {
             uint64_t  cb, cl;
             const int ci = lookup_contig(S.cc, A.g, at, r.rname_off, r.rname_len, cb, cl);
-            if (MODE == kModePss) {
+            int code_fk = kFiltered;
+            if (MODE != kModePss) {
+                FkHits h;
+                const TallyCfg &F = (MODE == kModeBoth) ? A.cfg_fk : A.cfg;
+                code_fk = fk_record(at, r, true, ci, cb, cl, A.g, F, h);
+                if (h.add5) atomicAdd(A.fk_hist + h.idx5, 1ull);
+                if (h.add3) atomicAdd(A.fk_hist + (1ull << (2 * F.K)) + h.idx3, 1ull);
+                if (MODE == kModeBoth) atomicAdd(&S.stats_fk[stat_slot(code_fk)], 1u);
+            }
+            if (MODE != kModeFragkon) {
                 PssStreams st;
                 code = pss_record(at, r, true, ci, cb, cl, A.g, A.cfg, st);
                 if (code == kCounted) {
@@ -401,13 +413,13 @@ __device__ __noinline__ void long_record(const TallyArgs *Ap, TallyShared *Sp, u
                     }
                 }
             } else {
-                FkHits h;
-                code = fk_record(at, r, true, ci, cb, cl, A.g, A.cfg, h);
-                if (h.add5) atomicAdd(A.fk_hist + h.idx5, 1ull);
-                if (h.add3) atomicAdd(A.fk_hist + (1ull << (2 * A.cfg.K)) + h.idx3, 1ull);
+                code = code_fk;
             }
+        } else if (MODE == kModeBoth) {
+            atomicAdd(&S.stats_fk[stat_slot(code)], 1u);      // a line that does not parse fails for both programs
         }
         atomicAdd(&S.stats[kStLines], 1u);
+        if (MODE == kModeBoth) atomicAdd(&S.stats_fk[kStLines], 1u);
         atomicAdd(&S.stats[stat_slot(code)], 1u);
         log_outcome(A, c0, code);
         c0 += (uint64_t)L;
@@ -478,7 +490,7 @@ __device__ __forceinline__ void flush_acc(uint32_t (&acc)[NACC], int rows, uint3
 __device__ __forceinline__ void cta_prologue(TallyShared &T, const TallyArgs &A, uint32_t tid, uint32_t nthreads)
 {
     for (uint32_t i = tid; i < 2 * 32 * 16; i += nthreads) T.table[i] = 0;
-    if (tid < 8) T.stats[tid] = 0;
+    if (tid < 8) { T.stats[tid] = 0; T.stats_fk[tid] = 0; }
     const bool fits = A.g.n_contigs <= (uint32_t)kCacheContigs && A.names_bytes <= (uint32_t)kCacheNames && A.g.n_contigs > 0;
     if (fits) {
         for (uint32_t i = tid; i < (uint32_t)kCacheSlots; i += nthreads) T.cc.slot[i] = 0xffu;
@@ -516,7 +528,7 @@ __device__ __forceinline__ void cta_prologue(TallyShared &T, const TallyArgs &A,
 template <int MODE>
 __device__ __forceinline__ void cta_epilogue(const TallyShared &T, const TallyArgs &A, uint32_t tid, uint32_t nthreads, int rows)
 {
-    if (MODE == kModePss) {
+    if (MODE != kModeFragkon) {
         for (uint32_t i = tid; i < 2 * 32 * 16; i += nthreads) {
             const uint32_t v = T.table[i];
             const uint32_t tb = i >> 9, row = (i >> 4) & 31u, cell = i & 15u;
@@ -524,6 +536,7 @@ __device__ __forceinline__ void cta_epilogue(const TallyShared &T, const TallyAr
         }
     }
     if (tid < kStN && T.stats[tid]) atomicAdd(A.stats + tid, (unsigned long long)T.stats[tid]);
+    if (MODE == kModeBoth && tid < kStN && T.stats_fk[tid]) atomicAdd(A.stats_fk + tid, (unsigned long long)T.stats_fk[tid]);
 }
 
 // geometry of one tile: smem position p <-> global offset t0 - kPrefix + p
@@ -643,23 +656,28 @@ __device__ __forceinline__ void process_batch(const TallyArgs &A, TallyShared &T
     uint64_t   cb, cl;
     const int  ci = lookup_contig(T.cc, A.g, at, r.rname_off, valid ? r.rname_len : 0, cb, cl);
     PssStreams st;
-    if (MODE == kModePss) {
+    int        code_fk = code;                                  // fragkon's outcome in the fused mode
+    if (MODE != kModePss) {
+        FkHits          h;
+        const TallyCfg &F = (MODE == kModeBoth) ? A.cfg_fk : A.cfg;
+        const int       rc = fk_record(at, r, valid, ci, cb, cl, A.g, F, h);
+        if (valid) code_fk = rc;
+        if (h.add5) atomicAdd(A.fk_hist + h.idx5, 1ull);
+        if (h.add3) atomicAdd(A.fk_hist + (1ull << (2 * F.K)) + h.idx3, 1ull);
+    }
+    if (MODE != kModeFragkon) {
         const int rc = pss_record(at, r, valid, ci, cb, cl, A.g, A.cfg, st);
         if (valid) code = rc;
     } else {
-        FkHits    h;
-        const int rc = fk_record(at, r, valid, ci, cb, cl, A.g, A.cfg, h);
-        if (valid) code = rc;
-        if (h.add5) atomicAdd(A.fk_hist + h.idx5, 1ull);
-        if (h.add3) atomicAdd(A.fk_hist + (1ull << (2 * A.cfg.K)) + h.idx3, 1ull);
+        code = code_fk;
     }
     if (code < 98) log_outcome(A, goff, code);
     __syncwarp();
-    if (MODE == kModePss) {
+    if (MODE != kModeFragkon) {
         tally_rows(st, acc, rows, lane);
         if (++acc_iters >= kFlushEvery) { flush_acc(acc, rows, lane, T.table); acc_iters = 0; }
     }
-    if (code == 98) { long_record<MODE>(&A, &T, goff); code = 99; }
+    if (code == 98) { long_record<MODE>(&A, &T, goff); code = 99; code_fk = 99; }
     __syncwarp();
     const uint32_t m_any = __ballot_sync(full, code != 99);
     if (m_any) {
@@ -675,6 +693,21 @@ __device__ __forceinline__ void process_batch(const TallyArgs &A, TallyShared &T
             if (m2) atomicAdd(&T.stats[kStFiltered], (uint32_t)__popc(m2));
             if (m3) atomicAdd(&T.stats[kStParseFail], (uint32_t)__popc(m3));
             if (m4) atomicAdd(&T.stats[kStUndefined], (uint32_t)__popc(m4));
+        }
+        if (MODE == kModeBoth) {
+            const uint32_t f0 = __ballot_sync(full, code_fk == kCounted);
+            const uint32_t f1 = __ballot_sync(full, code_fk == kNoContig);
+            const uint32_t f2 = __ballot_sync(full, code_fk == kFiltered);
+            const uint32_t f3 = __ballot_sync(full, code_fk == kParseFail);
+            const uint32_t f4 = __ballot_sync(full, code_fk == kUndefined);
+            if (lane == 0) {
+                atomicAdd(&T.stats_fk[kStLines], (uint32_t)__popc(m_any));
+                if (f0) atomicAdd(&T.stats_fk[kStCounted], (uint32_t)__popc(f0));
+                if (f1) atomicAdd(&T.stats_fk[kStNoContig], (uint32_t)__popc(f1));
+                if (f2) atomicAdd(&T.stats_fk[kStFiltered], (uint32_t)__popc(f2));
+                if (f3) atomicAdd(&T.stats_fk[kStParseFail], (uint32_t)__popc(f3));
+                if (f4) atomicAdd(&T.stats_fk[kStUndefined], (uint32_t)__popc(f4));
+            }
         }
     }
 }
@@ -780,7 +813,7 @@ __global__ void __launch_bounds__(kThreads, PSS_TALLY_CTAS_PER_SM) tally_kernel(
         if (n_nl == 0) __syncthreads();
     }
 
-    if (MODE == kModePss) flush_acc(acc, rows, lane, S.sh.table);
+    if (MODE != kModeFragkon) flush_acc(acc, rows, lane, S.sh.table);
     __syncthreads();
     cta_epilogue<MODE>(S.sh, A, tid, kThreads, rows);
 }

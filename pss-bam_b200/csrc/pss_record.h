@@ -166,7 +166,7 @@ PSS_HD uint64_t rev_fields64(uint64_t x, int n)
 // ---------------------------------------------------------------------------
 // outcomes and options
 // ---------------------------------------------------------------------------
-enum : int { kModePss = 0, kModeFragkon = 1 };
+enum : int { kModePss = 0, kModeFragkon = 1, kModeBoth = 2 };   // kModeBoth: both tallies from one scan of the text
 
 enum : int {          // per-record outcomes (pssgpu.h pssgpu_debug_fetch)
     kCounted = 0, kNoContig = 1, kFiltered = -1, kParseFail = -2, kUndefined = -3,

@@ -56,10 +56,11 @@ struct pssgpu_ctx {
     // tally
     int       mode = -1;
     TallyCfg  cfg{};
+    TallyCfg  cfg_fk{};                       // fragkon options of the fused mode
     unsigned long long *d_tables = nullptr;   // pss: 2*(R+2)*16
     unsigned long long *d_fk = nullptr;       // fragkon: 2*4^K
     size_t    fk_elems = 0;
-    unsigned long long *d_stats = nullptr;    // kStN
+    unsigned long long *d_stats = nullptr;    // 2 x kStN: outcomes, and fragkon's outcomes in the fused mode
     int       tally_grid_pss = 0, tally_grid_fk = 0;
 
     // host feed staging
@@ -331,20 +332,23 @@ int launch_tally(pssgpu_ctx *ctx, const uint8_t *d_sam, size_t len, uint64_t str
     a.sam = d_sam; a.len = len; a.stream_off = stream_off;
     a.g = dev_genome(ctx);
     a.cfg = ctx->cfg;
+    a.cfg_fk = ctx->cfg_fk;
     a.names_bytes = ctx->names_bytes;
     a.pss_tables = ctx->d_tables;
     a.fk_hist = ctx->d_fk;
     a.stats = ctx->d_stats;
+    a.stats_fk = ctx->d_stats + kStN;
     a.dbg_off = ctx->dbg ? ctx->d_dbg_off : nullptr;
     a.dbg_code = ctx->dbg ? ctx->d_dbg_code : nullptr;
     a.dbg_n = ctx->dbg ? ctx->d_dbg_n : nullptr;
     a.dbg_cap = ctx->dbg_cap;
     const uint64_t n_tiles = (len + kTileMain - 1) / kTileMain;
     time_begin(ctx, len);
-    const int      max_grid = MODE == kModePss ? ctx->tally_grid_pss : ctx->tally_grid_fk;
+    const int      max_grid = MODE == kModeFragkon ? ctx->tally_grid_fk : ctx->tally_grid_pss;
     const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)max_grid);
-    if (MODE == kModeFragkon || ctx->cfg.R + 2 <= 18) tally_kernel<MODE, 9><<<grid, kThreads, sizeof(TallySmem), ctx->stream>>>(a);
-    else tally_kernel<MODE, 16><<<grid, kThreads, sizeof(TallySmem), ctx->stream>>>(a);
+    if (MODE == kModeFragkon) tally_kernel<kModeFragkon, 9><<<grid, kThreads, sizeof(TallySmem), ctx->stream>>>(a);
+    else if (ctx->cfg.R + 2 <= 18) tally_kernel<MODE, 9><<<grid, kThreads, sizeof(TallySmem), ctx->stream>>>(a);
+    else tally_kernel<MODE == kModeFragkon ? kModePss : MODE, 16><<<grid, kThreads, sizeof(TallySmem), ctx->stream>>>(a);
     time_end(ctx);
     CU(cudaGetLastError());
     return PSSGPU_OK;
@@ -352,15 +356,16 @@ int launch_tally(pssgpu_ctx *ctx, const uint8_t *d_sam, size_t len, uint64_t str
 
 int launch_tally_mode(pssgpu_ctx *ctx, const uint8_t *d_sam, size_t len, uint64_t stream_off)
 {
-    return ctx->mode == kModePss ? launch_tally<kModePss>(ctx, d_sam, len, stream_off)
-                                 : launch_tally<kModeFragkon>(ctx, d_sam, len, stream_off);
+    return ctx->mode == kModePss  ? launch_tally<kModePss>(ctx, d_sam, len, stream_off)
+         : ctx->mode == kModeBoth ? launch_tally<kModeBoth>(ctx, d_sam, len, stream_off)
+                                  : launch_tally<kModeFragkon>(ctx, d_sam, len, stream_off);
 }
 
 int begin_common(pssgpu_ctx *ctx)
 {
     CU(cudaStreamSynchronize(ctx->stream));
-    if (!ctx->d_stats) CU(cudaMalloc(&ctx->d_stats, kStN * sizeof(unsigned long long)));
-    CU(cudaMemsetAsync(ctx->d_stats, 0, kStN * sizeof(unsigned long long), ctx->stream));
+    if (!ctx->d_stats) CU(cudaMalloc(&ctx->d_stats, 2 * kStN * sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(ctx->d_stats, 0, 2 * kStN * sizeof(unsigned long long), ctx->stream));
     if (ctx->d_dbg_n) CU(cudaMemsetAsync(ctx->d_dbg_n, 0, sizeof(unsigned long long), ctx->stream));
     ctx->carry_len = 0;
     ctx->cur = 0;
@@ -404,6 +409,8 @@ int pssgpu_init(int device, pssgpu_ctx **out)
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tally_kernel<kModePss, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TallySmem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tally_kernel<kModePss, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TallySmem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tally_kernel<kModeFragkon, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TallySmem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tally_kernel<kModeBoth, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TallySmem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tally_kernel<kModeBoth, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TallySmem));
     int occ_p = 0, occ_f = 0;
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, tally_kernel<kModePss, 16>, kThreads, sizeof(TallySmem));
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, tally_kernel<kModeFragkon, 9>, kThreads, sizeof(TallySmem));
@@ -475,34 +482,95 @@ void pssgpu_pss_default_params(pssgpu_pss_params *p)
     p->merged_only = 0;          // :18
 }
 
-int pssgpu_pss_begin(pssgpu_ctx *ctx, const pssgpu_pss_params *p)
+namespace {
+
+int pss_cfg(pssgpu_ctx *ctx, const pssgpu_pss_params *p, TallyCfg &c)
 {
-    if (!ctx || !p) return fail(ctx, PSSGPU_EINVAL, "pss_begin: null argument");
-    if (!ctx->have_genome) return fail(ctx, PSSGPU_ENOGENOME, "pss_begin: no genome resident");
     if (p->region_len < 0 || p->region_len > kMaxRegion)
-        return fail(ctx, PSSGPU_EUNSUPP, "pss_begin: region_len %d outside [0,%d]", p->region_len, kMaxRegion);
-    Bind bind(ctx);
-    TallyCfg c{};
+        return fail(ctx, PSSGPU_EUNSUPP, "region_len %d outside [0,%d]", p->region_len, kMaxRegion);
+    c = TallyCfg{};
     c.mode = kModePss;
     c.R = p->region_len;
     c.min_len = p->min_len;
     c.max_len = p->max_len;
     c.min_mq = (uint32_t)p->min_mq;      // `sp->mapq < MIN_MQ` converts MIN_MQ to unsigned (pss-bam.c:409)
     c.merged_only = p->merged_only ? 1u : 0u;
-    c.K = 0;
     int rc;
     if ((rc = ctx_string(ctx, p->up_ctx, &c.up_mask, &c.up_other, c.up_ctx)) != PSSGPU_OK) return rc;
     if ((rc = ctx_string(ctx, p->down_ctx, &c.down_mask, &c.down_other, c.down_ctx)) != PSSGPU_OK) return rc;
     if ((c.up_other || c.down_other) && ctx->exc_overflow)
-        return fail(ctx, PSSGPU_EUNSUPP, "pss_begin: -U/-D name bytes outside " PSSGPU_SYM_CHARS " and the genome holds more than %llu such bytes",
+        return fail(ctx, PSSGPU_EUNSUPP, "-U/-D name bytes outside " PSSGPU_SYM_CHARS " and the genome holds more than %llu such bytes",
                     (unsigned long long)kExcCap);
-    if ((rc = begin_common(ctx)) != PSSGPU_OK) return rc;
+    return PSSGPU_OK;
+}
+
+int fk_cfg(pssgpu_ctx *ctx, const pssgpu_fragkon_params *p, TallyCfg &c)
+{
+    if (p->klen < 1 || p->klen > kMaxFragK) return fail(ctx, PSSGPU_EUNSUPP, "klen %d outside [1,%d]", p->klen, kMaxFragK);
+    c = TallyCfg{};
+    c.mode = kModeFragkon;
+    c.K = p->klen;
+    c.min_len = p->min_len;
+    c.max_len = p->max_len;
+    c.min_mq = (uint32_t)p->min_mq;
+    c.merged_only = p->merged_only ? 1u : 0u;
+    return PSSGPU_OK;
+}
+
+int alloc_pss_tables(pssgpu_ctx *ctx, int R)
+{
     cudaFree(ctx->d_tables); ctx->d_tables = nullptr;
-    const size_t elems = 2 * (size_t)(c.R + 2) * 16;
+    const size_t elems = 2 * (size_t)(R + 2) * 16;
     CU(cudaMalloc(&ctx->d_tables, elems * sizeof(unsigned long long)));
     CU(cudaMemsetAsync(ctx->d_tables, 0, elems * sizeof(unsigned long long), ctx->stream));
+    return PSSGPU_OK;
+}
+
+int alloc_fk_tables(pssgpu_ctx *ctx, int K)
+{
+    const size_t elems = 2ull << (2 * K);
+    if (elems != ctx->fk_elems) {
+        cudaFree(ctx->d_fk); ctx->d_fk = nullptr; ctx->fk_elems = 0;
+        CU(cudaMalloc(&ctx->d_fk, elems * sizeof(unsigned long long)));
+        ctx->fk_elems = elems;
+    }
+    CU(cudaMemsetAsync(ctx->d_fk, 0, elems * sizeof(unsigned long long), ctx->stream));
+    return PSSGPU_OK;
+}
+
+}  // namespace
+
+int pssgpu_pss_begin(pssgpu_ctx *ctx, const pssgpu_pss_params *p)
+{
+    if (!ctx || !p) return fail(ctx, PSSGPU_EINVAL, "pss_begin: null argument");
+    if (!ctx->have_genome) return fail(ctx, PSSGPU_ENOGENOME, "pss_begin: no genome resident");
+    Bind bind(ctx);
+    TallyCfg c;
+    int rc;
+    if ((rc = pss_cfg(ctx, p, c)) != PSSGPU_OK) return rc;
+    if ((rc = begin_common(ctx)) != PSSGPU_OK) return rc;
+    if ((rc = alloc_pss_tables(ctx, c.R)) != PSSGPU_OK) return rc;
     ctx->cfg = c;
     ctx->mode = kModePss;
+    return PSSGPU_OK;
+}
+
+int pssgpu_both_begin(pssgpu_ctx *ctx, const pssgpu_pss_params *p, const pssgpu_fragkon_params *f)
+{
+    if (!ctx || !p || !f) return fail(ctx, PSSGPU_EINVAL, "both_begin: null argument");
+    if (!ctx->have_genome) return fail(ctx, PSSGPU_ENOGENOME, "both_begin: no genome resident");
+    Bind bind(ctx);
+    TallyCfg c, cf;
+    int rc;
+    if ((rc = pss_cfg(ctx, p, c)) != PSSGPU_OK) return rc;
+    if ((rc = fk_cfg(ctx, f, cf)) != PSSGPU_OK) return rc;
+    if ((rc = begin_common(ctx)) != PSSGPU_OK) return rc;
+    if ((rc = alloc_pss_tables(ctx, c.R)) != PSSGPU_OK) return rc;
+    if ((rc = alloc_fk_tables(ctx, cf.K)) != PSSGPU_OK) return rc;
+    c.mode = kModeBoth;
+    ctx->cfg = c;
+    ctx->cfg_fk = cf;
+    ctx->mode = kModeBoth;
     return PSSGPU_OK;
 }
 
@@ -580,7 +648,7 @@ int pssgpu_sync(pssgpu_ctx *ctx)
 int pssgpu_pss_finish(pssgpu_ctx *ctx, uint64_t *fwd, uint64_t *rev)
 {
     if (!ctx || !fwd || !rev) return fail(ctx, PSSGPU_EINVAL, "pss_finish: null argument");
-    if (ctx->mode != kModePss) return fail(ctx, PSSGPU_EINVAL, "pss_finish: no pss tally open");
+    if (ctx->mode != kModePss && ctx->mode != kModeBoth) return fail(ctx, PSSGPU_EINVAL, "pss_finish: no pss tally open");
     if (ctx->carry_len) return fail(ctx, PSSGPU_EINVAL, "pss_finish: %zu bytes of an unterminated line pending (feed with last=1)", ctx->carry_len);
     Bind bind(ctx);
     const size_t half = (size_t)(ctx->cfg.R + 2) * 16 * sizeof(uint64_t);
@@ -595,7 +663,7 @@ int pssgpu_pss_finish(pssgpu_ctx *ctx, uint64_t *fwd, uint64_t *rev)
 int pssgpu_pss_finish_device(pssgpu_ctx *ctx, void *d_tables)
 {
     if (!ctx || !d_tables) return fail(ctx, PSSGPU_EINVAL, "pss_finish_device: null argument");
-    if (ctx->mode != kModePss) return fail(ctx, PSSGPU_EINVAL, "pss_finish_device: no pss tally open");
+    if (ctx->mode != kModePss && ctx->mode != kModeBoth) return fail(ctx, PSSGPU_EINVAL, "pss_finish_device: no pss tally open");
     if (ctx->carry_len) return fail(ctx, PSSGPU_EINVAL, "pss_finish_device: unterminated line pending");
     Bind bind(ctx);
     const size_t bytes = 2 * (size_t)(ctx->cfg.R + 2) * 16 * sizeof(uint64_t);
@@ -605,13 +673,14 @@ int pssgpu_pss_finish_device(pssgpu_ctx *ctx, void *d_tables)
     return PSSGPU_OK;
 }
 
-int pssgpu_get_stats(pssgpu_ctx *ctx, pssgpu_stats *out)
+namespace {
+int read_stats(pssgpu_ctx *ctx, pssgpu_stats *out, int which)
 {
     if (!ctx || !out) return fail(ctx, PSSGPU_EINVAL, "get_stats: null argument");
     if (!ctx->d_stats) return fail(ctx, PSSGPU_EINVAL, "get_stats: no tally was opened");
     Bind bind(ctx);
     unsigned long long h[kStN];
-    CU(cudaMemcpyAsync(h, ctx->d_stats, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(h, ctx->d_stats + which * kStN, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     time_collect(ctx);
     out->lines = h[kStLines];
@@ -621,6 +690,15 @@ int pssgpu_get_stats(pssgpu_ctx *ctx, pssgpu_stats *out)
     out->parse_fail = h[kStParseFail];
     out->undefined = h[kStUndefined];
     return PSSGPU_OK;
+}
+}  // namespace
+
+int pssgpu_get_stats(pssgpu_ctx *ctx, pssgpu_stats *out) { return read_stats(ctx, out, 0); }
+
+int pssgpu_get_fragkon_stats(pssgpu_ctx *ctx, pssgpu_stats *out)
+{
+    if (ctx && ctx->mode != kModeBoth) return read_stats(ctx, out, 0);      // a fragkon-only tally keeps them in the first set
+    return read_stats(ctx, out, 1);
 }
 
 // ---- fragkon ------------------------------------------------------------------
@@ -638,25 +716,12 @@ int pssgpu_fragkon_begin(pssgpu_ctx *ctx, const pssgpu_fragkon_params *p)
 {
     if (!ctx || !p) return fail(ctx, PSSGPU_EINVAL, "fragkon_begin: null argument");
     if (!ctx->have_genome) return fail(ctx, PSSGPU_ENOGENOME, "fragkon_begin: no genome resident");
-    if (p->klen < 1 || p->klen > kMaxFragK)
-        return fail(ctx, PSSGPU_EUNSUPP, "fragkon_begin: klen %d outside [1,%d]", p->klen, kMaxFragK);
     Bind bind(ctx);
-    TallyCfg c{};
-    c.mode = kModeFragkon;
-    c.K = p->klen;
-    c.min_len = p->min_len;
-    c.max_len = p->max_len;
-    c.min_mq = (uint32_t)p->min_mq;
-    c.merged_only = p->merged_only ? 1u : 0u;
+    TallyCfg c;
     int rc;
+    if ((rc = fk_cfg(ctx, p, c)) != PSSGPU_OK) return rc;
     if ((rc = begin_common(ctx)) != PSSGPU_OK) return rc;
-    const size_t elems = 2ull << (2 * c.K);
-    if (elems != ctx->fk_elems) {
-        cudaFree(ctx->d_fk); ctx->d_fk = nullptr; ctx->fk_elems = 0;
-        CU(cudaMalloc(&ctx->d_fk, elems * sizeof(unsigned long long)));
-        ctx->fk_elems = elems;
-    }
-    CU(cudaMemsetAsync(ctx->d_fk, 0, elems * sizeof(unsigned long long), ctx->stream));
+    if ((rc = alloc_fk_tables(ctx, c.K)) != PSSGPU_OK) return rc;
     ctx->cfg = c;
     ctx->mode = kModeFragkon;
     return PSSGPU_OK;
@@ -665,7 +730,7 @@ int pssgpu_fragkon_begin(pssgpu_ctx *ctx, const pssgpu_fragkon_params *p)
 int pssgpu_fragkon_finish(pssgpu_ctx *ctx, uint64_t *fp, uint64_t *tp)
 {
     if (!ctx || !fp || !tp) return fail(ctx, PSSGPU_EINVAL, "fragkon_finish: null argument");
-    if (ctx->mode != kModeFragkon) return fail(ctx, PSSGPU_EINVAL, "fragkon_finish: no fragkon tally open");
+    if (ctx->mode != kModeFragkon && ctx->mode != kModeBoth) return fail(ctx, PSSGPU_EINVAL, "fragkon_finish: no fragkon tally open");
     if (ctx->carry_len) return fail(ctx, PSSGPU_EINVAL, "fragkon_finish: unterminated line pending (feed with last=1)");
     Bind bind(ctx);
     const size_t half = (ctx->fk_elems / 2) * sizeof(uint64_t);
@@ -680,7 +745,7 @@ int pssgpu_fragkon_finish(pssgpu_ctx *ctx, uint64_t *fp, uint64_t *tp)
 int pssgpu_fragkon_finish_device(pssgpu_ctx *ctx, void *d_out)
 {
     if (!ctx || !d_out) return fail(ctx, PSSGPU_EINVAL, "fragkon_finish_device: null argument");
-    if (ctx->mode != kModeFragkon) return fail(ctx, PSSGPU_EINVAL, "fragkon_finish_device: no fragkon tally open");
+    if (ctx->mode != kModeFragkon && ctx->mode != kModeBoth) return fail(ctx, PSSGPU_EINVAL, "fragkon_finish_device: no fragkon tally open");
     if (ctx->carry_len) return fail(ctx, PSSGPU_EINVAL, "fragkon_finish_device: unterminated line pending");
     Bind bind(ctx);
     CU(cudaMemcpyAsync(d_out, ctx->d_fk, ctx->fk_elems * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));

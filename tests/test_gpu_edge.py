@@ -187,3 +187,25 @@ def test_error_codes(small):
         ctx.pss_finish()
     ctx.feed(b"", last=True)
     ctx.pss_finish()
+
+
+def test_fused_pss_and_fragkon_pass(small):
+    """One scan of the text feeding both programs' tables == the two separate runs (== the oracle)."""
+    g, ora, ctx = small
+    rng = random.Random(5)
+    good = Synth.sam(reads_cfg_config2(seed=31, min_len=20, max_len=90), g, 0, 20000).split(b"\n")[:-1]
+    lines = [_mutate(rng, ln) if rng.random() < 0.2 else ln for ln in good]
+    lines.insert(100, good[0] + b"\tXX:Z:" + b"t" * 5000)                   # a record longer than the look-ahead
+    sam = b"\n".join(lines) + b"\n"
+    for p, fk in ((PssParams(), FkParams(klen=8)),
+                  (PssParams(region_len=20, min_len=30, max_len=80, min_mq=20, merged_only=1), FkParams(klen=5, min_len=25, min_mq=7))):
+        f, r, st = ora.pss(sam, p)
+        fp, tp, fst = ora.fragkon(sam, fk)
+        ctx.both_begin(_opts(p), pkg.FragkonOptions(fk.klen, fk.min_len, fk.max_len, fk.min_mq, fk.merged_only))
+        for i in range(0, len(sam), 300007):
+            ctx.feed(sam[i:i + 300007], last=(i + 300007 >= len(sam)))
+        gf, gr = ctx.pss_finish()
+        gfp, gtp = ctx.fragkon_finish()
+        assert ctx.stats() == st and ctx.fragkon_stats() == fst
+        assert np.array_equal(gf, f) and np.array_equal(gr, r)
+        assert np.array_equal(gfp, fp) and np.array_equal(gtp, tp)
