@@ -126,43 +126,49 @@ def ref_paths():
     return d, os.path.join(d, "pss-bam"), os.path.join(d, "samtools")
 
 
-def run_reference_sample(n_proc, reads_per_proc, genome_mb, seed, repeats=1):
-    """Time the unmodified reference binary on `n_proc` shards in parallel (one single-threaded process each; the
-    reference has no threads).  Returns (reads_per_s, tally_seconds, load_seconds)."""
-    from pss_testlib import Synth, reads_cfg_config2
-    d, exe, shim = ref_paths()
-    if not (os.path.exists(exe) and os.path.exists(shim)):
-        raise FileNotFoundError("oracle/_ref/pss-bam not built (make -C oracle ref needs /root/reference)")
-    nc = 4
-    g = Synth.genome(GENOME_SEED + 1, [genome_mb * 1_000_000 // nc] * nc, n_frac=0.01, lower_frac=0.03)
-    work = tempfile.mkdtemp(prefix="pssbench_ref_")
-    try:
-        with open(os.path.join(work, "genome.fa"), "wb") as f:
+class ReferenceSample:
+    """The unmodified reference binary on a bounded sample: `n_proc` single-threaded processes in parallel (the
+    reference has no threads), each on its own shard of config-2 reads against a `genome_mb` Mb genome.  Files are
+    written once; every run() times one pass; the FASTA load time (same concurrency, empty SAM) is measured once
+    and subtracted, because the B200 arm also starts its clock with the genome resident."""
+
+    def __init__(self, n_proc, reads_per_proc, genome_mb, seed):
+        from pss_testlib import Synth, reads_cfg_config2
+        d, exe, shim = ref_paths()
+        if not (os.path.exists(exe) and os.path.exists(shim)):
+            raise FileNotFoundError("oracle/_ref/pss-bam not built (make -C oracle ref needs /root/reference)")
+        self.exe, self.n_proc, self.reads = exe, n_proc, n_proc * reads_per_proc
+        nc = 4
+        g = Synth.genome(GENOME_SEED + 1, [genome_mb * 1_000_000 // nc] * nc, n_frac=0.01, lower_frac=0.03)
+        self.work = tempfile.mkdtemp(prefix="pssbench_ref_")
+        with open(os.path.join(self.work, "genome.fa"), "wb") as f:
             f.write(g.fasta_bytes())
         cfg = reads_cfg_config2(seed=seed)
         for p in range(n_proc):
-            with open(os.path.join(work, f"shard{p}.sam"), "wb") as f:
+            with open(os.path.join(self.work, f"shard{p}.sam"), "wb") as f:
                 f.write(Synth.sam(cfg, g, p * reads_per_proc, (p + 1) * reads_per_proc))
-        open(os.path.join(work, "empty.sam"), "wb").close()
-        env = dict(os.environ)
-        env["PATH"] = d + os.pathsep + env.get("PATH", "")
+        open(os.path.join(self.work, "empty.sam"), "wb").close()
+        self.env = dict(os.environ)
+        self.env["PATH"] = d + os.pathsep + self.env.get("PATH", "")
+        self.load = min(self._run(["empty.sam"] * n_proc) for _ in range(2))
 
-        def run(sams):
-            t0 = time.perf_counter()
-            ps = [subprocess.Popen([exe, "-F", "genome.fa", "-B", s, "-o", f"out{i}"], cwd=work, env=env,
-                                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for i, s in enumerate(sams)]
-            for p in ps:
-                if p.wait() != 0:
-                    raise RuntimeError("reference pss-bam failed")
-            return time.perf_counter() - t0
+    def _run(self, sams):
+        t0 = time.perf_counter()
+        ps = [subprocess.Popen([self.exe, "-F", "genome.fa", "-B", s, "-o", f"out{i}"], cwd=self.work, env=self.env,
+                               stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for i, s in enumerate(sams)]
+        for p in ps:
+            if p.wait() != 0:
+                raise RuntimeError("reference pss-bam failed")
+        return time.perf_counter() - t0
 
-        load = run(["empty.sam"] * n_proc)                       # FASTA load only (fgetc loop), same concurrency
-        times = [run([f"shard{p}.sam" for p in range(n_proc)]) for _ in range(repeats)]
-        total = min(times)
-        tally = max(total - load, 1e-9)
-        return n_proc * reads_per_proc / tally, tally, load, times
-    finally:
-        shutil.rmtree(work, ignore_errors=True)
+    def run(self):
+        """-> (reads per second, tally seconds) of one pass over all shards."""
+        total = self._run([f"shard{p}.sam" for p in range(self.n_proc)])
+        tally = max(total - self.load, 1e-9)
+        return self.reads / tally, tally
+
+    def close(self):
+        shutil.rmtree(self.work, ignore_errors=True)
 
 
 def main_reference(a):
@@ -172,26 +178,31 @@ def main_reference(a):
     from pss_testlib import Synth
     cores = os.cpu_count() or 1
     Synth.set_threads(cores)                                  # torchrun exports OMP_NUM_THREADS=1
-    per = max(50_000, a.cpu_sample_reads // 4)
+    # bounded: about 1 s of tally per step on every core, so that any --steps/--warmup ends within minutes
+    per = max(20_000, min(a.cpu_sample_reads // 4, 400_000))
     line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "higher_is_better": True, "n_gpus": a.gpus,
             "steps": a.steps, "warmup": a.warmup, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic", "config": {"workload": workload_name(a)}, "gpu_launches": 0}
+    ref = None
     try:
-        vals, secs = [], []
-        for it in range(a.warmup + a.steps):
-            v, tally, load, _ = run_reference_sample(cores, per, a.cpu_genome_mb, READS_SEED + it)
-            if it >= a.warmup:
-                vals.append(v)
-                secs.append(tally)
-        value = statistics.mean(vals)
+        ref = ReferenceSample(cores, per, a.cpu_genome_mb, READS_SEED)
+        for _ in range(a.warmup):
+            ref.run()
+        t0 = time.perf_counter()
+        runs = [ref.run() for _ in range(a.steps)]
+        value = statistics.mean(v for v, _ in runs)
         sample = (f"unmodified reference oracle/_ref/pss-bam (stock Makefile flags -gdwarf-2 -g, no -O), {cores} "
                   f"single-threaded processes in parallel, {per} config-2 reads each on a {a.cpu_genome_mb} Mb 4-contig "
-                  f"genome; FASTA load time (same concurrency, empty SAM) subtracted")
-        line.update({"value": value, "ms_per_step": 1e3 * statistics.mean(secs),
+                  f"genome; FASTA load time ({ref.load:.2f} s at the same concurrency, empty SAM) subtracted from every step")
+        line.update({"value": value, "ms_per_step": 1e3 * statistics.mean(t for _, t in runs),
                      "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
-                     "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
-    except Exception as ex:  # the oracle port is the fallback named by the contract
+                     "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                     "wall_s": time.perf_counter() - t0})
+    except Exception as ex:
         line.update({"unavailable": f"{type(ex).__name__}: {ex}"})
+    finally:
+        if ref:
+            ref.close()
     print(json.dumps(line), flush=True)
 
 
@@ -399,7 +410,10 @@ def main_b200(a):
     }
     if not a.no_cpu_baseline:
         try:
-            v, tally, load, _ = run_reference_sample(1, a.cpu_sample_reads, a.cpu_genome_mb, READS_SEED)
+            ref = ReferenceSample(1, a.cpu_sample_reads, a.cpu_genome_mb, READS_SEED)
+            v, tally = ref.run()
+            load = ref.load
+            ref.close()
             line["cpu_baseline"] = {
                 "value": v, "unit": UNIT, "cores": 1, "kind": "reference",
                 "sample": (f"unmodified reference oracle/_ref/pss-bam (stock flags -gdwarf-2 -g, no -O; single-threaded), "
