@@ -215,17 +215,31 @@ def main_b200(a):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: anything libraries print there (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world != a.gpus:
         if world == 1 and a.gpus > 1:
             raise SystemExit("launch with: python -m torch.distributed.run --nproc-per-node %d bench.py --gpus %d" % (a.gpus, a.gpus))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
     torch.cuda.set_device(local)
+    try:                                                     # host threads and pinned buffers next to this rank's GPU
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+    except Exception:
+        pass
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cores = os.cpu_count() or 1
-    Synth.set_threads(max(1, cores // max(1, world)))      # torchrun exports OMP_NUM_THREADS=1
+    try:
+        mine = len(os.sched_getaffinity(0))
+    except Exception:
+        mine = cores
+    Synth.set_threads(max(1, min(mine, cores // max(1, world))))   # torchrun exports OMP_NUM_THREADS=1
 
     pkg = importlib.import_module("pss-bam_b200")
     ctx = pkg.Context(local)
@@ -423,7 +437,8 @@ def main_b200(a):
         except Exception as ex:
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference",
                                     "sample": f"unavailable: {type(ex).__name__}: {ex}"}
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
