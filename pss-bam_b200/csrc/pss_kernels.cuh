@@ -162,27 +162,29 @@ __global__ void __launch_bounds__(256) widen_kernel(const unsigned int *__restri
 // ===========================================================================
 // tuning knobs (defaults = the measured best; other values are only used by tuning builds)
 #ifndef PSS_TALLY_CTAS_PER_SM
-#define PSS_TALLY_CTAS_PER_SM 4
-#endif
-#ifndef PSS_TILE_MAIN
-#define PSS_TILE_MAIN 32768
+#define PSS_TALLY_CTAS_PER_SM 5
 #endif
 #ifndef PSS_TALLY_THREADS
-#define PSS_TALLY_THREADS 256
+#define PSS_TALLY_THREADS 128
 #endif
-constexpr int kTileMain   = PSS_TILE_MAIN;                            // bytes of SAM a CTA owns per tile
-constexpr int kTileOver   = 2048;                             // look-ahead so the last owned record is whole
-constexpr int kPrefix     = 16;                               // bytes before the tile (is byte -1 a '\n'?)
-constexpr int kTileSpan   = kPrefix + kTileMain + kTileOver;  // 34832 staged bytes
-constexpr int kThreads    = PSS_TALLY_THREADS;
+#ifndef PSS_TALLY_ITERS
+#define PSS_TALLY_ITERS 8
+#endif
+constexpr int kThreads    = PSS_TALLY_THREADS;                // threads per CTA = records a CTA takes per tile
 constexpr int kWarps      = kThreads / 32;
-constexpr int kWords      = (kTileSpan + 31) / 32;                // 32-byte chunks = mask words (1089)
-constexpr int kWordsPerThread = (kWords + kThreads - 1) / kThreads;   // 5
-constexpr int kRecCap     = 1024;                             // records materialised per pass
+constexpr int kIters      = PSS_TALLY_ITERS;                  // 32-byte chunks per thread and tile
+constexpr int kChunks     = kIters * kThreads;                // chunks = mask words of one tile
+constexpr int kSpan       = kChunks * 32;                     // bytes of staged text
+constexpr int kPrefix     = 16;                               // the bulk copy lands at bytes + kPrefix; the byte before the first
+                                                              // record (a '\n') sits in [kPrefix - 1, 2 * kPrefix)
+constexpr int kStageMax   = kSpan - 48;                       // most bytes of one bulk copy: the data always ends below kSpan - 32
+constexpr int kSegs       = kIters * kWarps;                  // warp-iterations of the scan = segments of the newline ranking
 constexpr int kCacheContigs = 64;                             // contig table kept in shared memory when it fits
 constexpr int kCacheNames   = 1024;
 constexpr int kCacheSlots   = 128;
 constexpr int kFlushEvery   = 1900;                           // warp iterations between flushes of the 16-bit partial sums
+static_assert(kThreads % 32 == 0 && kSegs <= 64, "the newline ranking keeps at most two segment counts per lane");
+static_assert(kSpan < (1 << 20) && kThreads <= 1024, "pass A packs a newline position into 20 bits and its rank into the rest");
 
 struct ContigCache {
     uint32_t n;                                               // 0: not cached, use the global table
@@ -201,14 +203,14 @@ struct TallyShared {                                          // per-CTA tables,
 };
 
 struct TallySmem {
-    alignas(128) uint8_t bytes[kWords * 32];                  // staged SAM text
-    uint32_t le[kWords + 8];                                  // bit i of word w: byte 32w+i is <= 0x20
-    uint32_t nl[kWords + 8];                                  //                  byte 32w+i is '\n'
-    uint16_t wpre[kWords + 8];                                // newlines before word w
-    uint16_t nlpos[kRecCap + 4];                              // newline positions of this pass
+    alignas(128) uint8_t bytes[kSpan + 32];                   // staged SAM text (+ slack for word reads past the last record)
+    uint32_t le[kChunks + 8];                                 // bit i of word c: byte 32c+i is <= 0x20; 8 all-ones sentinels
+    uint32_t seg[64];                                         // per segment (one warp-iteration of the scan): which chunks hold a newline
+    uint32_t nlpos[kThreads + 4];                             // positions of the first kThreads + 1 newlines
+    uint32_t warp_sum[kWarps];                                // generic newline listing only
+    uint32_t ctl[2];                                          // range handed to this CTA
+    unsigned long long long_end;                              // where a record longer than the tile ends
     TallyShared sh;
-    uint32_t warp_sum[kWarps];
-    uint32_t n_newlines;
     alignas(8) uint64_t bar;
 };
 
@@ -216,6 +218,9 @@ struct TallyArgs {
     const uint8_t *sam;          // device, 16-byte aligned
     uint64_t       len;
     uint64_t       stream_off;   // offset of sam[0] within everything fed (debug log only)
+    uint64_t       range_bytes;  // the text is handed out in ranges of this many bytes (multiple of 32)
+    unsigned int  *range_ctr;    // next range (zero before the launch)
+    uint32_t       one;          // 1, opaque to the compiler: turns additions into IMADs (FMA pipe) where the ALU pipe is the limit
     DevGenome      g;
     TallyCfg       cfg;          // pss-bam options (fragkon's when only fragkon runs)
     TallyCfg       cfg_fk;       // fragkon options of the fused mode
@@ -259,18 +264,52 @@ struct GlobalAt {                // positions relative to p; nothing before p is
     }
 };
 
-// 0x80 in every byte of w that is <= 0x20 / that is '\n'
-__device__ __forceinline__ void classify4(uint32_t w, uint32_t &zle, uint32_t &znl)
+// LOP3 / IMAD spelled out: the compiler's canonical forms of these expressions cost an extra instruction per word
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c)
 {
-    zle = ~(((w & 0x7f7f7f7fu) + 0x5f5f5f5fu) | w) & 0x80808080u;
-    // among the flagged bytes (all <= 0x20, so bits 6 and 7 are clear) '\n' is the one whose low six bits equal 0x0a
-    const uint32_t y = (w ^ 0x0a0a0a0au) & 0x3f3f3f3fu;
-    znl = zle & ~(y + 0x7f7f7f7fu);
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+    return d;
+}
+__device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// 0x80 in every byte of w that is <= 0x20 / that is '\n'.  Three ALU-pipe and three FMA-pipe instructions per word:
+// `one` is 1 at run time but a kernel argument, so opaque to the compiler: the additions are issued as IMADs (the
+// kernel is bound by the integer ALU pipe, the FMA pipe is otherwise idle).  On the low seven bits v of a byte, bit 7
+// of v + (0x80 - k) says v >= k; a byte is <= 0x20 when its bit 7 is clear and v < 0x21, and '\n' when, in addition,
+// v >= 0x0a and v < 0x0b.
+__device__ __forceinline__ void classify4(uint32_t w, uint32_t one, uint32_t &zle, uint32_t &znl)
+{
+    const uint32_t v = w & 0x7f7f7f7fu;
+    const uint32_t ge21 = imad(v, one, 0x5f5f5f5fu);
+    const uint32_t ge0a = imad(v, one, 0x76767676u);
+    const uint32_t ge0b = imad(v, one, 0x75757575u);
+    zle = lop3<0x02>(ge21, w, 0x80808080u);                             // ~(ge21 | w) & 0x80808080
+    znl = lop3<0x20>(zle, ge0b, ge0a);                                  // zle & ~ge0b & ge0a
 }
 // 8 flag bytes (0x80 / 0) in two words -> 8-bit mask << 7, via two byte dot products
 __device__ __forceinline__ uint32_t gather8(uint32_t z0, uint32_t z1)
 {
     return __dp4a(z1, 0x80402010u, __dp4a(z0, 0x08040201u, 0u));
+}
+// the two mask words of one 32-byte chunk
+__device__ __forceinline__ void classify32(const uint8_t *p, uint32_t one, uint32_t &le32, uint32_t &nl32)
+{
+    const uint4 v0 = *reinterpret_cast<const uint4 *>(p);
+    const uint4 v1 = *reinterpret_cast<const uint4 *>(p + 16);
+    uint32_t zl[8], zn[8];
+    classify4(v0.x, one, zl[0], zn[0]); classify4(v0.y, one, zl[1], zn[1]);
+    classify4(v0.z, one, zl[2], zn[2]); classify4(v0.w, one, zl[3], zn[3]);
+    classify4(v1.x, one, zl[4], zn[4]); classify4(v1.y, one, zl[5], zn[5]);
+    classify4(v1.z, one, zl[6], zn[6]); classify4(v1.w, one, zl[7], zn[7]);
+    // the four 8-bit groups do not overlap: sums instead of ORs, so the shifts ride on IMADs
+    le32 = (gather8(zl[0], zl[1]) >> 7) + gather8(zl[2], zl[3]) * 2u + gather8(zl[4], zl[5]) * 512u + gather8(zl[6], zl[7]) * 131072u;
+    nl32 = (gather8(zn[0], zn[1]) >> 7) + gather8(zn[2], zn[3]) * 2u + gather8(zn[4], zn[5]) * 512u + gather8(zn[6], zn[7]) * 131072u;
 }
 
 __device__ __forceinline__ void log_outcome(const TallyArgs &A, uint64_t goff, int code)
@@ -370,18 +409,20 @@ __device__ __forceinline__ int lookup_contig(const ContigCache &C, const DevGeno
     return ci;
 }
 
-// A record the tile could not hold (longer than the look-ahead, or longer than
-// fgets' 200000-byte buffer): walked from global memory by one thread, split
-// the way fgets(buf, MAX_LINE_LEN+1) splits it (pss-bam.c:761-764), counted
-// with shared-memory atomics.  Rare by construction.
+// A record the tile cannot hold (longer than kStageMax, or longer than fgets'
+// 200000-byte buffer): walked from global memory by one thread, split the way
+// fgets(buf, MAX_LINE_LEN+1) splits it (pss-bam.c:761-764), counted with
+// shared-memory atomics.  Returns the offset of the byte after the record.
+// Rare by construction.
 template <int MODE>
-__device__ __noinline__ void long_record(const TallyArgs *Ap, TallyShared *Sp, uint64_t gstart)
+__device__ __noinline__ uint64_t long_record(const TallyArgs *Ap, TallyShared *Sp, uint64_t gstart)
 {
     const TallyArgs &A = *Ap;
     TallyShared     &S = *Sp;
     uint64_t p = gstart;
     while (p < A.len && __ldg(A.sam + p) != '\n') p++;
     uint64_t total = p - gstart + (p < A.len ? 1u : 0u);
+    const uint64_t g_end = gstart + total;
     uint64_t c0 = gstart;
     while (total > 0) {
         const int L = total > (uint64_t)kMaxLine ? kMaxLine : (int)total;
@@ -425,6 +466,7 @@ __device__ __noinline__ void long_record(const TallyArgs *Ap, TallyShared *Sp, u
         c0 += (uint64_t)L;
         total -= (uint64_t)L;
     }
+    return g_end;
 }
 
 // ballot of "(word & mask) != 0" over the full warp: one LOP3-with-predicate + one VOTE
@@ -483,7 +525,7 @@ __device__ __forceinline__ void flush_acc(uint32_t (&acc)[NACC], int rows, uint3
 }
 
 // ---------------------------------------------------------------------------
-// building blocks shared by the two tally kernels
+// building blocks of the tally kernel
 // ---------------------------------------------------------------------------
 // zero the CTA tables and mirror the contig table into shared memory (24 human
 // chromosomes take < 1 KB).  Called by every thread of the CTA.
@@ -539,101 +581,63 @@ __device__ __forceinline__ void cta_epilogue(const TallyShared &T, const TallyAr
     if (MODE == kModeBoth && tid < kStN && T.stats_fk[tid]) atomicAdd(A.stats_fk + tid, (unsigned long long)T.stats_fk[tid]);
 }
 
-// geometry of one tile: smem position p <-> global offset t0 - kPrefix + p
-struct TileGeo {
-    uint64_t t0;
-    int      data_end;      // first smem position past the data
-    bool     sees_end;      // the staged span reaches the end of the buffer
-};
-__device__ __forceinline__ TileGeo tile_geo(const TallyArgs &A, uint64_t tile)
+// Generic newline listing (a tile in which some 32-byte chunk holds two or more
+// newlines: lines shorter than 32 bytes, never real SAM): every thread walks
+// kIters consecutive chunks, a block scan orders the counts, a second walk
+// stores the first kThreads + 1 positions.  Returns the number of newlines.
+__device__ __noinline__ uint32_t list_newlines_generic(TallySmem *Sp, int n_valid, uint32_t one)
 {
-    TileGeo g;
-    g.t0 = tile * kTileMain;
-    const uint64_t avail = A.len - g.t0;                                       // > 0
-    g.sees_end = avail <= (uint64_t)(kTileMain + kTileOver);
-    g.data_end = kPrefix + (g.sees_end ? (int)avail : kTileMain + kTileOver);
-    return g;
-}
-// one bulk async copy of the tile (plus 16 bytes before it) into `bytes`, completion on `bar`
-__device__ __forceinline__ void stage_tile(const TallyArgs &A, const TileGeo &g, uint8_t *bytes, uint64_t *bar)
-{
-    fence_proxy_async();
-    const uint64_t len16 = (A.len + 15) & ~15ull;
-    const uint64_t src = g.t0 ? g.t0 - kPrefix : 0;
-    uint8_t       *dst = bytes + (g.t0 ? 0 : kPrefix);
-    uint64_t       nb = len16 - src;
-    const uint64_t cap = (uint64_t)kTileSpan - (g.t0 ? 0 : kPrefix);
-    if (nb > cap) nb = cap;
-    mbar_expect_tx(bar, (uint32_t)nb);
-    bulk_g2s(dst, A.sam + src, (uint32_t)nb, bar);
-}
-// phase 1: classify bytes, 32 per thread and step -> one le / nl mask word each
-__device__ __forceinline__ void classify_tile(const uint8_t *bytes, uint32_t *le, uint32_t *nl, const TileGeo &g,
-                                              int first, int stride)
-{
-    for (int w = first; w < kWords; w += stride) {
-        const uint4 v0 = *reinterpret_cast<const uint4 *>(bytes + 32 * w);
-        const uint4 v1 = *reinterpret_cast<const uint4 *>(bytes + 32 * w + 16);
-        uint32_t zl[8], zn[8];
-        classify4(v0.x, zl[0], zn[0]); classify4(v0.y, zl[1], zn[1]);
-        classify4(v0.z, zl[2], zn[2]); classify4(v0.w, zl[3], zn[3]);
-        classify4(v1.x, zl[4], zn[4]); classify4(v1.y, zl[5], zn[5]);
-        classify4(v1.z, zl[6], zn[6]); classify4(v1.w, zl[7], zn[7]);
-        uint32_t le32 = (gather8(zl[0], zl[1]) >> 7) | (gather8(zl[2], zl[3]) << 1)
-                      | (gather8(zl[4], zl[5]) << 9) | (gather8(zl[6], zl[7]) << 17);
-        uint32_t nl32 = (gather8(zn[0], zn[1]) >> 7) | (gather8(zn[2], zn[3]) << 1)
-                      | (gather8(zn[4], zn[5]) << 9) | (gather8(zn[6], zn[7]) << 17);
-        const int lo = 32 * w;
-        if (lo + 32 > g.data_end) {                                            // tail of the data (rare)
-            const uint32_t keep = lo >= g.data_end ? 0u : ((1u << (g.data_end - lo)) - 1u);
-            le32 &= keep;
-            nl32 &= keep;
-            if (g.sees_end && g.data_end >= lo && g.data_end < lo + 32) {      // end of buffer terminates the last line
-                le32 |= 1u << (g.data_end - lo);
-                nl32 |= 1u << (g.data_end - lo);
-            }
-        }
-        le[w] = le32;
-        nl[w] = nl32;
+    TallySmem     &S = *Sp;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, full = 0xffffffffu;
+    const int      c0 = (int)tid * kIters;
+    uint32_t       sum = 0;
+    for (int k = 0; k < kIters; k++) {
+        if (c0 + k >= n_valid) break;
+        uint32_t le32, nl32;
+        classify32(S.bytes + 32 * (c0 + k), one, le32, nl32);
+        sum += (uint32_t)__popc(nl32);
     }
-}
-// newline positions with ordinal in [pass, pass + kRecCap] -> nlpos[]; this thread's words are [w0, w0 + n)
-__device__ __forceinline__ void list_newlines(const uint32_t *nl, const uint16_t *wpre, uint16_t *nlpos, int pass, int w0, int n)
-{
-    for (int k = 0; k < n; k++) {
-        if (w0 + k >= kWords) break;
-        uint32_t bits = nl[w0 + k];
-        int      ord = (int)wpre[w0 + k] - pass;
-        while (bits) {
-            const int bit = __ffs((int)bits) - 1;
-            bits &= bits - 1;
-            if (ord >= 0 && ord <= kRecCap) nlpos[ord] = (uint16_t)((w0 + k) * 32 + bit);
+    uint32_t inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(full, inc, d);
+        if ((int)lane >= d) inc += t;
+    }
+    __syncthreads();                                  // warp_sum is free again
+    if (lane == 31) S.warp_sum[warp] = inc;
+    __syncthreads();
+    uint32_t base = 0, total = 0;
+    for (int w = 0; w < kWarps; w++) {
+        const uint32_t v = S.warp_sum[w];
+        if (w < (int)warp) base += v;
+        total += v;
+    }
+    uint32_t ord = base + inc - sum;
+    for (int k = 0; k < kIters; k++) {
+        if (c0 + k >= n_valid) break;
+        uint32_t le32, nl32;
+        classify32(S.bytes + 32 * (c0 + k), one, le32, nl32);
+        while (nl32) {
+            if (ord <= (uint32_t)kThreads) S.nlpos[ord] = (uint32_t)((c0 + k) * 32 + __ffs((int)nl32) - 1);
+            nl32 &= nl32 - 1u;
             ord++;
         }
     }
+    return total;
 }
 
-// One warp-load of records: record i runs from newline i (exclusive) to
-// newline i+1 of the pass' list.  Parses, filters, gathers, tallies, counts
-// outcomes.  All 32 lanes of the warp must call it together.
+// One warp-load of records: this lane's record is [start, pe) with its
+// terminator at pe (has == false: no record for the lane).  Parses, filters,
+// gathers, tallies, counts outcomes.  All 32 lanes of the warp must call it
+// together.
 template <int MODE, int NACC>
 __device__ __forceinline__ void process_batch(const TallyArgs &A, TallyShared &T, const uint8_t *bytes, const uint32_t *le,
-                                              const uint16_t *nlpos, int i0, int cnt, int pass, int n_nl, const TileGeo &g,
-                                              uint32_t lane, uint32_t (&acc)[NACC], int &acc_iters, int rows)
+                                              bool has, int start, int pe, uint64_t goff,
+                                              uint32_t lane, uint32_t (&acc)[NACC], int &acc_iters, int rows,
+                                              uint32_t &st_acc, uint32_t &st_acc_fk)
 {
     const uint32_t full = 0xffffffffu;
-    const int      i = i0 + (int)lane;
-    int            code = 99;                                           // 99 = no record for this lane
-    uint64_t       goff = 0;
-    int            start = 0, pe = -1;
-    if (i < cnt) {
-        start = (int)nlpos[i] + 1;
-        if (start >= kPrefix && start < kPrefix + kTileMain && start < g.data_end) {
-            goff = g.t0 + (uint64_t)(start - kPrefix);
-            if (pass + i + 1 < n_nl) { pe = (int)nlpos[i + 1]; code = kNeedSlow; }
-            else code = 98;                                             // not whole in this tile
-        }
-    }
+    int            code = has ? (int)kNeedSlow : 99;                    // 99 = no record for this lane
     const SmemAt at{ bytes };
     RecView      r;
     r.flag = 0; r.pos = 0; r.mapq = 0; r.tlen = 0;
@@ -671,53 +675,53 @@ __device__ __forceinline__ void process_batch(const TallyArgs &A, TallyShared &T
     } else {
         code = code_fk;
     }
-    if (code < 98) log_outcome(A, goff, code);
+    if (code != 99) log_outcome(A, goff, code);
     __syncwarp();
     if (MODE != kModeFragkon) {
         tally_rows(st, acc, rows, lane);
         if (++acc_iters >= kFlushEvery) { flush_acc(acc, rows, lane, T.table); acc_iters = 0; }
     }
-    if (code == 98) { long_record<MODE>(&A, &T, goff); code = 99; code_fk = 99; }
-    __syncwarp();
-    const uint32_t m_any = __ballot_sync(full, code != 99);
-    if (m_any) {
+    // outcome counters: lane k (< kStN) keeps counter k of this warp in a register (stats[] order: lines, counted,
+    // no contig, filtered, parse failure, undefined); they reach shared memory once, at the end of the kernel
+    {
+        const uint32_t m_any = __ballot_sync(full, code != 99);
         const uint32_t m0 = __ballot_sync(full, code == kCounted);
         const uint32_t m1 = __ballot_sync(full, code == kNoContig);
         const uint32_t m2 = __ballot_sync(full, code == kFiltered);
         const uint32_t m3 = __ballot_sync(full, code == kParseFail);
         const uint32_t m4 = __ballot_sync(full, code == kUndefined);
-        if (lane == 0) {
-            atomicAdd(&T.stats[kStLines], (uint32_t)__popc(m_any));
-            if (m0) atomicAdd(&T.stats[kStCounted], (uint32_t)__popc(m0));
-            if (m1) atomicAdd(&T.stats[kStNoContig], (uint32_t)__popc(m1));
-            if (m2) atomicAdd(&T.stats[kStFiltered], (uint32_t)__popc(m2));
-            if (m3) atomicAdd(&T.stats[kStParseFail], (uint32_t)__popc(m3));
-            if (m4) atomicAdd(&T.stats[kStUndefined], (uint32_t)__popc(m4));
-        }
+        const uint32_t mine = lane == 0 ? m_any : lane == 1 ? m0 : lane == 2 ? m1 : lane == 3 ? m2 : lane == 4 ? m3 : m4;
+        st_acc += (uint32_t)__popc(mine);
         if (MODE == kModeBoth) {
             const uint32_t f0 = __ballot_sync(full, code_fk == kCounted);
             const uint32_t f1 = __ballot_sync(full, code_fk == kNoContig);
             const uint32_t f2 = __ballot_sync(full, code_fk == kFiltered);
             const uint32_t f3 = __ballot_sync(full, code_fk == kParseFail);
             const uint32_t f4 = __ballot_sync(full, code_fk == kUndefined);
-            if (lane == 0) {
-                atomicAdd(&T.stats_fk[kStLines], (uint32_t)__popc(m_any));
-                if (f0) atomicAdd(&T.stats_fk[kStCounted], (uint32_t)__popc(f0));
-                if (f1) atomicAdd(&T.stats_fk[kStNoContig], (uint32_t)__popc(f1));
-                if (f2) atomicAdd(&T.stats_fk[kStFiltered], (uint32_t)__popc(f2));
-                if (f3) atomicAdd(&T.stats_fk[kStParseFail], (uint32_t)__popc(f3));
-                if (f4) atomicAdd(&T.stats_fk[kStUndefined], (uint32_t)__popc(f4));
-            }
+            const uint32_t mine_fk = lane == 0 ? m_any : lane == 1 ? f0 : lane == 2 ? f1 : lane == 3 ? f2 : lane == 4 ? f3 : f4;
+            st_acc_fk += (uint32_t)__popc(mine_fk);
         }
     }
 }
 
 // ---------------------------------------------------------------------------
-// tally kernel: one tile at a time per CTA, phases separated by block barriers; four CTAs per SM overlap
-// each other's staging, scan and record phases.  (A producer/consumer variant with scan warps and record warps
-// handing tiles over through mbarriers was measured and dropped: the record phase is bound by the latency of one
-// warp-load of records times the number of such loads resident per SM, which shared memory caps at about 20 either
-// way -- profiles/r1_ncu_tally_pipeline_experiment.txt.)
+// tally kernel.
+//
+// The text is handed out in ranges (an atomic counter: a CTA that is done
+// takes the next one); a CTA owns the records that START in its range and
+// walks them in tiles of exactly kThreads records: a tile begins at the byte
+// after the last record of the previous one, so in the record phase every lane
+// of every warp has a record (a fixed 32 KiB tile left a quarter of the lanes
+// idle).  Per tile:
+//   stage     one cp.async.bulk (TMA engine) of as many bytes as kThreads
+//             records are expected to take (running estimate), on an mbarrier
+//   pass A    32 bytes per thread and step: SWAR classification into the
+//             "<= 0x20" mask word (stored, the record phase walks it) and the
+//             newline mask word, which is ranked on the spot with one ballot
+//             and one popcount and kept in a register
+//   pass B    scan of the kSegs ballot counts (two shuffles deep), newline
+//             positions of ordinals 0..kThreads to shared memory
+//   records   one thread per record (process_batch)
 // ---------------------------------------------------------------------------
 // NACC = registers of packed partial sums per lane: 9 cover -r <= 16 (the default is 15), 16 cover -r <= 30
 template <int MODE, int NACC>
@@ -727,98 +731,180 @@ __global__ void __launch_bounds__(kThreads, PSS_TALLY_CTAS_PER_SM) tally_kernel(
     TallySmem &S = *reinterpret_cast<TallySmem *>(smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t full = 0xffffffffu;
+    const uint32_t lt_mask = (1u << lane) - 1u;
 
-    for (uint32_t i = tid; i < 8; i += kThreads) { S.le[kWords + i] = ~0u; S.nl[kWords + i] = 0u; }
+    for (uint32_t i = tid; i < 8; i += kThreads) S.le[kChunks + i] = ~0u;
+    if (tid < kPrefix) S.bytes[tid] = 'x';                    // never written by a copy; byte 15 becomes '\n' at offset 0
     if (tid == 0) { mbar_init(&S.bar, 1); fence_mbar_init(); }
     cta_prologue(S.sh, A, tid, kThreads);
 
-    const uint64_t n_tiles = (A.len + kTileMain - 1) / kTileMain;
     const int      rows = A.cfg.R + 2;
+    const uint32_t one = A.one;
     uint32_t       phase = 0;
     uint32_t       acc[NACC];
     int            acc_iters = 0;
+    uint32_t       st_acc = 0, st_acc_fk = 0;                 // lane k: outcome counter k of this warp
 #pragma unroll
     for (int i = 0; i < NACC; i++) acc[i] = 0;
+    const uint64_t len16 = (A.len + 15) & ~15ull;
+    int            est = kStageMax;                           // bytes the next kThreads records are expected to take
 
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const TileGeo g = tile_geo(A, tile);
-        if (tid == 0) stage_tile(A, g, S.bytes, &S.bar);
-        if (g.t0 == 0 && tid < kPrefix) S.bytes[tid] = '\n';                   // "byte -1" of the stream
-        // one warp sleeps on the mbarrier; the others wait at the block barrier without spending issue slots,
-        // then take their own (immediately successful) acquire of the completed phase
-        if (warp == 0) mbar_wait(&S.bar, phase);
+    for (;;) {
+        // ---- next range ----
+        __syncthreads();                                      // everybody is done with ctl (and with the last tile)
+        if (tid == 0) S.ctl[0] = atomicAdd(A.range_ctr, 1u);
         __syncthreads();
-        if (warp != 0) mbar_wait(&S.bar, phase);
-        phase ^= 1u;
+        const uint64_t range_begin = (uint64_t)S.ctl[0] * A.range_bytes;
+        if (range_begin >= A.len) break;
+        const uint64_t range_end = (range_begin + A.range_bytes < A.len) ? range_begin + A.range_bytes : A.len;
+        uint64_t       pos = range_begin;                     // everything that starts before pos is somebody's business
+        bool           want_full = false;
 
-        classify_tile(S.bytes, S.le, S.nl, g, (int)tid, kThreads);
-        __syncthreads();
-
-        // newlines before each mask word (block scan), and -- fused -- the position list of the first pass
-        {
-            const int w0 = (int)tid * kWordsPerThread;
-            uint32_t  nlw[kWordsPerThread], c[kWordsPerThread], sum = 0;
-#pragma unroll
-            for (int k = 0; k < kWordsPerThread; k++) {
-                nlw[k] = (w0 + k < kWords) ? S.nl[w0 + k] : 0u;
-                c[k] = (uint32_t)__popc(nlw[k]);
-                sum += c[k];
+        while (pos < range_end) {
+            // ---- stage ----
+            const uint64_t gsrc = pos ? ((pos - 1) & ~15ull) : 0;                 // 16-byte aligned source
+            const int64_t  gbase = (int64_t)gsrc - kPrefix;                       // global offset of bytes[0]
+            const int      head = (int)((int64_t)pos - 1 - gbase);                // position of the byte before pos: 15..31
+            int            want = want_full ? kStageMax : est;
+            want = (want + 16) & ~31; want -= 16;                                 // kPrefix + want is a multiple of 32
+            if (want > kStageMax) want = kStageMax;
+            const uint64_t left = len16 - gsrc;
+            const bool     sees_end = left <= (uint64_t)want;                     // the copy reaches the end of the text
+            const int      nb = sees_end ? (int)left : want;
+            const bool     is_full = sees_end || want >= kStageMax;
+            const int      data_end = sees_end ? (int)((int64_t)A.len - gbase) : kPrefix + nb;
+            if (tid == 0) {
+                fence_proxy_async();
+                mbar_expect_tx(&S.bar, (uint32_t)nb);
+                bulk_g2s(S.bytes + kPrefix, A.sam + gsrc, (uint32_t)nb, &S.bar);
             }
-            uint32_t inc = sum;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t t = __shfl_up_sync(full, inc, d);
-                if ((int)lane >= d) inc += t;
-            }
-            if (lane == 31) S.warp_sum[warp] = inc;
+            // one warp sleeps on the mbarrier; the others wait at the block barrier without spending issue slots,
+            // then take their own (immediately successful) acquire of the completed phase
+            if (warp == 0) mbar_wait(&S.bar, phase);
             __syncthreads();
-            uint32_t base = 0;
-            if (warp > 0) {                      // sum of the warps below (<= 7 loads, warp uniform)
-                const uint32_t ws = lane < warp ? S.warp_sum[lane] : 0u;
-                base = __reduce_add_sync(full, ws);
-            }
-            uint32_t run = base + inc - sum;
-#pragma unroll
-            for (int k = 0; k < kWordsPerThread; k++) {
-                if (w0 + k < kWords) S.wpre[w0 + k] = (uint16_t)run;         // only read again by later passes
-                // a 32-byte chunk rarely holds more than one newline: the first one is stored without a branch
-                const uint32_t bits = nlw[k];
-                if (bits != 0u && run <= (uint32_t)kRecCap) S.nlpos[run] = (uint16_t)((w0 + k) * 32 + __ffs((int)bits) - 1);
-                uint32_t rest = bits & (bits - 1u);
-                if (__any_sync(full, rest != 0u)) {
-                    uint32_t ord = run + 1;
-                    while (rest) {
-                        if (ord <= (uint32_t)kRecCap) S.nlpos[ord] = (uint16_t)((w0 + k) * 32 + __ffs((int)rest) - 1);
-                        rest &= rest - 1u;
-                        ord++;
-                    }
-                }
-                run += c[k];
-            }
-            if (tid == kThreads - 1) S.n_newlines = run;
-        }
-        __syncthreads();
-        const int n_nl = (int)S.n_newlines;
+            if (warp != 0) mbar_wait(&S.bar, phase);
+            phase ^= 1u;
 
-        for (int pass = 0; pass < n_nl; pass += kRecCap) {
-            if (pass > 0) {                      // rare: more than kRecCap newlines in one tile
-                list_newlines(S.nl, S.wpre, S.nlpos, pass, (int)tid * kWordsPerThread, kWordsPerThread);
-                __syncthreads();
+            // bytes before the record start / after the end of the text are neutralised by the thread that scans them
+            // (same thread, program order: no barrier).  The end of the buffer terminates the last line.
+            const int tail_chunk = data_end >> 5;
+            const int n_valid = sees_end ? tail_chunk + 1 : (data_end >> 5);      // chunks that hold text
+            if (tid == 0) {
+                S.bytes[kPrefix - 1] = pos == 0 ? '\n' : 'x';
+                for (int i = kPrefix; i < head; i++) S.bytes[i] = 'x';
             }
-            const int cnt = (n_nl - pass) < kRecCap ? (n_nl - pass) : kRecCap;
-            for (int i0 = (int)warp * 32; i0 < cnt; i0 += kThreads)
-                process_batch<MODE, NACC>(A, S.sh, S.bytes, S.le, S.nlpos, i0, cnt, pass, n_nl, g, lane, acc, acc_iters, rows);
-            __syncthreads();             // tile (and nlpos) fully consumed before it is overwritten
+            if (sees_end && tid == (uint32_t)(tail_chunk % kThreads)) {
+                S.bytes[data_end] = '\n';
+                for (int i = data_end + 1; i < 32 * (tail_chunk + 1); i++) S.bytes[i] = 'x';
+            }
+
+            // ---- pass A: classify, rank newlines ----
+            constexpr uint32_t kNoNl = 0xfffffu;              // "this chunk holds no newline"
+            uint32_t pk[kIters];                              // position | rank << 20 of this thread's newline of step it
+            uint32_t multi = 0;
+#pragma unroll
+            for (int it = 0; it < kIters; it++) {
+                pk[it] = kNoNl;
+                if (it * kThreads < n_valid + 8) {            // block-uniform
+                    const int c = it * kThreads + (int)tid;
+                    uint32_t  le32, nl32;
+                    classify32(S.bytes + 32 * c, one, le32, nl32);
+                    if ((it + 1) * kThreads > n_valid) {      // block-uniform: the step that runs over the end of the text
+                        const bool in = c < n_valid;
+                        le32 = in ? le32 : ~0u;               // sentinels: every mask walk ends there
+                        nl32 = in ? nl32 : 0u;
+                    }
+                    S.le[c] = le32;
+                    const uint32_t b = __ballot_sync(full, nl32 != 0u);
+                    multi |= nl32 & (nl32 - 1u);
+                    const uint32_t rank = (uint32_t)__popc(b & lt_mask);
+                    const uint32_t p16 = (uint32_t)(32 * c) + (uint32_t)__ffs((int)nl32) - 1u;
+                    pk[it] = nl32 ? (p16 + (rank << 20)) : kNoNl;
+                    if (lane == 0) S.seg[it * kWarps + (int)warp] = b;
+                } else if (lane == 0) {
+                    S.seg[it * kWarps + (int)warp] = 0u;
+                }
+            }
+            const int any_multi = __syncthreads_or((int)(multi != 0u));
+
+            // ---- pass B: newline ordinals -> positions ----
+            uint32_t n_nl;
+            if (!any_multi) {
+                uint32_t v0 = (lane < (uint32_t)kSegs) ? (uint32_t)__popc(S.seg[lane]) : 0u;
+                uint32_t v1 = (kSegs > 32 && lane + 32 < (uint32_t)kSegs) ? (uint32_t)__popc(S.seg[lane + 32]) : 0u;
+                uint32_t x = v0 | (v1 << 16);
+                uint32_t inc = x;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = __shfl_up_sync(full, inc, d);
+                    if ((int)lane >= d) inc += t;
+                }
+                const uint32_t tot = __shfl_sync(full, inc, 31);
+                const uint32_t ex = inc - x;                   // exclusive, both halves
+                n_nl = (tot & 0xffffu) + (tot >> 16);
+#pragma unroll
+                for (int it = 0; it < kIters; it++) {
+                    const int      s = it * kWarps + (int)warp;
+                    const uint32_t e = __shfl_sync(full, ex, s & 31);
+                    const uint32_t base = (s < 32) ? (e & 0xffffu) : ((tot & 0xffffu) + (e >> 16));
+                    const uint32_t ord = base + (pk[it] >> 20);
+                    if (pk[it] != kNoNl && ord <= (uint32_t)kThreads) S.nlpos[ord] = pk[it] & 0xfffffu;
+                }
+            } else {
+                n_nl = list_newlines_generic(&S, n_valid, one);
+            }
+            __syncthreads();
+
+            // ---- records ----
+            const int n_take = (int)n_nl - 1 < kThreads ? (int)n_nl - 1 : kThreads;     // whole records at hand (may be <= 0)
+            {
+                const bool     in = (int)tid < n_take;
+                const int      start = in ? (int)S.nlpos[tid] + 1 : kPrefix;
+                const int      pe = in ? (int)S.nlpos[tid + 1] : kPrefix;
+                const uint64_t goff = (uint64_t)(gbase + start);
+                const bool     has = in && start < data_end && goff < range_end;
+                if (__any_sync(full, has))
+                    process_batch<MODE, NACC>(A, S.sh, S.bytes, S.le, has, start, pe, goff, lane, acc, acc_iters, rows, st_acc, st_acc_fk);
+            }
+
+            // ---- where the next tile begins (block-uniform: every thread derives it from the same shared data) ----
+            uint64_t next;
+            bool     next_full = false;
+            if (n_nl == 0) {
+                next = (uint64_t)(gbase + data_end);          // no line end in sight yet (only while looking for the first record)
+            } else if (n_take <= 0) {
+                const uint64_t first = (uint64_t)(gbase + (int)S.nlpos[0] + 1);
+                if (first > pos || !is_full) {
+                    next = first; next_full = true;           // stage again from the record start, as much as fits
+                } else {                                       // a record longer than a tile
+                    __syncthreads();
+                    if (tid == 0) S.long_end = (first < range_end) ? long_record<MODE>(&A, &S.sh, first) : first;
+                    __syncthreads();
+                    next = S.long_end;
+                    if (first >= range_end) next = range_end;
+                }
+            } else {
+                const int used = (int)S.nlpos[n_take] - (int)S.nlpos[0];          // bytes of the n_take records
+                next = (uint64_t)(gbase + (int)S.nlpos[n_take] + 1);
+                const float per = (float)used / (float)n_take;
+                int e2 = (int)(per * (float)kThreads * 1.03f) + 768;
+                est = e2 > kStageMax ? kStageMax : e2;
+            }
+            want_full = next_full;
+            pos = next;
+            __syncthreads();                                  // tile (and nlpos) fully consumed before it is overwritten
         }
-        if (n_nl == 0) __syncthreads();
     }
 
     if (MODE != kModeFragkon) flush_acc(acc, rows, lane, S.sh.table);
+    if (lane < (uint32_t)kStN) {
+        if (st_acc) atomicAdd(&S.sh.stats[lane], st_acc);
+        if (MODE == kModeBoth && st_acc_fk) atomicAdd(&S.sh.stats_fk[lane], st_acc_fk);
+    }
     __syncthreads();
     cta_epilogue<MODE>(S.sh, A, tid, kThreads, rows);
 }
 
 static_assert(sizeof(TallySmem) + 1024 <= 232448 / PSS_TALLY_CTAS_PER_SM, "the CTAs of the tally kernel must fit one SM");
-static_assert(kTileSpan < 65536 && kTileSpan % 16 == 0, "newline positions are kept as u16; bulk copies move 16-byte units");
 
 }  // namespace pssgpu

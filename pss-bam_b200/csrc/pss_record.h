@@ -437,8 +437,21 @@ PSS_HD int split_fast(const B &b, const uint32_t *le, int p0, int pe, RecView &r
         bits = z0 ? (z1 ? m2 : m1) : m0;
         w += z0 ? (z1 ? 2 : 1) : 0;
     }
+    // SEQ and QUAL: reads of up to ~150 bases end within the next five mask words; looked at in one go, so that the
+    // lanes of a warp do not loop a different number of times (longer fields fall through to the loop in PSS_NEXT_SEP)
+#define PSS_SKIP5()                                                                             \
+    do {                                                                                        \
+        const uint32_t b1 = le[w + 1], b2 = le[w + 2], b3 = le[w + 3], b4 = le[w + 4], b5 = le[w + 5]; \
+        const bool     h0 = bits != 0u, h1 = b1 != 0u, h2 = b2 != 0u, h3 = b3 != 0u, h4 = b4 != 0u;    \
+        const uint32_t x = h0 ? bits : h1 ? b1 : h2 ? b2 : h3 ? b3 : h4 ? b4 : b5;              \
+        w += h0 ? 0 : h1 ? 1 : h2 ? 2 : h3 ? 3 : h4 ? 4 : 5;                                    \
+        bits = x;                                                                               \
+    } while (0)
+    PSS_SKIP5();
     PSS_NEXT_SEP(9);                                // end of SEQ
+    PSS_SKIP5();
     PSS_NEXT_SEP(10);                               // end of QUAL
+#undef PSS_SKIP5
 #undef PSS_NEXT_SEP
     // separators 1..10 must be '\t', the 11th any white space (or the end of the line)
 #pragma unroll
@@ -553,8 +566,15 @@ PSS_HD bool cigar_is_nM(const B &b, int off, int len, int64_t n)
     bool ok = (len >= 2) && (len <= 10) && (n >= 0);
     if (!ok) len = 2;
     ok = ok && (b(off + len - 1) == 'M') && !(b(off) == '0' && len != 2);
-    // read lengths have at most four digits; longer numbers can only matter for paired records with a huge TLEN
-    const uint32_t v = (len <= 5) ? dec4(b, off, off + len - 1, ok) : dec9(b, off, off + len - 1, ok);
+    if (n >= 10000) {                     // only a paired record with a huge TLEN gets here: a real (rare) branch
+        const uint32_t v = dec9(b, off, off + len - 1, ok);
+        return ok && (int64_t)v == n;
+    }
+    // n has at most four digits and leading zeros are out: a longer CIGAR cannot be "<n>M".  (Records with indels have
+    // longer CIGARs, and they are common: no second, nine-digit parse on their account.)
+    ok = ok && (len <= 5);
+    if (!ok) len = 2;
+    const uint32_t v = dec4(b, off, off + len - 1, ok);
     return ok && (int64_t)v == n;
 }
 

@@ -62,6 +62,7 @@ struct pssgpu_ctx {
     size_t    fk_elems = 0;
     unsigned long long *d_stats = nullptr;    // 2 x kStN: outcomes, and fragkon's outcomes in the fused mode
     int       tally_grid_pss = 0, tally_grid_fk = 0;
+    unsigned int *d_range_ctr = nullptr;      // work counter of the tally kernel (zeroed before every launch)
 
     // host feed staging
     uint8_t  *d_stage[2] = { nullptr, nullptr };
@@ -342,10 +343,19 @@ int launch_tally(pssgpu_ctx *ctx, const uint8_t *d_sam, size_t len, uint64_t str
     a.dbg_code = ctx->dbg ? ctx->d_dbg_code : nullptr;
     a.dbg_n = ctx->dbg ? ctx->d_dbg_n : nullptr;
     a.dbg_cap = ctx->dbg_cap;
-    const uint64_t n_tiles = (len + kTileMain - 1) / kTileMain;
-    time_begin(ctx, len);
     const int      max_grid = MODE == kModeFragkon ? ctx->tally_grid_fk : ctx->tally_grid_pss;
-    const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)max_grid);
+    // ranges handed out by an atomic counter: about eight per CTA on large inputs, never below 128 KiB
+    uint64_t rb = len / ((uint64_t)max_grid * 8u);
+    if (const char *e = getenv("PSSGPU_RANGE_KB")) rb = strtoull(e, nullptr, 10) << 10;
+    else rb = std::min<uint64_t>(std::max<uint64_t>(rb, 128u << 10), 1u << 20);
+    rb = (rb + 31) & ~31ull;
+    const uint64_t n_ranges = (len + rb - 1) / rb;
+    a.range_bytes = rb;
+    a.range_ctr = ctx->d_range_ctr;
+    a.one = 1u;
+    CU(cudaMemsetAsync(ctx->d_range_ctr, 0, sizeof(unsigned int), ctx->stream));
+    time_begin(ctx, len);
+    const unsigned grid = (unsigned)std::min<uint64_t>(n_ranges, (uint64_t)max_grid);
     if (MODE == kModeFragkon) tally_kernel<kModeFragkon, 9><<<grid, kThreads, sizeof(TallySmem), ctx->stream>>>(a);
     else if (ctx->cfg.R + 2 <= 18) tally_kernel<MODE, 9><<<grid, kThreads, sizeof(TallySmem), ctx->stream>>>(a);
     else tally_kernel<MODE == kModeFragkon ? kModePss : MODE, 16><<<grid, kThreads, sizeof(TallySmem), ctx->stream>>>(a);
@@ -365,6 +375,7 @@ int begin_common(pssgpu_ctx *ctx)
 {
     CU(cudaStreamSynchronize(ctx->stream));
     if (!ctx->d_stats) CU(cudaMalloc(&ctx->d_stats, 2 * kStN * sizeof(unsigned long long)));
+    if (!ctx->d_range_ctr) CU(cudaMalloc(&ctx->d_range_ctr, sizeof(unsigned int)));
     CU(cudaMemsetAsync(ctx->d_stats, 0, 2 * kStN * sizeof(unsigned long long), ctx->stream));
     if (ctx->d_dbg_n) CU(cudaMemsetAsync(ctx->d_dbg_n, 0, sizeof(unsigned long long), ctx->stream));
     ctx->carry_len = 0;
@@ -434,7 +445,7 @@ void pssgpu_destroy(pssgpu_ctx *ctx)
     Bind bind(ctx);
     cudaStreamSynchronize(ctx->stream);
     free_genome(ctx);
-    cudaFree(ctx->d_tables); cudaFree(ctx->d_fk); cudaFree(ctx->d_stats);
+    cudaFree(ctx->d_tables); cudaFree(ctx->d_fk); cudaFree(ctx->d_stats); cudaFree(ctx->d_range_ctr);
     cudaFree(ctx->d_stage[0]); cudaFree(ctx->d_stage[1]);
     cudaFree(ctx->d_dbg_off); cudaFree(ctx->d_dbg_code); cudaFree(ctx->d_dbg_n);
     for (auto &p : ctx->ev) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }

@@ -1,0 +1,6 @@
+#!/bin/bash
+# developer tool: build a differently tuned libpssgpu (same ABI) into build/variants/<name>.so;  usage: build_variant.sh name -DPSS_...=...
+set -e
+name=$1; shift
+cd "$(dirname "$0")/../pss-bam_b200/csrc"
+nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --expt-extended-lambda -shared -Xcompiler -fPIC "$@" -o ../../build/variants/$name.so pssgpu.cu

@@ -22,6 +22,7 @@ ap.add_argument("--config", type=int, default=2)
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--mode", default="pss")
 ap.add_argument("--k", type=int, default=8)
+ap.add_argument("--tally-only", action="store_true")
 a = ap.parse_args()
 
 t = time.time()
@@ -55,15 +56,21 @@ for it in range(a.iters):
     ms = tm["kernel_ms"]
     print(f"iter {it}: kernel {ms:.3f} ms  {n / ms / 1e6:.1f} GB/s  {a.reads / ms / 1e6:.3f} G reads/s  launches {tm['launches']}", flush=True)
 print(ctx.stats())
+if a.tally_only:
+    sys.exit(0)
 
 # host-fed (e2e) path
-begin()
-torch.cuda.synchronize()
-t = time.time()
-ctx.feed_ptr(host.data_ptr(), n, last=True)
-ctx.sync()
-dt = time.time() - t
-print(f"host feed (pinned): {dt * 1e3:.1f} ms  {n / dt / 1e9:.2f} GB/s  {a.reads / dt / 1e6:.2f} M reads/s")
+for rep in range(2):
+    begin()
+    ctx.timing_reset(True)
+    torch.cuda.synchronize()
+    t = time.time()
+    ctx.feed_ptr(host.data_ptr(), n, last=True)
+    ctx.sync()
+    dt = time.time() - t
+    tm = ctx.timing()
+    print(f"host feed (pinned): {dt * 1e3:.1f} ms  {n / dt / 1e9:.2f} GB/s  {a.reads / dt / 1e6:.2f} M reads/s  kernels {tm['kernel_ms']:.3f} ms in {tm['launches']} launches")
+    print(ctx.stats())
 
 for k in (8, 12):
     ctx.timing_reset(True)
