@@ -57,6 +57,12 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// L2 prefetch of [src, src + bytes): size multiple of 16, address 16-byte aligned
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src_gmem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
+
 // ===========================================================================
 // K6  genome pack
 // ===========================================================================
@@ -162,18 +168,22 @@ __global__ void __launch_bounds__(256) widen_kernel(const unsigned int *__restri
 // ===========================================================================
 // tuning knobs (defaults = the measured best; other values are only used by tuning builds)
 #ifndef PSS_TALLY_CTAS_PER_SM
-#define PSS_TALLY_CTAS_PER_SM 5
+#define PSS_TALLY_CTAS_PER_SM 2
 #endif
 #ifndef PSS_TALLY_THREADS
-#define PSS_TALLY_THREADS 128
+#define PSS_TALLY_THREADS 256
 #endif
 #ifndef PSS_TALLY_ITERS
-#define PSS_TALLY_ITERS 8
+#define PSS_TALLY_ITERS 4
+#endif
+#ifndef PSS_TALLY_PREFETCH
+#define PSS_TALLY_PREFETCH 1                                  // L2 prefetch of the next tile while the records of this one are processed
 #endif
 constexpr int kThreads    = PSS_TALLY_THREADS;                // threads per CTA = records a CTA takes per tile
 constexpr int kWarps      = kThreads / 32;
-constexpr int kIters      = PSS_TALLY_ITERS;                  // 32-byte chunks per thread and tile
-constexpr int kChunks     = kIters * kThreads;                // chunks = mask words of one tile
+constexpr int kIters      = PSS_TALLY_ITERS;                  // 64-byte slots (two 32-byte chunks) per thread and tile
+constexpr int kSlots      = kIters * kThreads;
+constexpr int kChunks     = 2 * kSlots;                       // chunks = mask words of one tile
 constexpr int kSpan       = kChunks * 32;                     // bytes of staged text
 constexpr int kPrefix     = 16;                               // the bulk copy lands at bytes + kPrefix; the byte before the first
                                                               // record (a '\n') sits in [kPrefix - 1, 2 * kPrefix)
@@ -204,7 +214,7 @@ struct TallyShared {                                          // per-CTA tables,
 
 struct TallySmem {
     alignas(128) uint8_t bytes[kSpan + 32];                   // staged SAM text (+ slack for word reads past the last record)
-    uint32_t le[kChunks + 8];                                 // bit i of word c: byte 32c+i is <= 0x20; 8 all-ones sentinels
+    alignas(8) uint32_t le[kChunks + 8];                      // bit i of word c: byte 32c+i is <= 0x20; 8 all-ones sentinels
     uint32_t seg[64];                                         // per segment (one warp-iteration of the scan): which chunks hold a newline
     uint32_t nlpos[kThreads + 4];                             // positions of the first kThreads + 1 newlines
     uint32_t warp_sum[kWarps];                                // generic newline listing only
@@ -292,6 +302,17 @@ __device__ __forceinline__ void classify4(uint32_t w, uint32_t one, uint32_t &zl
     zle = lop3<0x02>(ge21, w, 0x80808080u);                             // ~(ge21 | w) & 0x80808080
     znl = lop3<0x20>(zle, ge0b, ge0a);                                  // zle & ~ge0b & ge0a
 }
+// The scan's variant: the "<= 0x20" flags as above, and instead of the exact newline flags just bit 1 of every byte
+// (one AND).  '\n' = 0x0a has it, '\t' = 0x09 and ' ' = 0x20 do not: "<= 0x20 and bit 1" finds every newline plus
+// a few control bytes that real text does not contain; pass A checks each candidate against the byte itself and
+// sends a tile with a false one to the exact listing.  Three ALU-pipe + one FMA-pipe instruction per word.
+__device__ __forceinline__ void classify4_fast(uint32_t w, uint32_t one, uint32_t &zle, uint32_t &p1)
+{
+    const uint32_t v = w & 0x7f7f7f7fu;
+    const uint32_t ge21 = imad(v, one, 0x5f5f5f5fu);
+    zle = lop3<0x02>(ge21, w, 0x80808080u);                             // ~(ge21 | w) & 0x80808080
+    p1 = w & 0x02020202u;
+}
 // 8 flag bytes (0x80 / 0) in two words -> 8-bit mask << 7, via two byte dot products
 __device__ __forceinline__ uint32_t gather8(uint32_t z0, uint32_t z1)
 {
@@ -310,6 +331,21 @@ __device__ __forceinline__ void classify32(const uint8_t *p, uint32_t one, uint3
     // the four 8-bit groups do not overlap: sums instead of ORs, so the shifts ride on IMADs
     le32 = (gather8(zl[0], zl[1]) >> 7) + gather8(zl[2], zl[3]) * 2u + gather8(zl[4], zl[5]) * 512u + gather8(zl[6], zl[7]) * 131072u;
     nl32 = (gather8(zn[0], zn[1]) >> 7) + gather8(zn[2], zn[3]) * 2u + gather8(zn[4], zn[5]) * 512u + gather8(zn[6], zn[7]) * 131072u;
+}
+
+// one 32-byte chunk for the scan: "<= 0x20" mask word and newline-candidate mask word
+__device__ __forceinline__ void classify32_fast(const uint4 &v0, const uint4 &v1, uint32_t one, uint32_t &le32, uint32_t &nc32)
+{
+    uint32_t zl[8], zp[8];
+    classify4_fast(v0.x, one, zl[0], zp[0]); classify4_fast(v0.y, one, zl[1], zp[1]);
+    classify4_fast(v0.z, one, zl[2], zp[2]); classify4_fast(v0.w, one, zl[3], zp[3]);
+    classify4_fast(v1.x, one, zl[4], zp[4]); classify4_fast(v1.y, one, zl[5], zp[5]);
+    classify4_fast(v1.z, one, zl[6], zp[6]); classify4_fast(v1.w, one, zl[7], zp[7]);
+    le32 = (gather8(zl[0], zl[1]) >> 7) + gather8(zl[2], zl[3]) * 2u + gather8(zl[4], zl[5]) * 512u + gather8(zl[6], zl[7]) * 131072u;
+    // plane flags are 0x02, not 0x80: the same dot products give the mask << 1
+    const uint32_t p32 = (gather8(zp[0], zp[1]) >> 1) + gather8(zp[2], zp[3]) * 128u + gather8(zp[4], zp[5]) * 32768u
+                       + gather8(zp[6], zp[7]) * 8388608u;
+    nc32 = le32 & p32;
 }
 
 __device__ __forceinline__ void log_outcome(const TallyArgs &A, uint64_t goff, int code)
@@ -583,15 +619,15 @@ __device__ __forceinline__ void cta_epilogue(const TallyShared &T, const TallyAr
 
 // Generic newline listing (a tile in which some 32-byte chunk holds two or more
 // newlines: lines shorter than 32 bytes, never real SAM): every thread walks
-// kIters consecutive chunks, a block scan orders the counts, a second walk
+// 2 * kIters consecutive chunks, a block scan orders the counts, a second walk
 // stores the first kThreads + 1 positions.  Returns the number of newlines.
 __device__ __noinline__ uint32_t list_newlines_generic(TallySmem *Sp, int n_valid, uint32_t one)
 {
     TallySmem     &S = *Sp;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, full = 0xffffffffu;
-    const int      c0 = (int)tid * kIters;
+    const int      c0 = (int)tid * 2 * kIters;
     uint32_t       sum = 0;
-    for (int k = 0; k < kIters; k++) {
+    for (int k = 0; k < 2 * kIters; k++) {
         if (c0 + k >= n_valid) break;
         uint32_t le32, nl32;
         classify32(S.bytes + 32 * (c0 + k), one, le32, nl32);
@@ -613,7 +649,7 @@ __device__ __noinline__ uint32_t list_newlines_generic(TallySmem *Sp, int n_vali
         total += v;
     }
     uint32_t ord = base + inc - sum;
-    for (int k = 0; k < kIters; k++) {
+    for (int k = 0; k < 2 * kIters; k++) {
         if (c0 + k >= n_valid) break;
         uint32_t le32, nl32;
         classify32(S.bytes + 32 * (c0 + k), one, le32, nl32);
@@ -793,39 +829,46 @@ __global__ void __launch_bounds__(kThreads, PSS_TALLY_CTAS_PER_SM) tally_kernel(
                 S.bytes[kPrefix - 1] = pos == 0 ? '\n' : 'x';
                 for (int i = kPrefix; i < head; i++) S.bytes[i] = 'x';
             }
-            if (sees_end && tid == (uint32_t)(tail_chunk % kThreads)) {
+            if (sees_end && tid == (uint32_t)((tail_chunk >> 1) % kThreads)) {   // the thread that scans this chunk
                 S.bytes[data_end] = '\n';
                 for (int i = data_end + 1; i < 32 * (tail_chunk + 1); i++) S.bytes[i] = 'x';
             }
 
             // ---- pass A: classify, rank newlines ----
-            constexpr uint32_t kNoNl = 0xfffffu;              // "this chunk holds no newline"
+            constexpr uint32_t kNoNl = 0xfffffu;              // "this slot holds no newline"
             uint32_t pk[kIters];                              // position | rank << 20 of this thread's newline of step it
-            uint32_t multi = 0;
+            uint32_t redo = 0;                                // a slot with two newlines, or a false candidate: exact listing
 #pragma unroll
             for (int it = 0; it < kIters; it++) {
                 pk[it] = kNoNl;
-                if (it * kThreads < n_valid + 8) {            // block-uniform
-                    const int c = it * kThreads + (int)tid;
-                    uint32_t  le32, nl32;
-                    classify32(S.bytes + 32 * c, one, le32, nl32);
-                    if ((it + 1) * kThreads > n_valid) {      // block-uniform: the step that runs over the end of the text
-                        const bool in = c < n_valid;
-                        le32 = in ? le32 : ~0u;               // sentinels: every mask walk ends there
-                        nl32 = in ? nl32 : 0u;
+                if (it * 2 * kThreads < n_valid + 8) {        // block-uniform
+                    const int      c = 2 * (it * kThreads + (int)tid);           // this thread's two chunks: c, c + 1
+                    const uint8_t *src = S.bytes + 32 * c;
+                    const uint4    q0 = *reinterpret_cast<const uint4 *>(src), q1 = *reinterpret_cast<const uint4 *>(src + 16);
+                    const uint4    q2 = *reinterpret_cast<const uint4 *>(src + 32), q3 = *reinterpret_cast<const uint4 *>(src + 48);
+                    uint32_t le_a, nc_a, le_b, nc_b;
+                    classify32_fast(q0, q1, one, le_a, nc_a);
+                    classify32_fast(q2, q3, one, le_b, nc_b);
+                    if ((it + 1) * 2 * kThreads > n_valid) {  // block-uniform: the step that runs over the end of the text
+                        const bool in_a = c < n_valid, in_b = c + 1 < n_valid;
+                        le_a = in_a ? le_a : ~0u;  nc_a = in_a ? nc_a : 0u;       // sentinels: every mask walk ends there
+                        le_b = in_b ? le_b : ~0u;  nc_b = in_b ? nc_b : 0u;
                     }
-                    S.le[c] = le32;
-                    const uint32_t b = __ballot_sync(full, nl32 != 0u);
-                    multi |= nl32 & (nl32 - 1u);
+                    *reinterpret_cast<uint2 *>(&S.le[c]) = make_uint2(le_a, le_b);
+                    const bool     has = (nc_a | nc_b) != 0u;
+                    const uint32_t b = __ballot_sync(full, has);
                     const uint32_t rank = (uint32_t)__popc(b & lt_mask);
-                    const uint32_t p16 = (uint32_t)(32 * c) + (uint32_t)__ffs((int)nl32) - 1u;
-                    pk[it] = nl32 ? (p16 + (rank << 20)) : kNoNl;
+                    const uint32_t x = nc_a ? nc_a : nc_b;
+                    const uint32_t p = (uint32_t)(32 * c) + (nc_a ? 0u : 32u) + (uint32_t)__ffs((int)x) - 1u;
+                    // exactly one candidate in the slot, and it is a '\n'
+                    redo |= (x & (x - 1u)) | (nc_a ? nc_b : 0u) | (has ? ((uint32_t)S.bytes[has ? p : 0u] ^ 0x0au) : 0u);
+                    pk[it] = has ? (p + (rank << 20)) : kNoNl;
                     if (lane == 0) S.seg[it * kWarps + (int)warp] = b;
                 } else if (lane == 0) {
                     S.seg[it * kWarps + (int)warp] = 0u;
                 }
             }
-            const int any_multi = __syncthreads_or((int)(multi != 0u));
+            const int any_multi = __syncthreads_or((int)(redo != 0u));
 
             // ---- pass B: newline ordinals -> positions ----
             uint32_t n_nl;
@@ -847,27 +890,19 @@ __global__ void __launch_bounds__(kThreads, PSS_TALLY_CTAS_PER_SM) tally_kernel(
                     const int      s = it * kWarps + (int)warp;
                     const uint32_t e = __shfl_sync(full, ex, s & 31);
                     const uint32_t base = (s < 32) ? (e & 0xffffu) : ((tot & 0xffffu) + (e >> 16));
-                    const uint32_t ord = base + (pk[it] >> 20);
-                    if (pk[it] != kNoNl && ord <= (uint32_t)kThreads) S.nlpos[ord] = pk[it] & 0xfffffu;
+                    const uint32_t v = pk[it];
+                    const uint32_t ord = base + (v >> 20);
+                    if (v != kNoNl && ord <= (uint32_t)kThreads) S.nlpos[ord] = v & 0xfffffu;
                 }
             } else {
                 n_nl = list_newlines_generic(&S, n_valid, one);
             }
             __syncthreads();
 
-            // ---- records ----
             const int n_take = (int)n_nl - 1 < kThreads ? (int)n_nl - 1 : kThreads;     // whole records at hand (may be <= 0)
-            {
-                const bool     in = (int)tid < n_take;
-                const int      start = in ? (int)S.nlpos[tid] + 1 : kPrefix;
-                const int      pe = in ? (int)S.nlpos[tid + 1] : kPrefix;
-                const uint64_t goff = (uint64_t)(gbase + start);
-                const bool     has = in && start < data_end && goff < range_end;
-                if (__any_sync(full, has))
-                    process_batch<MODE, NACC>(A, S.sh, S.bytes, S.le, has, start, pe, goff, lane, acc, acc_iters, rows, st_acc, st_acc_fk);
-            }
 
-            // ---- where the next tile begins (block-uniform: every thread derives it from the same shared data) ----
+            // ---- where the next tile begins (block-uniform: every thread derives it from the same shared data);
+            //      known before the records are looked at, so its first bytes can be on their way to L2 meanwhile ----
             uint64_t next;
             bool     next_full = false;
             if (n_nl == 0) {
@@ -889,7 +924,24 @@ __global__ void __launch_bounds__(kThreads, PSS_TALLY_CTAS_PER_SM) tally_kernel(
                 const float per = (float)used / (float)n_take;
                 int e2 = (int)(per * (float)kThreads * 1.03f) + 768;
                 est = e2 > kStageMax ? kStageMax : e2;
+                if (PSS_TALLY_PREFETCH && tid == 0 && next < range_end) {
+                    const uint64_t nsrc = (next - 1) & ~15ull;
+                    const uint64_t nleft = len16 - nsrc;
+                    const uint32_t nbytes = nleft < (uint64_t)est ? (uint32_t)nleft : (uint32_t)(est & ~15);
+                    bulk_prefetch_l2(A.sam + nsrc, nbytes);
+                }
             }
+            // ---- records ----
+            {
+                const bool     in = (int)tid < n_take;
+                const int      start = in ? (int)S.nlpos[tid] + 1 : kPrefix;
+                const int      pe = in ? (int)S.nlpos[tid + 1] : kPrefix;
+                const uint64_t goff = (uint64_t)(gbase + start);
+                const bool     has = in && start < data_end && goff < range_end;
+                if (__any_sync(full, has))
+                    process_batch<MODE, NACC>(A, S.sh, S.bytes, S.le, has, start, pe, goff, lane, acc, acc_iters, rows, st_acc, st_acc_fk);
+            }
+
             want_full = next_full;
             pos = next;
             __syncthreads();                                  // tile (and nlpos) fully consumed before it is overwritten

@@ -192,6 +192,7 @@ struct TallyCfg {
     uint32_t up_other, down_other;      // ctx string holds bytes outside the 15 named symbols
     char     up_ctx[kMaxCtxChars], down_ctx[kMaxCtxChars];
     int      K;
+    uint32_t zero;                      // 0, but a run-time value: see fetch_window()
 };
 
 // one SAM line after the 11 conversions of sam-parse.c:36-48 (offsets are
@@ -513,21 +514,41 @@ PSS_HD int find_contig(const DevGenome &g, const B &b, int off, int len)
 }
 
 // n_fields (<= 32) symbols starting at global base index gb: 2-bit codes and
-// 2-bit classes, field j at bits 2j.
-PSS_HD void load_window(const DevGenome &g, uint64_t gb, int n_fields, uint64_t &codes, uint64_t &classes)
+// 2-bit classes, field j at bits 2j.  In two steps: fetch_window() issues the
+// loads (HBM latency, a random 32-byte sector or two), window_fields() shifts
+// the symbols into place.  `late` must be 0; the caller derives it from values
+// it computes after the fetch (the decoded read bases), which keeps the
+// compiler from scheduling the first use of the loaded words -- where a warp
+// waits for HBM -- ahead of that work.
+struct RawWindow {
+    uint64_t g0, g1, g2;
+    uint32_t sh;
+};
+PSS_HD RawWindow fetch_window(const DevGenome &g, uint64_t gb, int n_fields)
 {
+    RawWindow w;
     const uint64_t gi = gb >> 4;
-    const uint32_t o = (uint32_t)(gb & 15u), sh = 2 * o;
-    const uint64_t g0 = g.groups[gi];
-    const uint64_t g1 = g.groups[gi + 1];
-    const uint64_t g2 = (o + (uint32_t)n_fields > 32u) ? g.groups[gi + 2] : 0ull;
-    const uint32_t c_lo = funnel_r((uint32_t)g0, (uint32_t)g1, sh);
-    const uint32_t c_hi = funnel_r((uint32_t)g1, (uint32_t)g2, sh);
-    const uint32_t k_lo = funnel_r((uint32_t)(g0 >> 32), (uint32_t)(g1 >> 32), sh);
-    const uint32_t k_hi = funnel_r((uint32_t)(g1 >> 32), (uint32_t)(g2 >> 32), sh);
+    const uint32_t o = (uint32_t)(gb & 15u);
+    w.sh = 2 * o;
+    w.g0 = g.groups[gi];
+    w.g1 = g.groups[gi + 1];
+    w.g2 = (o + (uint32_t)n_fields > 32u) ? g.groups[gi + 2] : 0ull;
+    return w;
+}
+PSS_HD void window_fields(const RawWindow &w, int n_fields, uint32_t late, uint64_t &codes, uint64_t &classes)
+{
+    const uint32_t sh = w.sh | late;
+    const uint32_t c_lo = funnel_r((uint32_t)w.g0, (uint32_t)w.g1, sh);
+    const uint32_t c_hi = funnel_r((uint32_t)w.g1, (uint32_t)w.g2, sh);
+    const uint32_t k_lo = funnel_r((uint32_t)(w.g0 >> 32), (uint32_t)(w.g1 >> 32), sh);
+    const uint32_t k_hi = funnel_r((uint32_t)(w.g1 >> 32), (uint32_t)(w.g2 >> 32), sh);
     const uint64_t m = low_fields_mask(n_fields);
     codes   = (((uint64_t)c_hi << 32) | c_lo) & m;
     classes = (((uint64_t)k_hi << 32) | k_lo) & m;
+}
+PSS_HD void load_window(const DevGenome &g, uint64_t gb, int n_fields, uint64_t &codes, uint64_t &classes)
+{
+    window_fields(fetch_window(g, gb, n_fields), n_fields, 0u, codes, classes);
 }
 
 // the byte behind an "other" symbol (binary search in the exception list)
@@ -676,8 +697,8 @@ PSS_HD int pss_record(const B &b, const RecView &r, bool valid, int ci, uint64_t
     // the two windows leave for HBM before the rest of the record is looked at
     const int W = R + 2;
     uint64_t lc, lk, rc, rk;
-    load_window(g, live ? ctg_base + (uint64_t)(s - 2) : (uint64_t)kPadBases, W, lc, lk);             // g[0 .. W)
-    load_window(g, live ? ctg_base + (uint64_t)(e + 2 - (W - 1)) : (uint64_t)kPadBases, W, rc, rk);   // g[n+3-(W-1) .. n+3]
+    const RawWindow lw = fetch_window(g, live ? ctg_base + (uint64_t)(s - 2) : (uint64_t)kPadBases, W);             // g[0 .. W)
+    const RawWindow rw = fetch_window(g, live ? ctg_base + (uint64_t)(e + 2 - (W - 1)) : (uint64_t)kPadBases, W);   // g[n+3-(W-1) .. n+3]
 
     PSS_DROP(!cigar_is_nM(b, r.cigar_off, r.cigar_len, n), kFiltered);      // :411
     // paired: n comes from TLEN; with a shorter SEQ the reference reads bytes
@@ -695,6 +716,11 @@ PSS_HD int pss_record(const B &b, const RecView &r, bool valid, int ci, uint64_t
     const uint64_t m = low_fields_mask(W);
     pre = (pre << 4) & m;  pre_bad = (pre_bad << 4) & m;
     suf = (suf << 4) & m;  suf_bad = (suf_bad << 4) & m;
+
+    // the genome windows are first touched here, after the read has been decoded (P.zero is 0)
+    const uint32_t late = ((uint32_t)pre ^ (uint32_t)suf ^ (uint32_t)pre_bad ^ (uint32_t)suf_bad) & P.zero;
+    window_fields(lw, W, late, lc, lk);
+    window_fields(rw, W, late, rc, rk);
 
     rc = rev_fields64(rc, W);                                               // row j <-> g[n+3-j]
     rk = rev_fields64(rk, W);

@@ -98,6 +98,25 @@ def test_malformed_lines(small):
         _check(ctx, ora, b"\n".join(lines) + b"\n", fk=FkParams(klen=7))
 
 
+def test_control_bytes_that_look_like_newlines(small):
+    """The scan takes "<= 0x20 with bit 1 set" as a newline candidate and verifies it against the byte: VT, 0x02,
+    0x0e ... must send their tile to the exact listing, never split a line."""
+    g, ora, ctx = small
+    good = Synth.sam(reads_cfg_config2(seed=31, min_len=30, max_len=150), g, 0, 6000).split(b"\n")[:-1]
+    rng = random.Random(17)
+    odd = [0x02, 0x03, 0x06, 0x07, 0x0b, 0x0e, 0x0f, 0x12, 0x16, 0x1a, 0x1e, 0x1f, 0x0c, 0x0d, 0x01, 0x08, 0x20]
+    lines = []
+    for i, ln in enumerate(good):
+        if 1500 <= i < 4500 and rng.random() < 0.04:          # the first and last tiles stay clean (fast path)
+            b = bytearray(ln)
+            for _ in range(rng.choice([1, 1, 2])):
+                b[rng.randrange(len(b))] = rng.choice(odd)
+            ln = bytes(b)
+        lines.append(ln)
+    _check(ctx, ora, b"\n".join(lines) + b"\n", fk=FkParams(klen=6))
+    _check(ctx, ora, b"\r\n".join(lines[:2000]) + b"\r\n")        # CRLF text
+
+
 def test_exotic_context_bytes(small):
     g, ora, ctx = small
     sam = Synth.sam(reads_cfg_config1(seed=9, read_len=40), g, 0, 200).split(b"\n")[:-1]
