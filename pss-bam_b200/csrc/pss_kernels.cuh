@@ -477,7 +477,12 @@ __device__ __noinline__ uint64_t long_record(const TallyArgs *Ap, TallyShared *S
                 if (h.add3) atomicAdd(A.fk_hist + (1ull << (2 * F.K)) + h.idx3, 1ull);
                 if (MODE == kModeBoth) atomicAdd(&S.stats_fk[stat_slot(code_fk)], 1u);
             }
-            if (MODE != kModeFragkon) {
+            if (MODE != kModeFragkon && A.cfg.R > kMaxRegion) {
+                const int rows = A.cfg.R + 2;
+                code = pss_record_wide(at, r, ci, cb, cl, A.g, A.cfg, [&](int tb, int row, int cell) {
+                    atomicAdd(A.pss_tables + ((size_t)tb * rows + row) * 16 + cell, 1ull);
+                });
+            } else if (MODE != kModeFragkon) {
                 PssStreams st;
                 code = pss_record(at, r, true, ci, cb, cl, A.g, A.cfg, st);
                 if (code == kCounted) {
@@ -519,7 +524,7 @@ __device__ __forceinline__ uint32_t ballot_bits(uint32_t word, uint32_t mask)
 // "which lanes hit my cell" into a popcount.  acc[] packs two rows per
 // register (16-bit partial sums).  All 32 lanes must be converged.
 template <int NACC>
-__device__ __forceinline__ void tally_rows(const PssStreams &st, uint32_t (&acc)[NACC], int rows, uint32_t lane)
+__device__ __forceinline__ void tally_rows(const PssStreams &st, uint32_t (&acc)[NACC ? NACC : 1], int rows, uint32_t lane)
 {
     const bool     tb = lane >= 16;
     const uint32_t cell = lane & 15u;
@@ -547,7 +552,7 @@ __device__ __forceinline__ void tally_rows(const PssStreams &st, uint32_t (&acc)
     }
 }
 template <int NACC>
-__device__ __forceinline__ void flush_acc(uint32_t (&acc)[NACC], int rows, uint32_t lane, uint32_t *table)
+__device__ __forceinline__ void flush_acc(uint32_t (&acc)[NACC ? NACC : 1], int rows, uint32_t lane, uint32_t *table)
 {
     const uint32_t tb = lane >> 4, cell = lane & 15u;
 #pragma unroll
@@ -669,7 +674,7 @@ __device__ __noinline__ uint32_t list_newlines_generic(TallySmem *Sp, int n_vali
 template <int MODE, int NACC>
 __device__ __forceinline__ void process_batch(const TallyArgs &A, TallyShared &T, const uint8_t *bytes, const uint32_t *le,
                                               bool has, int start, int pe, uint64_t goff,
-                                              uint32_t lane, uint32_t (&acc)[NACC], int &acc_iters, int rows,
+                                              uint32_t lane, uint32_t (&acc)[NACC ? NACC : 1], int &acc_iters, int rows,
                                               uint32_t &st_acc, uint32_t &st_acc_fk)
 {
     const uint32_t full = 0xffffffffu;
@@ -705,7 +710,12 @@ __device__ __forceinline__ void process_batch(const TallyArgs &A, TallyShared &T
         if (h.add5) atomicAdd(A.fk_hist + h.idx5, 1ull);
         if (h.add3) atomicAdd(A.fk_hist + (1ull << (2 * F.K)) + h.idx3, 1ull);
     }
-    if (MODE != kModeFragkon) {
+    if (MODE != kModeFragkon && NACC == 0) {                     // -r beyond the ballot tally: straight to the global tables
+        if (valid)
+            code = pss_record_wide(at, r, ci, cb, cl, A.g, A.cfg, [&](int tb, int row, int cell) {
+                atomicAdd(A.pss_tables + ((size_t)tb * rows + row) * 16 + cell, 1ull);
+            });
+    } else if (MODE != kModeFragkon) {
         const int rc = pss_record(at, r, valid, ci, cb, cl, A.g, A.cfg, st);
         if (valid) code = rc;
     } else {
@@ -713,9 +723,9 @@ __device__ __forceinline__ void process_batch(const TallyArgs &A, TallyShared &T
     }
     if (code != 99) log_outcome(A, goff, code);
     __syncwarp();
-    if (MODE != kModeFragkon) {
-        tally_rows(st, acc, rows, lane);
-        if (++acc_iters >= kFlushEvery) { flush_acc(acc, rows, lane, T.table); acc_iters = 0; }
+    if (MODE != kModeFragkon && NACC > 0) {
+        tally_rows<NACC>(st, acc, rows, lane);
+        if (++acc_iters >= kFlushEvery) { flush_acc<NACC>(acc, rows, lane, T.table); acc_iters = 0; }
     }
     // outcome counters: lane k (< kStN) keeps counter k of this warp in a register (stats[] order: lines, counted,
     // no contig, filtered, parse failure, undefined); they reach shared memory once, at the end of the kernel
@@ -759,7 +769,8 @@ __device__ __forceinline__ void process_batch(const TallyArgs &A, TallyShared &T
 //             positions of ordinals 0..kThreads to shared memory
 //   records   one thread per record (process_batch)
 // ---------------------------------------------------------------------------
-// NACC = registers of packed partial sums per lane: 9 cover -r <= 16 (the default is 15), 16 cover -r <= 30
+// NACC = registers of packed partial sums per lane: 9 cover -r <= 16 (the default is 15), 16 cover -r <= 30;
+// 0 = any -r, through pss_record_wide() and global atomics (exact, not tuned)
 template <int MODE, int NACC>
 __global__ void __launch_bounds__(kThreads, PSS_TALLY_CTAS_PER_SM) tally_kernel(const __grid_constant__ TallyArgs A)
 {
@@ -777,11 +788,11 @@ __global__ void __launch_bounds__(kThreads, PSS_TALLY_CTAS_PER_SM) tally_kernel(
     const int      rows = A.cfg.R + 2;
     const uint32_t one = A.one;
     uint32_t       phase = 0;
-    uint32_t       acc[NACC];
+    uint32_t       acc[NACC ? NACC : 1];
     int            acc_iters = 0;
     uint32_t       st_acc = 0, st_acc_fk = 0;                 // lane k: outcome counter k of this warp
 #pragma unroll
-    for (int i = 0; i < NACC; i++) acc[i] = 0;
+    for (int i = 0; i < (NACC ? NACC : 1); i++) acc[i] = 0;
     const uint64_t len16 = (A.len + 15) & ~15ull;
     int            est = kStageMax;                           // bytes the next kThreads records are expected to take
 
@@ -948,7 +959,7 @@ __global__ void __launch_bounds__(kThreads, PSS_TALLY_CTAS_PER_SM) tally_kernel(
         }
     }
 
-    if (MODE != kModeFragkon) flush_acc(acc, rows, lane, S.sh.table);
+    if (MODE != kModeFragkon && NACC > 0) flush_acc<NACC>(acc, rows, lane, S.sh.table);
     if (lane < (uint32_t)kStN) {
         if (st_acc) atomicAdd(&S.sh.stats[lane], st_acc);
         if (MODE == kModeBoth && st_acc_fk) atomicAdd(&S.sh.stats_fk[lane], st_acc_fk);

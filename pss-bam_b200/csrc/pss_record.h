@@ -175,7 +175,8 @@ enum : int {          // per-record outcomes (pssgpu.h pssgpu_debug_fetch)
 enum : int { kStLines = 0, kStCounted, kStNoContig, kStFiltered, kStParseFail, kStUndefined, kStN };
 
 constexpr int kMaxCtxChars = 48;
-constexpr int kMaxRegion   = 30;        // R + 2 <= 32 bases per window
+constexpr int kMaxRegion   = 30;        // R + 2 <= 32 bases per window: the ballot tally of the kernels
+constexpr int kMaxRegionWide = 2045;    // larger -r go through pss_record_wide(); a counted read has n <= 2047 bases
 constexpr int kMaxFragK    = 14;
 constexpr int kMaxField    = 2047;      // sam-parse.h:10 MAX_FIELD_WIDTH - 1
 constexpr int kMaxLine     = 200000;    // sam-parse.h:8  MAX_LINE_LEN (fgets chunk, pss-bam.c:764)
@@ -758,6 +759,71 @@ PSS_HD int pss_record(const B &b, const RecView &r, bool valid, int ci, uint64_t
     st.b_read = (rev ? l_read : r_read) ^ flip;
     st.b_bad  = (live && want_b) ? (rev ? l_bad : r_bad) : kEvenBits;
     return code;
+}
+
+// ---------------------------------------------------------------------------
+// pss-bam.c:390-496 for any -r (R > kMaxRegion does not fit the 64-bit row
+// streams above): the same filters in the same order, then one table cell per
+// row and side handed to add(table, row, cell) -- table 0 = fwd_counts (5'
+// end), 1 = rev_counts.  Base by base, with real branches: -r beyond 30 is an
+// unusual request and this path only has to be exact.
+// ---------------------------------------------------------------------------
+PSS_HD uint32_t genome_sym(const DevGenome &g, uint64_t gb)
+{
+    const uint64_t grp = g.groups[gb >> 4];
+    const uint32_t sh = 2u * (uint32_t)(gb & 15u);
+    return (((uint32_t)grp >> sh) & 3u) | ((((uint32_t)(grp >> 32) >> sh) & 3u) << 2);
+}
+// code 0..3 of a read base after toupper (pss-bam.c:425), 4 if it is not one of ACGT
+PSS_HD uint32_t read_base_code(uint32_t c)
+{
+    c |= 0x20u;
+    return c == 'a' ? 0u : c == 'c' ? 1u : c == 'g' ? 2u : c == 't' ? 3u : 4u;
+}
+template <class B, class Add>
+PSS_HD int pss_record_wide(const B &b, const RecView &r, int ci, uint64_t ctg_base, uint64_t ctg_len,
+                           const DevGenome &g, const TallyCfg &P, Add add)
+{
+    if (ci < 0) return kNoContig;                                           // :393-396
+    if (ctg_len == 0) return kUndefined;
+    const bool    paired = r.flag & 1u;
+    const int64_t n = paired ? (r.tlen < 0 ? -(int64_t)r.tlen : (int64_t)r.tlen) : (int64_t)r.seq_len;
+    if (n > kMaxTlen) return kUndefined;
+    const int     R = P.R;
+    const int64_t s = (int64_t)(r.pos - 1), e = s + n - 1;                  // :403-404
+    if (s - 2 < 0) return kFiltered;                                        // :407
+    if ((uint64_t)(e + 2) > ctg_len - 1) return kFiltered;                  // :408
+    if (r.mapq < P.min_mq) return kFiltered;                                // :409
+    if (!((uint64_t)n >= P.min_len && (uint64_t)n <= P.max_len && n >= R)) return kFiltered;   // :96-103
+    if (r.flag & (4u | 256u | 512u | 1024u | 2048u)) return kFiltered;      // :412-416
+    if (P.merged_only && paired) return kFiltered;                          // :417
+    if (!cigar_is_nM(b, r.cigar_off, r.cigar_len, n)) return kFiltered;     // :411
+    if (paired && (int64_t)r.seq_len < n) return kUndefined;
+
+    const bool     rev = r.flag & 16u;
+    const uint64_t g0 = ctg_base + (uint64_t)(s - 2);                       // g[0]
+    const uint64_t gN = ctg_base + (uint64_t)(e + 2);                       // g[n+3]
+    const bool up_ok = ctx_member(g, P, false, genome_sym(g, rev ? gN - 1 : g0 + 1), rev, rev ? gN - 1 : g0 + 1, true);
+    const bool dn_ok = ctx_member(g, P, true, genome_sym(g, rev ? g0 + 1 : gN - 1), rev, rev ? g0 + 1 : gN - 1, true);
+    const bool pp = (r.flag & 2u) && !(r.flag & 8u);
+    const bool sel_a = pp && (r.flag & 64u) && up_ok;                       // :460 / :482
+    const bool sel_b = pp && !sel_a && (r.flag & 128u) && dn_ok;            // :471 / :488
+    const bool want_a = paired ? sel_a : (up_ok && dn_ok);
+    const bool want_b = paired ? sel_b : (up_ok && dn_ok);
+    if (!(want_a || want_b)) return kFiltered;
+
+    const uint32_t flip = rev ? 3u : 0u;                                    // complement
+    for (int j = 0; j < R + 2; j++) {
+        // row j: context rows 0, 1 (read := ref), then position j - 2 from that end
+        const uint32_t sl = genome_sym(g, g0 + (uint64_t)j), sr = genome_sym(g, gN - (uint64_t)j);
+        const uint32_t ql = j < 2 ? sl : read_base_code(b(r.seq_off + (j - 2)));
+        const uint32_t qr = j < 2 ? sr : read_base_code(b(r.seq_off + (int)n - 1 - (j - 2)));
+        const uint32_t a_ref = rev ? sr : sl, a_read = rev ? qr : ql;       // 5' end of the molecule
+        const uint32_t b_ref = rev ? sl : sr, b_read = rev ? ql : qr;       // 3' end
+        if (want_a && a_ref < 4u && a_read < 4u) add(0, j, (int)(((a_read ^ flip) << 2) | (a_ref ^ flip)));
+        if (want_b && b_ref < 4u && b_read < 4u) add(1, j, (int)(((b_read ^ flip) << 2) | (b_ref ^ flip)));
+    }
+    return kCounted;
 }
 
 // ---------------------------------------------------------------------------

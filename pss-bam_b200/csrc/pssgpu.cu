@@ -356,9 +356,11 @@ int launch_tally(pssgpu_ctx *ctx, const uint8_t *d_sam, size_t len, uint64_t str
     CU(cudaMemsetAsync(ctx->d_range_ctr, 0, sizeof(unsigned int), ctx->stream));
     time_begin(ctx, len);
     const unsigned grid = (unsigned)std::min<uint64_t>(n_ranges, (uint64_t)max_grid);
+    constexpr int PM = MODE == kModeFragkon ? kModePss : MODE;          // (never launched with MODE == kModeFragkon)
     if (MODE == kModeFragkon) tally_kernel<kModeFragkon, 9><<<grid, kThreads, sizeof(TallySmem), ctx->stream>>>(a);
     else if (ctx->cfg.R + 2 <= 18) tally_kernel<MODE, 9><<<grid, kThreads, sizeof(TallySmem), ctx->stream>>>(a);
-    else tally_kernel<MODE == kModeFragkon ? kModePss : MODE, 16><<<grid, kThreads, sizeof(TallySmem), ctx->stream>>>(a);
+    else if (ctx->cfg.R <= kMaxRegion) tally_kernel<PM, 16><<<grid, kThreads, sizeof(TallySmem), ctx->stream>>>(a);
+    else tally_kernel<PM, 0><<<grid, kThreads, sizeof(TallySmem), ctx->stream>>>(a);      // any -r: exact, not tuned
     time_end(ctx);
     CU(cudaGetLastError());
     return PSSGPU_OK;
@@ -422,6 +424,8 @@ int pssgpu_init(int device, pssgpu_ctx **out)
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tally_kernel<kModeFragkon, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TallySmem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tally_kernel<kModeBoth, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TallySmem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tally_kernel<kModeBoth, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TallySmem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tally_kernel<kModePss, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TallySmem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tally_kernel<kModeBoth, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TallySmem));
     int occ_p = 0, occ_f = 0;
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, tally_kernel<kModePss, 16>, kThreads, sizeof(TallySmem));
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, tally_kernel<kModeFragkon, 9>, kThreads, sizeof(TallySmem));
@@ -497,8 +501,8 @@ namespace {
 
 int pss_cfg(pssgpu_ctx *ctx, const pssgpu_pss_params *p, TallyCfg &c)
 {
-    if (p->region_len < 0 || p->region_len > kMaxRegion)
-        return fail(ctx, PSSGPU_EUNSUPP, "region_len %d outside [0,%d]", p->region_len, kMaxRegion);
+    if (p->region_len < 0 || p->region_len > kMaxRegionWide)
+        return fail(ctx, PSSGPU_EUNSUPP, "region_len %d outside [0,%d]", p->region_len, kMaxRegionWide);
     c = TallyCfg{};
     c.mode = kModePss;
     c.R = p->region_len;

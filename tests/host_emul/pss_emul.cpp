@@ -164,7 +164,9 @@ uint64_t emul_tally(void *gp, const char *sam, uint64_t len, int mode,
             if (code == kCounted) {
                 const int ci = find_contig(g, at, r.rname_off, r.rname_len);
                 const uint64_t cb = ci >= 0 ? g.contigs[ci].base_off : 0, cl = ci >= 0 ? g.contigs[ci].len : 0;
-                if (mode == kModePss) {
+                if (mode == kModePss && R > kMaxRegion) {
+                    code = pss_record_wide(at, r, ci, cb, cl, g, P, [&](int tb, int row, int cell) { (tb ? rev : fwd)[row * 16 + cell]++; });
+                } else if (mode == kModePss) {
                     PssStreams st;
                     code = pss_record(at, r, true, ci, cb, cl, g, P, st);
                     if (code == kCounted) {

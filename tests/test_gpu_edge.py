@@ -185,7 +185,7 @@ def test_device_resident_input_and_reuse(small):
 def test_error_codes(small):
     g, ora, ctx = small
     with pytest.raises(pkg.PssGpuError) as e:
-        ctx.pss_begin(pkg.PssOptions(region_len=31))
+        ctx.pss_begin(pkg.PssOptions(region_len=2046))        # a counted read has at most 2047 bases
     assert e.value.code == -5
     with pytest.raises(pkg.PssGpuError):
         ctx.fragkon_begin(pkg.FragkonOptions(klen=15))

@@ -64,7 +64,9 @@ def test_pss_options(world):
     g, ora, ctx = world
     sam = Synth.sam(reads_cfg_config2(seed=7), g, 0, 30000)
     for p in (PssParams(region_len=5), PssParams(region_len=30, min_len=40, max_len=120, min_mq=20),
-              PssParams(up_ctx=b"CT", down_ctx=b"AGN"), PssParams(merged_only=1), PssParams(region_len=0)):
+              PssParams(up_ctx=b"CT", down_ctx=b"AGN"), PssParams(merged_only=1), PssParams(region_len=0),
+              PssParams(region_len=31), PssParams(region_len=64, up_ctx=b"ACGTN"), PssParams(region_len=150)):   # > 30: pss_record_wide
+
         _check_pss(ctx, ora, sam, p)
 
 

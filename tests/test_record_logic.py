@@ -52,7 +52,8 @@ def test_random_reads_default_options(world, seed):
 
 @pytest.mark.parametrize("p", [
     PssParams(region_len=0), PssParams(region_len=1), PssParams(region_len=4), PssParams(region_len=16),
-    PssParams(region_len=29), PssParams(region_len=30), PssParams(min_len=35, max_len=90), PssParams(min_mq=37),
+    PssParams(region_len=29), PssParams(region_len=30), PssParams(region_len=31), PssParams(region_len=47),
+    PssParams(region_len=150), PssParams(min_len=35, max_len=90), PssParams(min_mq=37),
     PssParams(min_mq=-1), PssParams(up_ctx=b"C", down_ctx=b"G"), PssParams(up_ctx=b"ACGTN", down_ctx=b"acgt"),
     PssParams(up_ctx=b"RYKM*", down_ctx=b"ACGT-X."), PssParams(merged_only=1), PssParams(up_ctx=b"", down_ctx=b"ACGT"),
 ], ids=repr)
