@@ -191,18 +191,19 @@ constexpr int kStageMax   = kSpan - 48;                       // most bytes of o
 constexpr int kSegs       = kIters * kWarps;                  // warp-iterations of the scan = segments of the newline ranking
 constexpr int kCacheContigs = 64;                             // contig table kept in shared memory when it fits
 constexpr int kCacheNames   = 1024;
-constexpr int kCacheSlots   = 128;
+constexpr int kCacheSlots   = 1024;                          // u8 slots of the collision-free name table
 constexpr int kFlushEvery   = 1900;                           // warp iterations between flushes of the 16-bit partial sums
 static_assert(kThreads % 32 == 0 && kSegs <= 64, "the newline ranking keeps at most two segment counts per lane");
+static_assert(kThreads >= kCacheContigs, "one thread per cached contig fills the shared-memory table");
 static_assert(kSpan < (1 << 20) && kThreads <= 1024, "pass A packs a newline position into 20 bits and its rank into the rest");
 
 struct ContigCache {
     uint32_t n;                                               // 0: not cached, use the global table
-    uint32_t hash[kCacheContigs];
+    uint32_t seed;                                            // the host found it: no two names share a slot
     uint16_t name_w0[kCacheContigs], name_len[kCacheContigs]; // first word of the name in names32 / length in bytes
     uint64_t base_off[kCacheContigs], len[kCacheContigs];
-    uint8_t  slot[kCacheSlots];                               // open addressing, 0xff = empty
-    uint32_t names32[kCacheNames / 4 + kCacheContigs];        // names as zero-padded little-endian words
+    uint8_t  slot[kCacheSlots];                               // slot -> contig, 0xff = empty
+    uint32_t names32[kCacheNames / 4 + 2 * kCacheContigs];    // names as zero-padded little-endian words, one spare word each
 };
 
 struct TallyShared {                                          // per-CTA tables, outcome counters, contig table
@@ -235,6 +236,8 @@ struct TallyArgs {
     TallyCfg       cfg;          // pss-bam options (fragkon's when only fragkon runs)
     TallyCfg       cfg_fk;       // fragkon options of the fused mode
     uint32_t       names_bytes;  // total bytes of contig names
+    uint32_t       cc_seed;      // seed of the collision-free hash of the contig names ...
+    uint32_t       cc_ok;        // ... if the host found one (<= kCacheContigs names of <= kCacheNames bytes)
     unsigned long long *pss_tables;   // 2*(R+2)*16 u64: fwd then rev
     unsigned long long *fk_hist;      // 2*4^K u64: 5' then 3'
     unsigned long long *stats;        // kStN
@@ -374,10 +377,11 @@ __device__ __forceinline__ uint32_t field_word(const B &b, int off, int len, int
     return w;
 }
 template <class B>
-__device__ __forceinline__ uint32_t name_hash_words(const B &b, int off, int len)
+__device__ __forceinline__ uint32_t name_hash_words(const B &b, int off, int len, uint32_t seed)
 {
     // every name hashes at least its first two (zero padded) words: no loop for names of up to 8 bytes
-    uint32_t  h = kNameHashSeed ^ (uint32_t)len;
+    // (pssgpu.cu: host_name_hash is the same function; it searches the seed)
+    uint32_t  h = seed ^ (uint32_t)len;
     const int nw = (len + 3) >> 2;
     h = (h ^ field_word(b, off, len, 0)) * 0x9E3779B1u;  h ^= h >> 15;
     h = (h ^ field_word(b, off, len, 1)) * 0x9E3779B1u;  h ^= h >> 15;
@@ -388,51 +392,25 @@ __device__ __forceinline__ uint32_t name_hash_words(const B &b, int off, int len
     return h;
 }
 // find_seq (fasta-genome-io.c:202-213) against the shared-memory copy of the
-// contig table: hash and comparison run on whole words of RNAME.  The first
-// two probes are straight-line code (with 128 slots for <= 64 names a third
-// probe is rare), so the lanes of a warp do not drift apart here.
+// contig table.  The hash is collision free on the contig names (the host
+// searched the seed), so one probe and one whole-word comparison of RNAME
+// decide, in straight-line code: the lanes of a warp do not drift apart here.
 template <class B>
-__device__ __forceinline__ bool cache_name_equal(const ContigCache &C, uint32_t v, const B &b, int off, int len,
-                                                  uint32_t w0, uint32_t w1)
+__device__ __forceinline__ int cache_find(const ContigCache &C, const B &b, int off, int len, uint64_t &base, uint64_t &clen)
 {
-    const uint32_t *nm = C.names32 + C.name_w0[v];
-    bool eq = (int)C.name_len[v] == len;
-    if (len > 0) eq = eq && (nm[0] == w0);
-    if (len > 4) eq = eq && (nm[1] == w1);
+    const uint32_t h = name_hash_words(b, off, len, C.seed);
+    const uint32_t w0 = field_word(b, off, len, 0), w1 = field_word(b, off, len, 1);
+    const uint32_t v = C.slot[h & (kCacheSlots - 1)];
+    const uint32_t vv = v != 0xffu ? v : 0u;
+    const uint32_t *nm = C.names32 + C.name_w0[vv];
+    bool eq = (v != 0xffu) & ((int)C.name_len[vv] == len) & (nm[0] == w0 || len <= 0) & (nm[1] == w1 || len <= 4);
     if (len > 8) {                                    // long names: the remaining words
         const int nw = (len + 3) >> 2;
         for (int k = 2; eq && k < nw; k++) eq = (nm[k] == field_word(b, off, len, k));
     }
-    return eq;
-}
-template <class B>
-__device__ __forceinline__ int cache_find(const ContigCache &C, const B &b, int off, int len, uint64_t &base, uint64_t &clen)
-{
-    const uint32_t h = name_hash_words(b, off, len);
-    const uint32_t w0 = field_word(b, off, len, 0), w1 = field_word(b, off, len, 1);
-    uint32_t s = h & (kCacheSlots - 1);
-    int      found = -1;
-    bool     open = true;                             // still probing
-#pragma unroll
-    for (int t = 0; t < 2; t++) {
-        const uint32_t v = C.slot[s];
-        const bool occupied = (v != 0xffu);
-        const uint32_t vv = occupied ? v : 0u;
-        const bool hit = open && occupied && C.hash[vv] == h && cache_name_equal(C, vv, b, off, len, w0, w1);
-        if (hit) found = (int)vv;
-        open = open && occupied && !hit;
-        s = (s + 1) & (kCacheSlots - 1);
-    }
-    while (open) {                                    // rare: a third or later probe
-        const uint32_t v = C.slot[s];
-        if (v == 0xffu) break;
-        if (C.hash[v] == h && cache_name_equal(C, v, b, off, len, w0, w1)) { found = (int)v; break; }
-        s = (s + 1) & (kCacheSlots - 1);
-    }
-    base = C.base_off[found < 0 ? 0 : found];
-    clen = C.len[found < 0 ? 0 : found];
-    if (found < 0) { base = 0; clen = 0; }
-    return found;
+    base = eq ? C.base_off[vv] : 0;
+    clen = eq ? C.len[vv] : 0;
+    return eq ? (int)vv : -1;
 }
 template <class B>
 __device__ __forceinline__ int lookup_contig(const ContigCache &C, const DevGenome &g, const B &b, int off, int len,
@@ -574,14 +552,15 @@ __device__ __forceinline__ void cta_prologue(TallyShared &T, const TallyArgs &A,
 {
     for (uint32_t i = tid; i < 2 * 32 * 16; i += nthreads) T.table[i] = 0;
     if (tid < 8) { T.stats[tid] = 0; T.stats_fk[tid] = 0; }
-    const bool fits = A.g.n_contigs <= (uint32_t)kCacheContigs && A.names_bytes <= (uint32_t)kCacheNames && A.g.n_contigs > 0;
+    const bool fits = A.cc_ok != 0u && A.g.n_contigs <= (uint32_t)kCacheContigs && A.names_bytes <= (uint32_t)kCacheNames && A.g.n_contigs > 0;
     if (fits) {
         for (uint32_t i = tid; i < (uint32_t)kCacheSlots; i += nthreads) T.cc.slot[i] = 0xffu;
+        for (uint32_t i = tid; i < (uint32_t)(kCacheNames / 4 + 2 * kCacheContigs); i += nthreads) T.cc.names32[i] = 0u;
         if (tid == 0) {                          // word offsets of the padded names
             uint32_t w = 0;
             for (uint32_t i = 0; i < A.g.n_contigs; i++) {
                 T.cc.name_w0[i] = (uint16_t)w;
-                w += (A.g.contigs[i].name_len + 3u) >> 2;
+                w += ((A.g.contigs[i].name_len + 3u) >> 2) + 1u;      // + 1: names shorter than 5 bytes are compared on two words
             }
         }
     }
@@ -591,20 +570,12 @@ __device__ __forceinline__ void cta_prologue(TallyShared &T, const TallyArgs &A,
         const GlobalAt  nm{ reinterpret_cast<const uint8_t *>(A.g.names) };
         const int       nw = (int)((c.name_len + 3u) >> 2);
         for (int k = 0; k < nw; k++) T.cc.names32[T.cc.name_w0[tid] + k] = field_word(nm, (int)c.name_off, (int)c.name_len, k);
-        T.cc.hash[tid] = name_hash_words(nm, (int)c.name_off, (int)c.name_len);
+        const uint32_t h = name_hash_words(nm, (int)c.name_off, (int)c.name_len, A.cc_seed);
+        T.cc.slot[h & (kCacheSlots - 1)] = (uint8_t)tid;              // distinct slots: the host checked
         T.cc.name_len[tid] = (uint16_t)c.name_len;
         T.cc.base_off[tid] = c.base_off; T.cc.len[tid] = c.len;
     }
-    __syncthreads();
-    if (tid == 0) {
-        if (fits)
-            for (uint32_t i = 0; i < A.g.n_contigs; i++) {
-                uint32_t s = T.cc.hash[i] & (kCacheSlots - 1);
-                while (T.cc.slot[s] != 0xffu) s = (s + 1) & (kCacheSlots - 1);
-                T.cc.slot[s] = (uint8_t)i;
-            }
-        T.cc.n = fits ? A.g.n_contigs : 0u;
-    }
+    if (tid == 0) { T.cc.n = fits ? A.g.n_contigs : 0u; T.cc.seed = A.cc_seed; }
     __syncthreads();
 }
 // CTA tables -> global (after a __syncthreads)

@@ -47,6 +47,7 @@ struct pssgpu_ctx {
     uint32_t  *d_hash = nullptr;
     uint32_t   hash_mask = 0;
     uint32_t   names_bytes = 0;
+    uint32_t   cc_seed = 0, cc_ok = 0;        // collision-free hash of the contig names for the kernels' shared-memory table
     uint64_t  *d_exc_pos = nullptr;
     uint8_t   *d_exc_chr = nullptr;
     uint32_t   n_exc = 0;
@@ -213,6 +214,38 @@ int upload_impl(pssgpu_ctx *ctx, const pssgpu_contig *contigs, uint64_t n, bool 
         hash[slot] = (uint32_t)i + 1;
     }
 
+    // seed under which name_hash_words() (pss_kernels.cuh) sends the contig names to distinct slots of the kernels'
+    // shared-memory table: one probe per RNAME, no collision chains
+    uint32_t cc_seed = 0, cc_ok = 0;
+    if (n > 0 && n <= (uint64_t)kCacheContigs && names.size() <= (size_t)kCacheNames) {
+        auto host_name_hash = [&](uint64_t i, uint32_t seed) {
+            const uint32_t len = tab[i].name_len;
+            auto word = [&](uint32_t k) {
+                uint32_t w = 0;
+                for (uint32_t j = 0; j < 4; j++)
+                    if (4 * k + j < len) w |= (uint32_t)(uint8_t)names[tab[i].name_off + 4 * k + j] << (8 * j);
+                return w;
+            };
+            uint32_t       h = seed ^ len;
+            const uint32_t nw = (len + 3) >> 2;
+            h = (h ^ word(0)) * 0x9E3779B1u;  h ^= h >> 15;
+            h = (h ^ word(1)) * 0x9E3779B1u;  h ^= h >> 15;
+            for (uint32_t k = 2; k < nw; k++) { h = (h ^ word(k)) * 0x9E3779B1u;  h ^= h >> 15; }
+            return h;
+        };
+        for (uint32_t t = 0; t < 4096 && !cc_ok; t++) {
+            const uint32_t seed = kNameHashSeed + t * 0x85EBCA6Bu;
+            std::vector<uint8_t> used(kCacheSlots, 0);
+            bool clash = false;
+            for (uint64_t i = 0; i < n && !clash; i++) {
+                uint8_t &u = used[host_name_hash(i, seed) & (kCacheSlots - 1)];
+                clash = u != 0;
+                u = 1;
+            }
+            if (!clash) { cc_seed = seed; cc_ok = 1; }
+        }
+    }
+
     uint32_t *d_flags = nullptr;
     unsigned long long *d_exc_n = nullptr;
     uint8_t *d_piece = nullptr;
@@ -299,6 +332,8 @@ int upload_impl(pssgpu_ctx *ctx, const pssgpu_contig *contigs, uint64_t n, bool 
 #undef CUX
     ctx->hash_mask = hash_size - 1;
     ctx->names_bytes = (uint32_t)names.size();
+    ctx->cc_seed = cc_seed;
+    ctx->cc_ok = cc_ok;
     ctx->n_groups = n_groups;
     ctx->n_bases = total;
     ctx->n_contigs = n;
@@ -335,6 +370,8 @@ int launch_tally(pssgpu_ctx *ctx, const uint8_t *d_sam, size_t len, uint64_t str
     a.cfg = ctx->cfg;
     a.cfg_fk = ctx->cfg_fk;
     a.names_bytes = ctx->names_bytes;
+    a.cc_seed = ctx->cc_seed;
+    a.cc_ok = ctx->cc_ok;
     a.pss_tables = ctx->d_tables;
     a.fk_hist = ctx->d_fk;
     a.stats = ctx->d_stats;
