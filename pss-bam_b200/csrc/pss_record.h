@@ -413,6 +413,13 @@ PSS_HD int split_fast(const B &b, const uint32_t *le, int p0, int pe, RecView &r
         sep[f] = p;                                                                             \
         prev = p;                                                                               \
     } while (0)
+    {   // end of QNAME: names of up to ~64 bytes end within three mask words, looked at in one go (longer: the loop)
+        const uint32_t b1 = le[w + 1], b2 = le[w + 2];
+        const bool     h0 = bits != 0u, h1 = b1 != 0u;
+        const uint32_t x = h0 ? bits : h1 ? b1 : b2;
+        w += h0 ? 0 : h1 ? 1 : 2;
+        bits = x;
+    }
     PSS_NEXT_SEP(0);                                // end of QNAME
     {
         // FLAG .. TLEN are short: their eight separators normally sit within the next 64..96 bytes, so they
@@ -682,7 +689,8 @@ PSS_HD int pss_record(const B &b, const RecView &r, bool valid, int ci, uint64_t
 
     const bool paired = r.flag & 1u;
     // sam-parse.c:66-68: unpaired -> isize = strlen(seq); pss-bam.c:401: n = abs(isize)
-    const int64_t n = paired ? (r.tlen < 0 ? -(int64_t)r.tlen : (int64_t)r.tlen) : (int64_t)r.seq_len;
+    const uint32_t abs_tlen = r.tlen < 0 ? 0u - (uint32_t)r.tlen : (uint32_t)r.tlen;       // |INT_MIN| fits
+    const int64_t  n = (int64_t)(paired ? abs_tlen : (uint32_t)r.seq_len);
     PSS_DROP(n > kMaxTlen, kUndefined);           // reference: stack overflow in its VLAs before any filter
     const int     R = P.R;
     const int64_t s = (int64_t)(r.pos - 1);       // :403
@@ -738,12 +746,12 @@ PSS_HD int pss_record(const B &b, const RecView &r, bool valid, int ci, uint64_t
     const bool dn_ok = ctx_member(g, P, true, rev ? sym_l : sym_r, rev, rev ? gb_up : gb_dn, live);
 
     // which table(s) this record feeds: unpaired :428-447, paired :450-493
-    const bool pp = (r.flag & 2u) && !(r.flag & 8u);
-    const bool sel_a = pp && (r.flag & 64u) && up_ok;                       // :460 / :482
-    const bool sel_b = pp && !sel_a && (r.flag & 128u) && dn_ok;            // :471 / :488
-    const bool want_a = paired ? sel_a : (up_ok && dn_ok);
-    const bool want_b = paired ? sel_b : (up_ok && dn_ok);
-    PSS_DROP(!(want_a || want_b), kFiltered);
+    const bool pp = ((r.flag & 2u) != 0u) & ((r.flag & 8u) == 0u);
+    const bool sel_a = pp & ((r.flag & 64u) != 0u) & up_ok;                 // :460 / :482
+    const bool sel_b = pp & !sel_a & ((r.flag & 128u) != 0u) & dn_ok;       // :471 / :488
+    const bool want_a = paired ? sel_a : (up_ok & dn_ok);
+    const bool want_b = paired ? sel_b : (up_ok & dn_ok);
+    PSS_DROP(!(want_a | want_b), kFiltered);
 #undef PSS_DROP
 
     // class != 0 -> not one of ACGT -> the cell is skipped (:253-255, :176-188)
@@ -787,7 +795,8 @@ PSS_HD int pss_record_wide(const B &b, const RecView &r, int ci, uint64_t ctg_ba
     if (ci < 0) return kNoContig;                                           // :393-396
     if (ctg_len == 0) return kUndefined;
     const bool    paired = r.flag & 1u;
-    const int64_t n = paired ? (r.tlen < 0 ? -(int64_t)r.tlen : (int64_t)r.tlen) : (int64_t)r.seq_len;
+    const uint32_t abs_tlen = r.tlen < 0 ? 0u - (uint32_t)r.tlen : (uint32_t)r.tlen;       // |INT_MIN| fits
+    const int64_t  n = (int64_t)(paired ? abs_tlen : (uint32_t)r.seq_len);
     if (n > kMaxTlen) return kUndefined;
     const int     R = P.R;
     const int64_t s = (int64_t)(r.pos - 1), e = s + n - 1;                  // :403-404
