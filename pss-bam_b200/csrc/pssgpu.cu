@@ -832,7 +832,24 @@ int pssgpu_kmer_spectrum_shard_device(pssgpu_ctx *ctx, int k, int shard, int n_s
         CU(cudaMemsetAsync(d_counts, 0, bins * sizeof(uint64_t), ctx->stream));
     }
     time_begin(ctx, (g1 - g0) * sizeof(uint64_t));
-    if (g1 > g0) {
+    if (g1 > g0 && k >= 7 && k <= 9) {           // shared-memory bins, one CTA per SM and (slice, pass)
+        const uint32_t n_slices = (uint32_t)std::min<uint64_t>((uint64_t)ctx->sm_count, (g1 - g0 + kSpecSmemThreads - 1) / kSpecSmemThreads);
+        const uint32_t passes = (uint32_t)std::max<size_t>(1, bins >> kSpecSmemLog);
+        const size_t   smem = std::min<size_t>(bins, kSpecSmemBins) * sizeof(uint32_t);
+        const dim3     sg(n_slices * passes);
+#define PSS_SPEC(K_, CT_, PTR_)                                                                                        \
+        do {                                                                                                           \
+            cudaFuncSetAttribute(spectrum_smem_kernel<K_, CT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            spectrum_smem_kernel<K_, CT_><<<sg, kSpecSmemThreads, smem, ctx->stream>>>(ctx->d_groups, g0, g1, n_slices, PTR_); \
+        } while (0)
+        if (narrow) {
+            if (k == 7) PSS_SPEC(7, unsigned int, d_narrow); else if (k == 8) PSS_SPEC(8, unsigned int, d_narrow); else PSS_SPEC(9, unsigned int, d_narrow);
+        } else {
+            unsigned long long *w = (unsigned long long *)d_counts;
+            if (k == 7) PSS_SPEC(7, unsigned long long, w); else if (k == 8) PSS_SPEC(8, unsigned long long, w); else PSS_SPEC(9, unsigned long long, w);
+        }
+#undef PSS_SPEC
+    } else if (g1 > g0) {
         if (narrow) {
             if (k <= kSpectrumSmemK) spectrum_kernel<true, unsigned int><<<grid, 256, 0, ctx->stream>>>(ctx->d_groups, g0, g1, k, d_narrow);
             else spectrum_kernel<false, unsigned int><<<grid, 256, 0, ctx->stream>>>(ctx->d_groups, g0, g1, k, d_narrow);
