@@ -543,10 +543,11 @@ __device__ __forceinline__ uint32_t ballot_bits(uint32_t word, uint32_t mask)
 // owns cell (l & 15) of table (l >> 4); five ballots per table and row turn
 // "which lanes hit my cell" into a popcount.  acc[] packs two rows per
 // register (16-bit partial sums).  All 32 lanes must be converged.
-template <int NACC>
-__device__ __forceinline__ void tally_rows(const PssStreams &st, uint32_t (&acc)[NACC ? NACC : 1], int rows, uint32_t lane)
+template <int NACC, int ROWS>
+__device__ __forceinline__ void tally_rows(const PssStreams &st, uint32_t (&acc)[NACC ? NACC : 1], int rows, uint32_t lane, uint32_t one)
 {
-    const bool     tb = lane >= 16;
+    const uint32_t tbi = lane >> 4;                           // which table this lane counts for
+    const uint32_t neg1 = 0u - one;
     const uint32_t cell = lane & 15u;
     const uint32_t x0 = (cell & 1u) ? 0u : ~0u, x1 = (cell & 2u) ? 0u : ~0u;
     const uint32_t x2 = (cell & 4u) ? 0u : ~0u, x3 = (cell & 8u) ? 0u : ~0u;
@@ -555,9 +556,12 @@ __device__ __forceinline__ void tally_rows(const PssStreams &st, uint32_t (&acc)
     const uint32_t ag[2] = { ~(uint32_t)st.a_bad, ~(uint32_t)(st.a_bad >> 32) };
     const uint32_t br[2] = { (uint32_t)st.b_ref, (uint32_t)(st.b_ref >> 32) }, bq[2] = { (uint32_t)st.b_read, (uint32_t)(st.b_read >> 32) };
     const uint32_t bg[2] = { ~(uint32_t)st.b_bad, ~(uint32_t)(st.b_bad >> 32) };
+    // the ballots are warp uniform, the table a lane counts for is not: "tb ? b : a" as a + tb * (b - a), two IMADs
+    // on the idle FMA pipe instead of a SEL on the ALU pipe (the pipe this kernel is bound by)
+    auto pick = [&](uint32_t a, uint32_t b) { return imad(tbi, imad(a, neg1, b), a); };
 #pragma unroll
     for (int j = 0; j < 2 * NACC; j++) {
-        if (j >= rows) break;
+        if (ROWS ? j >= ROWS : j >= rows) break;              // ROWS: the row count as a compile-time constant (0: run time)
         const int      h = j >> 4;
         const uint32_t m0 = 1u << (2 * (j & 15)), m1 = 2u << (2 * (j & 15));
         const uint32_t a0 = ballot_bits(ar[h], m0), a1 = ballot_bits(ar[h], m1);
@@ -566,8 +570,7 @@ __device__ __forceinline__ void tally_rows(const PssStreams &st, uint32_t (&acc)
         const uint32_t b0 = ballot_bits(br[h], m0), b1 = ballot_bits(br[h], m1);
         const uint32_t b2 = ballot_bits(bq[h], m0), b3 = ballot_bits(bq[h], m1);
         const uint32_t bv = ballot_bits(bg[h], m0);
-        const uint32_t m = (tb ? bv : av) & ((tb ? b0 : a0) ^ x0) & ((tb ? b1 : a1) ^ x1)
-                         & ((tb ? b2 : a2) ^ x2) & ((tb ? b3 : a3) ^ x3);
+        const uint32_t m = pick(av, bv) & (pick(a0, b0) ^ x0) & (pick(a1, b1) ^ x1) & (pick(a2, b2) ^ x2) & (pick(a3, b3) ^ x3);
         acc[j >> 1] += (uint32_t)__popc(m) << (16 * (j & 1));
     }
 }
@@ -684,7 +687,7 @@ __device__ __noinline__ uint32_t list_newlines_generic(TallySmem *Sp, int n_vali
 // terminator at pe (has == false: no record for the lane).  Parses, filters,
 // gathers, tallies, counts outcomes.  All 32 lanes of the warp must call it
 // together.
-template <int MODE, int NACC>
+template <int MODE, int NACC, int ROWS>
 __device__ __forceinline__ void process_batch(const TallyArgs &A, TallyShared &T, const uint8_t *bytes, const uint32_t *le,
                                               bool has, int start, int pe, uint64_t goff,
                                               uint32_t lane, uint32_t (&acc)[NACC ? NACC : 1], int &acc_iters, int rows,
@@ -737,7 +740,7 @@ __device__ __forceinline__ void process_batch(const TallyArgs &A, TallyShared &T
     if (code != 99) log_outcome(A, goff, code);
     __syncwarp();
     if (MODE != kModeFragkon && NACC > 0) {
-        tally_rows<NACC>(st, acc, rows, lane);
+        tally_rows<NACC, ROWS>(st, acc, rows, lane, A.one);
         if (++acc_iters >= kFlushEvery) { flush_acc<NACC>(acc, rows, lane, T.table); acc_iters = 0; }
     }
     // outcome counters: lane k (< kStN) keeps counter k of this warp in a register (stats[] order: lines, counted,
@@ -783,8 +786,9 @@ __device__ __forceinline__ void process_batch(const TallyArgs &A, TallyShared &T
 //   records   one thread per record (process_batch)
 // ---------------------------------------------------------------------------
 // NACC = registers of packed partial sums per lane: 9 cover -r <= 16 (the default is 15), 16 cover -r <= 30;
-// 0 = any -r, through pss_record_wide() and global atomics (exact, not tuned)
-template <int MODE, int NACC>
+// 0 = any -r, through pss_record_wide() and global atomics (exact, not tuned).  ROWS = R + 2 as a compile-time
+// constant for the default -r 15 (the ballot loop then has no per-row exit test), 0 = taken from the arguments
+template <int MODE, int NACC, int ROWS>
 __global__ void __launch_bounds__(kThreads, PSS_TALLY_CTAS_PER_SM) tally_kernel(const __grid_constant__ TallyArgs A)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -963,7 +967,7 @@ __global__ void __launch_bounds__(kThreads, PSS_TALLY_CTAS_PER_SM) tally_kernel(
                 const uint64_t goff = (uint64_t)(gbase + start);
                 const bool     has = in && start < data_end && goff < range_end;
                 if (__any_sync(full, has))
-                    process_batch<MODE, NACC>(A, S.sh, S.bytes, S.le, has, start, pe, goff, lane, acc, acc_iters, rows, st_acc, st_acc_fk);
+                    process_batch<MODE, NACC, ROWS>(A, S.sh, S.bytes, S.le, has, start, pe, goff, lane, acc, acc_iters, rows, st_acc, st_acc_fk);
             }
 
             want_full = next_full;

@@ -394,10 +394,11 @@ int launch_tally(pssgpu_ctx *ctx, const uint8_t *d_sam, size_t len, uint64_t str
     time_begin(ctx, len);
     const unsigned grid = (unsigned)std::min<uint64_t>(n_ranges, (uint64_t)max_grid);
     constexpr int PM = MODE == kModeFragkon ? kModePss : MODE;          // (never launched with MODE == kModeFragkon)
-    if (MODE == kModeFragkon) tally_kernel<kModeFragkon, 9><<<grid, kThreads, sizeof(TallySmem), ctx->stream>>>(a);
-    else if (ctx->cfg.R + 2 <= 18) tally_kernel<MODE, 9><<<grid, kThreads, sizeof(TallySmem), ctx->stream>>>(a);
-    else if (ctx->cfg.R <= kMaxRegion) tally_kernel<PM, 16><<<grid, kThreads, sizeof(TallySmem), ctx->stream>>>(a);
-    else tally_kernel<PM, 0><<<grid, kThreads, sizeof(TallySmem), ctx->stream>>>(a);      // any -r: exact, not tuned
+    if (MODE == kModeFragkon) tally_kernel<kModeFragkon, 9, 0><<<grid, kThreads, sizeof(TallySmem), ctx->stream>>>(a);
+    else if (ctx->cfg.R == 15) tally_kernel<PM, 9, 17><<<grid, kThreads, sizeof(TallySmem), ctx->stream>>>(a);     // the default -r
+    else if (ctx->cfg.R + 2 <= 18) tally_kernel<PM, 9, 0><<<grid, kThreads, sizeof(TallySmem), ctx->stream>>>(a);
+    else if (ctx->cfg.R <= kMaxRegion) tally_kernel<PM, 16, 0><<<grid, kThreads, sizeof(TallySmem), ctx->stream>>>(a);
+    else tally_kernel<PM, 0, 0><<<grid, kThreads, sizeof(TallySmem), ctx->stream>>>(a);   // any -r: exact, not tuned
     time_end(ctx);
     CU(cudaGetLastError());
     return PSSGPU_OK;
@@ -456,16 +457,17 @@ int pssgpu_init(int device, pssgpu_ctx **out)
     c->sm_count = prop.multiProcessorCount;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tally_kernel<kModePss, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TallySmem));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tally_kernel<kModePss, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TallySmem));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tally_kernel<kModeFragkon, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TallySmem));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tally_kernel<kModeBoth, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TallySmem));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tally_kernel<kModeBoth, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TallySmem));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tally_kernel<kModePss, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TallySmem));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tally_kernel<kModeBoth, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TallySmem));
+    {   // every instantiation needs its dynamic shared memory raised above the 48 KB default
+        const void *kernels[] = {
+            (const void *)tally_kernel<kModePss, 9, 17>, (const void *)tally_kernel<kModePss, 9, 0>, (const void *)tally_kernel<kModePss, 16, 0>,
+            (const void *)tally_kernel<kModePss, 0, 0>, (const void *)tally_kernel<kModeFragkon, 9, 0>, (const void *)tally_kernel<kModeBoth, 9, 17>,
+            (const void *)tally_kernel<kModeBoth, 9, 0>, (const void *)tally_kernel<kModeBoth, 16, 0>, (const void *)tally_kernel<kModeBoth, 0, 0> };
+        for (const void *k : kernels)
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TallySmem));
+    }
     int occ_p = 0, occ_f = 0;
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, tally_kernel<kModePss, 16>, kThreads, sizeof(TallySmem));
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, tally_kernel<kModeFragkon, 9>, kThreads, sizeof(TallySmem));
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, tally_kernel<kModePss, 16, 0>, kThreads, sizeof(TallySmem));
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, tally_kernel<kModeFragkon, 9, 0>, kThreads, sizeof(TallySmem));
     if (e != cudaSuccess || occ_p < 1 || occ_f < 1) {
         fail(nullptr, PSSGPU_ECUDA, "pssgpu_init: %s (occupancy %d/%d)", cudaGetErrorString(e), occ_p, occ_f);
         if (c->stream) cudaStreamDestroy(c->stream);
