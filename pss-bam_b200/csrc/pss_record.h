@@ -146,6 +146,15 @@ PSS_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh)
     return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
 #endif
 }
+// low 32 bits of (hi:lo) >> sh, 0 <= sh <= 32 (clamping variant: a shift by 32 returns hi)
+PSS_HD uint32_t funnel_rc(uint32_t lo, uint32_t hi, uint32_t sh)
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_rc(lo, hi, sh);
+#else
+    return sh >= 32 ? hi : (sh ? (lo >> sh) | (hi << (32 - sh)) : lo);
+#endif
+}
 // reverse the order of the sixteen 2-bit fields of x
 PSS_HD uint32_t rev_fields32(uint32_t x)
 {
@@ -422,29 +431,33 @@ PSS_HD int split_fast(const B &b, const uint32_t *le, int p0, int pe, RecView &r
     }
     PSS_NEXT_SEP(0);                                // end of QNAME
     {
-        // FLAG .. TLEN are short: their eight separators normally sit within the next 64..96 bytes, so they
-        // are picked out of three mask words held in registers -- straight-line, no loads, no loops.  (A
-        // per-field skip loop would run for a handful of lanes at a time: fields end at random word offsets.)
-        uint32_t m0 = bits, m1 = le[w + 1], m2 = le[w + 2];
+        // FLAG .. TLEN are short.  A 96-bit window of the mask, anchored at the byte after the last separator, is
+        // shifted along: the next separator is then always the lowest set bit of its first word (fields of up to
+        // 31 bytes; longer ones are left to scan11) -- one find-first-set and three funnel shifts per field, in
+        // place of a chain of compares and selects over three words (the integer ALU pipe is what this kernel is
+        // bound by).
+        int            cur = sep[0] + 1;
+        const int      w0 = cur >> 5;
+        const uint32_t s0 = (uint32_t)(cur & 31);
+        const uint32_t q0 = le[w0], q1 = le[w0 + 1], q2 = le[w0 + 2], q3 = le[w0 + 3];
+        uint32_t h0 = funnel_r(q0, q1, s0), h1 = funnel_r(q1, q2, s0), h2 = funnel_r(q2, q3, s0);
 #pragma unroll
         for (int f = 1; f <= 8; f++) {
-            const bool     z0 = (m0 == 0u), z1 = (m1 == 0u);
-            const uint32_t x = z0 ? (z1 ? m2 : m1) : m0;
-            const int      base = z0 ? (z1 ? 64 : 32) : 0;
-            ok = ok && (x != 0u);                   // window exhausted: unusually long fields, let scan11 decide
-            int p = (w << 5) + base + ffs32(x) - 1;
-            if (p > pe || x == 0u) p = pe;
-            const uint32_t y = x & (x - 1u);
-            m0 = z0 ? m0 : y;
-            m1 = (z0 && !z1) ? y : m1;
-            m2 = (z0 && z1) ? y : m2;
-            ok = ok && (p > prev + 1) && (p < pe);
-            sep[f] = p;
-            prev = p;
+            const int t = ffs32(h0);                // 1 + distance to the separator, 0: none within 32 bytes
+            ok = ok && (t > 1);                     // found, and the field is not empty
+            cur += t;
+            sep[f] = cur - 1;
+#if !defined(__CUDA_ARCH__)
+            if (sep[f] > pe) sep[f] = pe;           // host build: stay inside the caller's buffer (the kernel's tile has slack; ok is false either way)
+#endif
+            h0 = funnel_rc(h0, h1, (uint32_t)t);
+            h1 = funnel_rc(h1, h2, (uint32_t)t);
+            h2 = funnel_rc(h2, 0u, (uint32_t)t);
         }
-        const bool z0 = (m0 == 0u), z1 = (m1 == 0u);    // cursor for the two long fields
-        bits = z0 ? (z1 ? m2 : m1) : m0;
-        w += z0 ? (z1 ? 2 : 1) : 0;
+        ok = ok && (sep[8] < pe);                   // fewer than 11 clean fields: scan11 decides
+        prev = sep[8];
+        w = cur >> 5;                               // cursor for the two long fields
+        bits = le[w] & (0xffffffffu << (cur & 31));
     }
     // SEQ and QUAL: reads of up to ~150 bases end within the next five mask words; looked at in one go, so that the
     // lanes of a warp do not loop a different number of times (longer fields fall through to the loop in PSS_NEXT_SEP)
