@@ -732,7 +732,7 @@ __device__ __forceinline__ void process_batch(const TallyArgs &A, TallyShared &T
                 atomicAdd(A.pss_tables + ((size_t)tb * rows + row) * 16 + cell, 1ull);
             });
     } else if (MODE != kModeFragkon) {
-        const int rc = pss_record(at, r, valid, ci, cb, cl, A.g, A.cfg, st);
+        const int rc = pss_record<SmemAt, (ROWS ? ROWS - 2 : -1)>(at, r, valid, ci, cb, cl, A.g, A.cfg, st);
         if (valid) code = rc;
     } else {
         code = code_fk;

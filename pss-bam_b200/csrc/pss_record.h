@@ -338,10 +338,16 @@ PSS_HD uint32_t value4(uint32_t t)                    // four digit values, most
     t = t * 10u + (t >> 8);
     return (t & 0xffu) * 100u + ((t >> 16) & 0xffu);
 }
-PSS_HD uint32_t keep_tail(uint32_t w, int drop)       // first `drop` (0..4) bytes -> '0'
+// w ^ "0000" with the first `drop` (>= 0) bytes forced to digit value 0: the digit values of a field that ends at the
+// end of w.  One clamped funnel shift makes the byte mask (a shift by 32 or more gives 0), one LOP3 applies it.
+PSS_HD uint32_t digit_tail(uint32_t w, int drop)
 {
+#if defined(__CUDA_ARCH__)
+    const uint32_t m = __funnelshift_lc(0u, 0xffffffffu, 8u * (uint32_t)drop);
+#else
     const uint32_t m = drop >= 4 ? 0u : (0xffffffffu << (8 * drop));
-    return (w & m) | (0x30303030u & ~m);
+#endif
+    return (w ^ 0x30303030u) & m;
 }
 template <class B>
 PSS_HD uint32_t dec_loop(const B &b, int a, int e, bool &ok)      // only for the first bytes of the whole input
@@ -358,7 +364,7 @@ PSS_HD uint32_t dec4(const B &b, int a, int e, bool &ok)
     ok = ok && (L >= 1) && (L <= 4);
     if (!ok) L = 1;
     if (B::kLookBack < 4 && e - 4 < b.lo()) return dec_loop(b, e - L, e, ok);
-    const uint32_t t = keep_tail(word_at(b, e - 4), 4 - L) ^ 0x30303030u;
+    const uint32_t t = digit_tail(word_at(b, e - 4), 4 - L);
     ok = ok && all_digits4(t);
     return value4(t);
 }
@@ -373,9 +379,9 @@ PSS_HD void digits9(const B &b, int a, int e, bool &ok)
     const int      p = e - 12, a0 = p & ~3, drop = 12 - L;
     const uint32_t sh = 8u * (uint32_t)(p & 3);
     const uint32_t x0 = b.word(a0), x1 = b.word(a0 + 4), x2 = b.word(a0 + 8), x3 = b.word(a0 + 12);
-    const uint32_t t0 = keep_tail(funnel_r(x0, x1, sh), drop) ^ 0x30303030u;
-    const uint32_t t1 = keep_tail(funnel_r(x1, x2, sh), drop - 4 < 0 ? 0 : drop - 4) ^ 0x30303030u;
-    const uint32_t t2 = keep_tail(funnel_r(x2, x3, sh), drop - 8 < 0 ? 0 : drop - 8) ^ 0x30303030u;
+    const uint32_t t0 = digit_tail(funnel_r(x0, x1, sh), drop);
+    const uint32_t t1 = digit_tail(funnel_r(x1, x2, sh), drop - 4 < 0 ? 0 : drop - 4);
+    const uint32_t t2 = digit_tail(funnel_r(x2, x3, sh), drop - 8 < 0 ? 0 : drop - 8);
     ok = ok && all_digits4(t0) && all_digits4(t1) && all_digits4(t2);
 }
 // value of the 1..9 digit field [a, e); anything else clears ok
@@ -389,9 +395,9 @@ PSS_HD uint32_t dec9(const B &b, int a, int e, bool &ok)
     const int      p = e - 12, a0 = p & ~3, drop = 12 - L;          // drop in 3..11
     const uint32_t sh = 8u * (uint32_t)(p & 3);
     const uint32_t x0 = b.word(a0), x1 = b.word(a0 + 4), x2 = b.word(a0 + 8), x3 = b.word(a0 + 12);
-    const uint32_t t0 = keep_tail(funnel_r(x0, x1, sh), drop) ^ 0x30303030u;
-    const uint32_t t1 = keep_tail(funnel_r(x1, x2, sh), drop - 4 < 0 ? 0 : drop - 4) ^ 0x30303030u;
-    const uint32_t t2 = keep_tail(funnel_r(x2, x3, sh), drop - 8 < 0 ? 0 : drop - 8) ^ 0x30303030u;
+    const uint32_t t0 = digit_tail(funnel_r(x0, x1, sh), drop);
+    const uint32_t t1 = digit_tail(funnel_r(x1, x2, sh), drop - 4 < 0 ? 0 : drop - 4);
+    const uint32_t t2 = digit_tail(funnel_r(x2, x3, sh), drop - 8 < 0 ? 0 : drop - 8);
     ok = ok && all_digits4(t0) && all_digits4(t1) && all_digits4(t2);
     return (value4(t0) * 10000u + value4(t1)) * 10000u + value4(t2);
 }
@@ -650,9 +656,10 @@ PSS_HD void codes_of_word(uint32_t w, uint32_t &codes8, uint32_t &bad8)
     bad8 = ((nz >> 7) * 0x01041040u) >> 24;
 }
 // 4*n_words (<= 32) read bases starting at byte `off`: field k = base k
-template <class B>
+template <class B, int NWC = 0>      // NWC: n_words as a compile-time constant (0: run time)
 PSS_HD void read_codes(const B &b, int off, int n_words, uint64_t &codes, uint64_t &bad)
 {
+    if (NWC) n_words = NWC;
     codes = 0; bad = 0;
     const int      a0 = off & ~3;
     const uint32_t sh = 8u * (uint32_t)(off & 3);
@@ -690,7 +697,7 @@ constexpr uint64_t kEvenBits = 0x5555555555555555ull;
 // gathers and the read decoding (a lane that drops out costs nothing, a warp
 // that splits executes everything twice).  `valid` = the record parsed; lanes
 // without a record pass valid == false and the RecView defaults.
-template <class B>
+template <class B, int RC = -1>      // RC: -r as a compile-time constant (-1: taken from P)
 PSS_HD int pss_record(const B &b, const RecView &r, bool valid, int ci, uint64_t ctg_base, uint64_t ctg_len,
                       const DevGenome &g, const TallyCfg &P, PssStreams &st)
 {
@@ -705,7 +712,7 @@ PSS_HD int pss_record(const B &b, const RecView &r, bool valid, int ci, uint64_t
     const uint32_t abs_tlen = r.tlen < 0 ? 0u - (uint32_t)r.tlen : (uint32_t)r.tlen;       // |INT_MIN| fits
     const int64_t  n = (int64_t)(paired ? abs_tlen : (uint32_t)r.seq_len);
     PSS_DROP(n > kMaxTlen, kUndefined);           // reference: stack overflow in its VLAs before any filter
-    const int     R = P.R;
+    const int     R = RC >= 0 ? RC : P.R;
     const int64_t s = (int64_t)(r.pos - 1);       // :403
     const int64_t e = s + n - 1;                  // :404
 
@@ -731,8 +738,8 @@ PSS_HD int pss_record(const B &b, const RecView &r, bool valid, int ci, uint64_t
     const int nw = (R + 3) >> 2;
     const int nn = live ? (int)n : 4 * nw;
     uint64_t  pre, pre_bad, suf, suf_bad;
-    read_codes(b, r.seq_off, nw, pre, pre_bad);
-    read_codes(b, r.seq_off + nn - 4 * nw, nw, suf, suf_bad);
+    read_codes<B, (RC >= 0 ? (RC + 3) >> 2 : 0)>(b, r.seq_off, nw, pre, pre_bad);
+    read_codes<B, (RC >= 0 ? (RC + 3) >> 2 : 0)>(b, r.seq_off + nn - 4 * nw, nw, suf, suf_bad);
     suf = rev_fields64(suf, 4 * nw);
     suf_bad = rev_fields64(suf_bad, 4 * nw);
     const uint64_t m = low_fields_mask(W);
