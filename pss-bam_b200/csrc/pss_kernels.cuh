@@ -866,30 +866,41 @@ __global__ void __launch_bounds__(kThreads, PSS_TALLY_CTAS_PER_SM) tally_kernel(
             constexpr uint32_t kNoNl = 0xfffffu;              // "this slot holds no newline"
             uint32_t pk[kIters];                              // position | rank << 20 of this thread's newline of step it
             uint32_t redo = 0;                                // a slot with two newlines, or a false candidate: exact listing
+            const uint32_t r4 = (lane >> 1) & 3u;             // quad swizzle of this lane (see below)
+            const uint32_t qo0 = 16u * r4, qo1 = 16u * (1u ^ r4), qo2 = 16u * (2u ^ r4), qo3 = 16u * (3u ^ r4);
+            const uint32_t rot16 = 16u * (r4 & 1u), hi_x = r4 >> 1, swz = 16u * r4;
 #pragma unroll
             for (int it = 0; it < kIters; it++) {
                 pk[it] = kNoNl;
                 if (it * 2 * kThreads < n_valid + 8) {        // block-uniform
                     const int      c = 2 * (it * kThreads + (int)tid);           // this thread's two chunks: c, c + 1
                     const uint8_t *src = S.bytes + 32 * c;
-                    const uint4    q0 = *reinterpret_cast<const uint4 *>(src), q1 = *reinterpret_cast<const uint4 *>(src + 16);
-                    const uint4    q2 = *reinterpret_cast<const uint4 *>(src + 32), q3 = *reinterpret_cast<const uint4 *>(src + 48);
-                    uint32_t le_a, nc_a, le_b, nc_b;
-                    classify32_fast(q0, q1, one, le_a, nc_a);
-                    classify32_fast(q2, q3, one, le_b, nc_b);
+                    // the four 16-byte quads of the slot are loaded in the order 0^r, 1^r, 2^r, 3^r, r = (lane / 2) % 4:
+                    // the eight lanes of a quarter warp then touch eight different bank groups (in natural order
+                    // lanes 64 bytes apart collide four ways).  A mask word in load order is a true mask word with its
+                    // halves swapped when r is odd; which of the two chunks it belongs to is r / 2.
+                    const uint4    q0 = *reinterpret_cast<const uint4 *>(src + qo0), q1 = *reinterpret_cast<const uint4 *>(src + qo1);
+                    const uint4    q2 = *reinterpret_cast<const uint4 *>(src + qo2), q3 = *reinterpret_cast<const uint4 *>(src + qo3);
+                    uint32_t le_x, nc_x, le_y, nc_y;
+                    classify32_fast(q0, q1, one, le_x, nc_x);
+                    classify32_fast(q2, q3, one, le_y, nc_y);
+                    le_x = __funnelshift_l(le_x, le_x, rot16);
+                    le_y = __funnelshift_l(le_y, le_y, rot16);
                     if ((it + 1) * 2 * kThreads > n_valid) {  // block-uniform: the step that runs over the end of the text
-                        const bool in_a = c < n_valid, in_b = c + 1 < n_valid;
-                        le_a = in_a ? le_a : ~0u;  nc_a = in_a ? nc_a : 0u;       // sentinels: every mask walk ends there
-                        le_b = in_b ? le_b : ~0u;  nc_b = in_b ? nc_b : 0u;
+                        const bool in_x = c + (int)hi_x < n_valid, in_y = c + 1 - (int)hi_x < n_valid;
+                        le_x = in_x ? le_x : ~0u;  nc_x = in_x ? nc_x : 0u;       // sentinels: every mask walk ends there
+                        le_y = in_y ? le_y : ~0u;  nc_y = in_y ? nc_y : 0u;
                     }
-                    *reinterpret_cast<uint2 *>(&S.le[c]) = make_uint2(le_a, le_b);
-                    const bool     has = (nc_a | nc_b) != 0u;
+                    S.le[c + (int)hi_x] = le_x;
+                    S.le[c + 1 - (int)hi_x] = le_y;
+                    const bool     has = (nc_x | nc_y) != 0u;
                     const uint32_t b = __ballot_sync(full, has);
                     const uint32_t rank = (uint32_t)__popc(b & lt_mask);
-                    const uint32_t x = nc_a ? nc_a : nc_b;
-                    const uint32_t p = (uint32_t)(32 * c) + (nc_a ? 0u : 32u) + (uint32_t)__ffs((int)x) - 1u;
+                    const uint32_t x = nc_x ? nc_x : nc_y;
+                    // bit index in load order -> byte offset in the slot: the quad index sits in bits 4..5
+                    const uint32_t p = (uint32_t)(32 * c) + ((((nc_x ? 0u : 32u) + (uint32_t)__ffs((int)x) - 1u) ^ swz) & 63u);
                     // exactly one candidate in the slot, and it is a '\n'
-                    redo |= (x & (x - 1u)) | (nc_a ? nc_b : 0u) | (has ? ((uint32_t)S.bytes[has ? p : 0u] ^ 0x0au) : 0u);
+                    redo |= (x & (x - 1u)) | (nc_x ? nc_y : 0u) | (has ? ((uint32_t)S.bytes[has ? p : 0u] ^ 0x0au) : 0u);
                     pk[it] = has ? (p + (rank << 20)) : kNoNl;
                     if (lane == 0) S.seg[it * kWarps + (int)warp] = b;
                 } else if (lane == 0) {
