@@ -229,7 +229,7 @@ constexpr int kChunks     = 2 * kSlots;                       // chunks = mask w
 constexpr int kSpan       = kChunks * 32;                     // bytes of staged text
 constexpr int kPrefix     = 16;                               // the bulk copy lands at bytes + kPrefix; the byte before the first
                                                               // record (a '\n') sits in [kPrefix - 1, 2 * kPrefix)
-constexpr int kStageMax   = kSpan - 48;                       // most bytes of one bulk copy: the data always ends below kSpan - 32
+constexpr int kStageMax   = kSpan - 80;                       // most bytes of one bulk copy: the data always ends below kSpan - 64
 constexpr int kSegs       = kIters * kWarps;                  // warp-iterations of the scan = segments of the newline ranking
 constexpr int kCacheContigs = 64;                             // contig table kept in shared memory when it fits
 constexpr int kCacheNames   = 1024;
@@ -830,7 +830,7 @@ __global__ void __launch_bounds__(kThreads, PSS_TALLY_CTAS_PER_SM) tally_kernel(
             const int64_t  gbase = (int64_t)gsrc - kPrefix;                       // global offset of bytes[0]
             const int      head = (int)((int64_t)pos - 1 - gbase);                // position of the byte before pos: 15..31
             int            want = want_full ? kStageMax : est;
-            want = (want + 16) & ~31; want -= 16;                                 // kPrefix + want is a multiple of 32
+            want = (want + 16) & ~63; want -= 16;                                 // kPrefix + want is a multiple of 64: whole slots
             if (want > kStageMax) want = kStageMax;
             const uint64_t left = len16 - gsrc;
             const bool     sees_end = left <= (uint64_t)want;                     // the copy reaches the end of the text
@@ -851,15 +851,15 @@ __global__ void __launch_bounds__(kThreads, PSS_TALLY_CTAS_PER_SM) tally_kernel(
 
             // bytes before the record start / after the end of the text are neutralised by the thread that scans them
             // (same thread, program order: no barrier).  The end of the buffer terminates the last line.
-            const int tail_chunk = data_end >> 5;
-            const int n_valid = sees_end ? tail_chunk + 1 : (data_end >> 5);      // chunks that hold text
+            const int tail_slot = data_end >> 6;
+            const int n_valid = 2 * (sees_end ? tail_slot + 1 : tail_slot);       // chunks that hold text: whole 64-byte slots
             if (tid == 0) {
                 S.bytes[kPrefix - 1] = pos == 0 ? '\n' : 'x';
                 for (int i = kPrefix; i < head; i++) S.bytes[i] = 'x';
             }
-            if (sees_end && tid == (uint32_t)((tail_chunk >> 1) % kThreads)) {   // the thread that scans this chunk
+            if (sees_end && tid == (uint32_t)(tail_slot % kThreads)) {            // the thread that scans this slot
                 S.bytes[data_end] = '\n';
-                for (int i = data_end + 1; i < 32 * (tail_chunk + 1); i++) S.bytes[i] = 'x';
+                for (int i = data_end + 1; i < 64 * (tail_slot + 1); i++) S.bytes[i] = 'x';
             }
 
             // ---- pass A: classify, rank newlines ----
@@ -886,21 +886,16 @@ __global__ void __launch_bounds__(kThreads, PSS_TALLY_CTAS_PER_SM) tally_kernel(
                     classify32_fast(q2, q3, one, le_y, nc_y);
                     le_x = __funnelshift_l(le_x, le_x, rot16);
                     le_y = __funnelshift_l(le_y, le_y, rot16);
-                    if ((it + 1) * 2 * kThreads > n_valid) {  // block-uniform: the step that runs over the end of the text
-                        const bool in_x = c + (int)hi_x < n_valid, in_y = c + 1 - (int)hi_x < n_valid;
-                        le_x = in_x ? le_x : ~0u;  nc_x = in_x ? nc_x : 0u;       // sentinels: every mask walk ends there
-                        le_y = in_y ? le_y : ~0u;  nc_y = in_y ? nc_y : 0u;
-                    }
                     S.le[c + (int)hi_x] = le_x;
                     S.le[c + 1 - (int)hi_x] = le_y;
-                    const bool     has = (nc_x | nc_y) != 0u;
+                    const bool     has = (nc_x | nc_y) != 0u && c < n_valid;      // slots past the text hold stale bytes
                     const uint32_t b = __ballot_sync(full, has);
                     const uint32_t rank = (uint32_t)__popc(b & lt_mask);
                     const uint32_t x = nc_x ? nc_x : nc_y;
                     // bit index in load order -> byte offset in the slot: the quad index sits in bits 4..5
                     const uint32_t p = (uint32_t)(32 * c) + ((((nc_x ? 0u : 32u) + (uint32_t)__ffs((int)x) - 1u) ^ swz) & 63u);
                     // exactly one candidate in the slot, and it is a '\n'
-                    redo |= (x & (x - 1u)) | (nc_x ? nc_y : 0u) | (has ? ((uint32_t)S.bytes[has ? p : 0u] ^ 0x0au) : 0u);
+                    redo |= has ? ((x & (x - 1u)) | (nc_x ? nc_y : 0u) | ((uint32_t)S.bytes[has ? p : 0u] ^ 0x0au)) : 0u;
                     pk[it] = has ? (p + (rank << 20)) : kNoNl;
                     if (lane == 0) S.seg[it * kWarps + (int)warp] = b;
                 } else if (lane == 0) {
@@ -908,6 +903,7 @@ __global__ void __launch_bounds__(kThreads, PSS_TALLY_CTAS_PER_SM) tally_kernel(
                 }
             }
             const int any_multi = __syncthreads_or((int)(redo != 0u));
+            if (tid < 8) S.le[n_valid + (int)tid] = ~0u;      // sentinels: every mask walk ends there (read after the next barrier)
 
             // ---- pass B: newline ordinals -> positions ----
             uint32_t n_nl;
