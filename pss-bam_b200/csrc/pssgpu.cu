@@ -383,7 +383,7 @@ int launch_tally(pssgpu_ctx *ctx, const uint8_t *d_sam, size_t len, uint64_t str
     const int      max_grid = MODE == kModeFragkon ? ctx->tally_grid_fk : ctx->tally_grid_pss;
     // ranges handed out by an atomic counter: about eight per CTA on large inputs, never below 128 KiB
     uint64_t rb = len / ((uint64_t)max_grid * 8u);
-    if (const char *e = getenv("PSSGPU_RANGE_KB")) rb = strtoull(e, nullptr, 10) << 10;
+    if (const char *e = getenv("PSSGPU_RANGE_KB")) rb = std::max<uint64_t>(1, strtoull(e, nullptr, 10)) << 10;   // developer / test switch
     else rb = std::min<uint64_t>(std::max<uint64_t>(rb, 128u << 10), 1u << 20);
     rb = (rb + 31) & ~31ull;
     const uint64_t n_ranges = (len + rb - 1) / rb;

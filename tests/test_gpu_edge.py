@@ -117,6 +117,28 @@ def test_control_bytes_that_look_like_newlines(small):
     _check(ctx, ora, b"\r\n".join(lines[:2000]) + b"\r\n")        # CRLF text
 
 
+def test_tiny_ranges(small, monkeypatch):
+    """Ranges of 1 KiB and 3 KiB (a developer switch of the library): a handful of records per range, so every kind of
+    range boundary occurs -- inside a record, right after a newline, inside a line longer than the range or a tile."""
+    g, ora, ctx = small
+    rng = random.Random(5)
+    good = Synth.sam(reads_cfg_config2(seed=41, min_len=30, max_len=150), g, 0, 5000).split(b"\n")[:-1]
+    lines = []
+    for i, ln in enumerate(good):
+        lines.append(_mutate(rng, ln) if rng.random() < 0.1 else ln)
+        if i % 500 == 250:
+            lines.append(ln + b"\tXX:Z:" + b"t" * (3000 + 40 * i))           # longer than a range
+        if i == 2500:
+            lines.append(b"q" * 70000)                                      # longer than a tile
+            lines.extend([b""] * 300)
+    sam = b"\n".join(lines) + b"\n"
+    for kb in ("1", "3"):
+        monkeypatch.setenv("PSSGPU_RANGE_KB", kb)
+        _check(ctx, ora, sam, fk=FkParams(klen=6))
+        _check(ctx, ora, sam[:-1])                                          # no final newline
+    monkeypatch.delenv("PSSGPU_RANGE_KB")
+
+
 def test_exotic_context_bytes(small):
     g, ora, ctx = small
     sam = Synth.sam(reads_cfg_config1(seed=9, read_len=40), g, 0, 200).split(b"\n")[:-1]
