@@ -223,8 +223,11 @@ __global__ void __launch_bounds__(256) widen_kernel(const unsigned int *__restri
 #endif
 constexpr int kThreads    = PSS_TALLY_THREADS;                // threads per CTA = records a CTA takes per tile
 constexpr int kWarps      = kThreads / 32;
-constexpr int kIters      = PSS_TALLY_ITERS;                  // 64-byte slots (two 32-byte chunks) per thread and tile
-constexpr int kSlots      = kIters * kThreads;
+#ifndef PSS_TALLY_SLOTS
+#define PSS_TALLY_SLOTS (PSS_TALLY_ITERS * PSS_TALLY_THREADS)
+#endif
+constexpr int kSlots      = PSS_TALLY_SLOTS;                  // 64-byte slots (two 32-byte chunks) of one tile; whole warps
+constexpr int kIters      = (kSlots + kThreads - 1) / kThreads;   // steps of the scan (the last one may leave warps out)
 constexpr int kChunks     = 2 * kSlots;                       // chunks = mask words of one tile
 constexpr int kSpan       = kChunks * 32;                     // bytes of staged text
 constexpr int kPrefix     = 16;                               // the bulk copy lands at bytes + kPrefix; the byte before the first
@@ -235,7 +238,7 @@ constexpr int kCacheContigs = 64;                             // contig table ke
 constexpr int kCacheNames   = 1024;
 constexpr int kCacheSlots   = 1024;                          // u8 slots of the collision-free name table
 constexpr int kFlushEvery   = 1900;                           // warp iterations between flushes of the 16-bit partial sums
-static_assert(kThreads % 32 == 0 && kSegs <= 64, "the newline ranking keeps at most two segment counts per lane");
+static_assert(kThreads % 32 == 0 && kSlots % 32 == 0 && kSegs <= 64, "the newline ranking keeps at most two segment counts per lane");
 static_assert(kThreads >= kCacheContigs, "one thread per cached contig fills the shared-memory table");
 static_assert(kSpan < (1 << 20) && kThreads <= 1024, "pass A packs a newline position into 20 bits and its rank into the rest");
 
@@ -872,7 +875,7 @@ __global__ void __launch_bounds__(kThreads, PSS_TALLY_CTAS_PER_SM) tally_kernel(
 #pragma unroll
             for (int it = 0; it < kIters; it++) {
                 pk[it] = kNoNl;
-                if (it * 2 * kThreads < n_valid + 8) {        // block-uniform
+                if (it * 2 * kThreads < n_valid + 8 && ((it + 1) * kThreads <= kSlots || it * kThreads + (int)tid < kSlots)) {   // block- / warp-uniform
                     const int      c = 2 * (it * kThreads + (int)tid);           // this thread's two chunks: c, c + 1
                     const uint8_t *src = S.bytes + 32 * c;
                     // the four 16-byte quads of the slot are loaded in the order 0^r, 1^r, 2^r, 3^r, r = (lane / 2) % 4:
