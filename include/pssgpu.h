@@ -87,6 +87,16 @@ typedef struct pssgpu_contig {
 int pssgpu_genome_upload(pssgpu_ctx *ctx, const pssgpu_contig *contigs, uint64_t n_contigs);
 /* Same, but each seq pointer is DEVICE memory holding the ASCII contig. */
 int pssgpu_genome_upload_device(pssgpu_ctx *ctx, const pssgpu_contig *contigs, uint64_t n_contigs);
+/* Packed-genome cache (takes the FASTA parse -- read_fasta's
+ * fgetc loop, fasta-genome-io.c:105-148, ~150 s for 3.1 Gb -- and the pack off
+ * the critical path of repeated runs).  save writes the resident genome (packed
+ * groups, contig table, names, exception list) to `path`; load makes the
+ * genome of such a file resident instead of pssgpu_genome_upload.  The file is
+ * tied to this library's packed layout (magic + layout version, sizes checked
+ * against the file length); a mismatch is PSSGPU_EINVAL and leaves no genome
+ * resident. */
+int pssgpu_genome_save(pssgpu_ctx *ctx, const char *path);
+int pssgpu_genome_load(pssgpu_ctx *ctx, const char *path);
 /* Total bases resident / bytes of HBM used by the packed genome. */
 int pssgpu_genome_info(const pssgpu_ctx *ctx, uint64_t *n_contigs, uint64_t *n_bases, uint64_t *hbm_bytes);
 

@@ -80,7 +80,7 @@ class _Timing(C.Structure):
 ABI_SYMBOLS = (
     "pssgpu_abi_version", "pssgpu_device_count", "pssgpu_init", "pssgpu_destroy", "pssgpu_last_error",
     "pssgpu_cuda_stream", "pssgpu_host_alloc", "pssgpu_host_free",
-    "pssgpu_genome_upload", "pssgpu_genome_upload_device", "pssgpu_genome_info",
+    "pssgpu_genome_upload", "pssgpu_genome_upload_device", "pssgpu_genome_save", "pssgpu_genome_load", "pssgpu_genome_info",
     "pssgpu_pss_default_params", "pssgpu_pss_begin", "pssgpu_feed", "pssgpu_feed_device", "pssgpu_sync",
     "pssgpu_pss_finish", "pssgpu_pss_finish_device", "pssgpu_get_stats", "pssgpu_both_begin", "pssgpu_get_fragkon_stats",
     "pssgpu_fragkon_default_params", "pssgpu_fragkon_begin", "pssgpu_fragkon_finish", "pssgpu_fragkon_finish_device",
@@ -117,6 +117,8 @@ def load_library():
     lib.pssgpu_genome_upload.argtypes = [P, C.POINTER(_Contig), C.c_uint64]
     lib.pssgpu_genome_upload_device.argtypes = [P, C.POINTER(_Contig), C.c_uint64]
     lib.pssgpu_genome_info.argtypes = [P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.pssgpu_genome_save.argtypes = [P, C.c_char_p]
+    lib.pssgpu_genome_load.argtypes = [P, C.c_char_p]
     lib.pssgpu_pss_default_params.argtypes = [C.POINTER(_PssParams)]
     lib.pssgpu_pss_default_params.restype = None
     lib.pssgpu_pss_begin.argtypes = [P, C.POINTER(_PssParams)]
@@ -232,6 +234,14 @@ class Context:
             keep.append(cid)
             arr[i] = _Contig(cid, ptr, n)
         self._ck(self.lib.pssgpu_genome_upload_device(self.h, arr, len(contigs)))
+
+    def save_genome(self, path):
+        """Write the resident packed genome to `path` (pssgpu_genome_save)."""
+        self._ck(self.lib.pssgpu_genome_save(self.h, os.fsencode(path)))
+
+    def load_genome(self, path):
+        """Make the packed genome of `path` resident (pssgpu_genome_load) instead of upload_genome()."""
+        self._ck(self.lib.pssgpu_genome_load(self.h, os.fsencode(path)))
 
     def genome_info(self):
         a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()

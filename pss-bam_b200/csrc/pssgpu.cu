@@ -514,6 +514,114 @@ void pssgpu_host_free(void *p) { if (p) cudaFreeHost(p); }
 int pssgpu_genome_upload(pssgpu_ctx *ctx, const pssgpu_contig *contigs, uint64_t n) { return upload_impl(ctx, contigs, n, false); }
 int pssgpu_genome_upload_device(pssgpu_ctx *ctx, const pssgpu_contig *contigs, uint64_t n) { return upload_impl(ctx, contigs, n, true); }
 
+// ---- packed-genome cache ------------------------------------------------------
+namespace {
+struct CacheHeader {
+    char     magic[8];            // "PSSGPUG" + layout version
+    uint64_t n_contigs, n_groups, n_bases, names_bytes, n_exc, hash_size;
+    uint32_t cc_seed, cc_ok, exc_overflow, pad_bases;
+};
+const char kCacheMagic[8] = { 'P', 'S', 'S', 'G', 'P', 'U', 'G', 1 };
+constexpr size_t kCachePiece = 64ull << 20;
+
+bool write_dev(FILE *f, const void *d, size_t bytes, std::vector<char> &buf)
+{
+    for (size_t off = 0; off < bytes; off += kCachePiece) {
+        const size_t nb = std::min(kCachePiece, bytes - off);
+        if (cudaMemcpy(buf.data(), (const char *)d + off, nb, cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+        if (fwrite(buf.data(), 1, nb, f) != nb) return false;
+    }
+    return true;
+}
+bool read_dev(FILE *f, void *d, size_t bytes, std::vector<char> &buf)
+{
+    for (size_t off = 0; off < bytes; off += kCachePiece) {
+        const size_t nb = std::min(kCachePiece, bytes - off);
+        if (fread(buf.data(), 1, nb, f) != nb) return false;
+        if (cudaMemcpy((char *)d + off, buf.data(), nb, cudaMemcpyHostToDevice) != cudaSuccess) return false;
+    }
+    return true;
+}
+}  // namespace
+
+int pssgpu_genome_save(pssgpu_ctx *ctx, const char *path)
+{
+    if (!ctx || !path) return fail(ctx, PSSGPU_EINVAL, "genome_save: null argument");
+    if (!ctx->have_genome) return fail(ctx, PSSGPU_ENOGENOME, "genome_save: no genome resident");
+    Bind bind(ctx);
+    CU(cudaStreamSynchronize(ctx->stream));
+    FILE *f = fopen(path, "wb");
+    if (!f) return fail(ctx, PSSGPU_EINVAL, "genome_save: cannot create %s", path);
+    CacheHeader h;
+    memset(&h, 0, sizeof h);
+    memcpy(h.magic, kCacheMagic, 8);
+    h.n_contigs = ctx->n_contigs; h.n_groups = ctx->n_groups; h.n_bases = ctx->n_bases; h.names_bytes = ctx->names_bytes;
+    h.n_exc = ctx->n_exc; h.hash_size = (uint64_t)ctx->hash_mask + 1; h.cc_seed = ctx->cc_seed; h.cc_ok = ctx->cc_ok;
+    h.exc_overflow = ctx->exc_overflow ? 1u : 0u; h.pad_bases = (uint32_t)kPadBases;
+    std::vector<char> buf(kCachePiece);
+    bool ok = fwrite(&h, sizeof h, 1, f) == 1
+           && write_dev(f, ctx->d_contigs, h.n_contigs * sizeof(DevContig), buf)
+           && write_dev(f, ctx->d_names, h.names_bytes, buf)
+           && write_dev(f, ctx->d_hash, h.hash_size * sizeof(uint32_t), buf)
+           && write_dev(f, ctx->d_exc_pos, h.n_exc * sizeof(uint64_t), buf)
+           && write_dev(f, ctx->d_exc_chr, h.n_exc, buf)
+           && write_dev(f, ctx->d_groups, h.n_groups * sizeof(uint64_t), buf);
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) { remove(path); return fail(ctx, PSSGPU_EINVAL, "genome_save: writing %s failed", path); }
+    ctx->d2h_bytes += h.n_groups * sizeof(uint64_t);
+    return PSSGPU_OK;
+}
+
+int pssgpu_genome_load(pssgpu_ctx *ctx, const char *path)
+{
+    if (!ctx || !path) return fail(ctx, PSSGPU_EINVAL, "genome_load: null argument");
+    Bind bind(ctx);
+    CU(cudaStreamSynchronize(ctx->stream));
+    free_genome(ctx);
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(ctx, PSSGPU_EINVAL, "genome_load: cannot open %s", path);
+    CacheHeader h;
+    bool ok = fread(&h, sizeof h, 1, f) == 1 && memcmp(h.magic, kCacheMagic, 8) == 0 && h.pad_bases == (uint32_t)kPadBases;
+    uint64_t want = 0;
+    if (ok) {
+        ok = h.n_contigs <= 0x7fffffffull && h.names_bytes <= 0xfffffff0ull && h.n_exc <= kExcCap && h.n_groups >= 2
+          && h.n_groups < (1ull << 40) && h.hash_size >= 16 && (h.hash_size & (h.hash_size - 1)) == 0 && h.hash_size <= (1ull << 32);
+        want = sizeof h + h.n_contigs * sizeof(DevContig) + h.names_bytes + h.hash_size * sizeof(uint32_t) + h.n_exc * 9
+             + h.n_groups * sizeof(uint64_t);
+        if (ok && (fseek(f, 0, SEEK_END) != 0 || (uint64_t)ftell(f) != want || fseek(f, (long)sizeof h, SEEK_SET) != 0)) ok = false;
+    }
+    if (!ok) { fclose(f); return fail(ctx, PSSGPU_EINVAL, "genome_load: %s is not a packed genome of this library version", path); }
+    std::vector<char> buf(kCachePiece);
+    cudaError_t e = cudaMalloc(&ctx->d_contigs, std::max<size_t>(1, h.n_contigs) * sizeof(DevContig));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_names, h.names_bytes + 16);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_hash, h.hash_size * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_exc_pos, kExcCap * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_exc_chr, kExcCap);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_groups, h.n_groups * sizeof(uint64_t));
+    ok = e == cudaSuccess
+      && read_dev(f, ctx->d_contigs, h.n_contigs * sizeof(DevContig), buf)
+      && read_dev(f, ctx->d_names, h.names_bytes, buf)
+      && read_dev(f, ctx->d_hash, h.hash_size * sizeof(uint32_t), buf)
+      && read_dev(f, ctx->d_exc_pos, h.n_exc * sizeof(uint64_t), buf)
+      && read_dev(f, ctx->d_exc_chr, h.n_exc, buf)
+      && read_dev(f, ctx->d_groups, h.n_groups * sizeof(uint64_t), buf);
+    fclose(f);
+    if (!ok) {
+        free_genome(ctx);
+        cudaGetLastError();
+        return fail(ctx, e == cudaErrorMemoryAllocation ? PSSGPU_ENOMEM : PSSGPU_EINVAL, "genome_load: reading %s failed", path);
+    }
+    ctx->hash_mask = (uint32_t)(h.hash_size - 1);
+    ctx->names_bytes = (uint32_t)h.names_bytes;
+    ctx->cc_seed = h.cc_seed; ctx->cc_ok = h.cc_ok;
+    ctx->n_groups = h.n_groups; ctx->n_bases = h.n_bases; ctx->n_contigs = h.n_contigs;
+    ctx->n_exc = (uint32_t)h.n_exc; ctx->exc_overflow = h.exc_overflow != 0;
+    ctx->genome_bytes = h.n_groups * sizeof(uint64_t) + kExcCap * 9 + h.n_contigs * sizeof(DevContig) + h.names_bytes + h.hash_size * 4;
+    ctx->h2d_bytes += h.n_groups * sizeof(uint64_t);
+    ctx->have_genome = true;
+    return PSSGPU_OK;
+}
+
 int pssgpu_genome_info(const pssgpu_ctx *ctx, uint64_t *n_contigs, uint64_t *n_bases, uint64_t *hbm_bytes)
 {
     if (!ctx || !ctx->have_genome) return PSSGPU_ENOGENOME;

@@ -66,9 +66,7 @@ int main(int argc, char *argv[])
 
     pssgpu_ctx *gpu = pss_open_device();
     fprintf(stderr, "Reading genome sequence from: %s\n", fasta_fn);
-    Genome *genome = init_genome(fasta_fn);
-    if (!genome) { fprintf(stderr, "ERROR: cannot read %s\n", fasta_fn); return 1; }
-    if (pss_upload_genome(gpu, genome) != PSSGPU_OK) pss_die(gpu, "genome upload");
+    pss_resident_genome(gpu, fasta_fn, NULL);
     fprintf(stderr, "Finished loading genome.\nCounting kmer contexts for: %s\n", bam_fn);
 
     if (pssgpu_fragkon_begin(gpu, &par) != PSSGPU_OK) pss_die(gpu, "fragkon_begin");
@@ -82,7 +80,6 @@ int main(int argc, char *argv[])
     pss_write_fragkon(stdout, fasta_fn, bam_fn, par.klen, fp, tp);
 
     free(fp); free(tp);
-    destroy_genome(genome);
     pssgpu_destroy(gpu);
     fprintf(stderr, "Done.\n");
     return 0;

@@ -37,15 +37,14 @@ int main(int argc, char *argv[])
     if (!fa_in || !*fa_in) help();
 
     pssgpu_ctx *gpu = pss_open_device();
-    Genome *genome = init_genome(fa_in);
-    if (!genome) { fprintf(stderr, "ERROR: cannot read %s\n", fa_in); return 1; }
-    if (pss_upload_genome(gpu, genome) != PSSGPU_OK) pss_die(gpu, "genome upload");
+    unsigned long n_seqs = 0;
+    pss_resident_genome(gpu, fa_in, &n_seqs);
     if (k < 1 || k > 14) { fprintf(stderr, "ERROR: k must be in [1,14] on this build\n"); return 1; }
 
     const size_t bins = (size_t)1 << (2 * k);
     uint64_t *counts = (uint64_t *)calloc(bins, sizeof *counts);
     if (pssgpu_kmer_spectrum(gpu, k, counts) != PSSGPU_OK) pss_die(gpu, "kmer_spectrum");
-    pss_write_spectrum(stdout, genome->n_seqs, k, counts);
+    pss_write_spectrum(stdout, n_seqs, k, counts);
     free(counts);
     pssgpu_destroy(gpu);
     exit(0);

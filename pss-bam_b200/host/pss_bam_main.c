@@ -78,9 +78,7 @@ int main(int argc, char *argv[])
     pssgpu_ctx *gpu = pss_open_device();
 
     fprintf(stderr, "Reading genome sequence from:\n%s\n", fasta_fn);
-    Genome *genome = init_genome(fasta_fn);
-    if (!genome) { fprintf(stderr, "ERROR: cannot read %s\n", fasta_fn); return 1; }
-    if (pss_upload_genome(gpu, genome) != PSSGPU_OK) pss_die(gpu, "genome upload");
+    pss_resident_genome(gpu, fasta_fn, NULL);
     fprintf(stderr, "Finished loading genome.\nCounting matches/mismatches from:\n%s\n", bam_fn);
 
     if (pssgpu_pss_begin(gpu, &par) != PSSGPU_OK) pss_die(gpu, "pss_begin");
@@ -107,7 +105,6 @@ int main(int argc, char *argv[])
                     (unsigned long long)st.filtered, (unsigned long long)st.parse_fail, (unsigned long long)st.undefined);
     }
     free(fwd); free(rev); free(fwd_rates); free(rev_rates);
-    destroy_genome(genome);
     pssgpu_destroy(gpu);
     fprintf(stderr, "Done.\n");
     return rc;

@@ -3,6 +3,7 @@
 
 #include <stdlib.h>
 #include <string.h>
+#include <sys/stat.h>
 
 #define PSS_PIPE_CHUNK (32u << 20)
 
@@ -35,6 +36,36 @@ int pss_upload_genome(pssgpu_ctx *ctx, const Genome *genome)
     rc = pssgpu_genome_upload(ctx, c, genome->n_seqs);
     free(c);
     return rc;
+}
+
+void pss_resident_genome(pssgpu_ctx *ctx, const char *fasta_fn, unsigned long *n_seqs)
+{
+    const char *env = getenv("PSSGPU_GENOME_CACHE");
+    char        cache[2 * MAX_FN_LEN + 16];
+    cache[0] = 0;
+    if (env && *env) {
+        if (strcmp(env, "1") == 0) snprintf(cache, sizeof cache, "%s.pssgpu", fasta_fn);
+        else {
+            const char *base = strrchr(fasta_fn, '/');
+            snprintf(cache, sizeof cache, "%s/%s.pssgpu", env, base ? base + 1 : fasta_fn);
+        }
+        struct stat sf, sc;
+        if (stat(fasta_fn, &sf) == 0 && stat(cache, &sc) == 0 && sc.st_mtime >= sf.st_mtime) {
+            uint64_t nc = 0;
+            if (pssgpu_genome_load(ctx, cache) == PSSGPU_OK && pssgpu_genome_info(ctx, &nc, NULL, NULL) == PSSGPU_OK) {
+                if (n_seqs) *n_seqs = (unsigned long)nc;
+                return;
+            }
+            fprintf(stderr, "WARNING: ignoring genome cache %s: %s\n", cache, pssgpu_last_error(ctx));
+        }
+    }
+    Genome *genome = init_genome(fasta_fn);
+    if (!genome) { fprintf(stderr, "ERROR: cannot read %s\n", fasta_fn); exit(1); }
+    if (pss_upload_genome(ctx, genome) != PSSGPU_OK) pss_die(ctx, "genome upload");
+    if (n_seqs) *n_seqs = (unsigned long)genome->n_seqs;
+    destroy_genome(genome);
+    if (cache[0] && pssgpu_genome_save(ctx, cache) != PSSGPU_OK)
+        fprintf(stderr, "WARNING: could not write genome cache %s: %s\n", cache, pssgpu_last_error(ctx));
 }
 
 FILE *pss_bam_to_sam(const char *bam_fn, const char *read_group)

@@ -11,6 +11,12 @@
 pssgpu_ctx *pss_open_device(void);
 /* Make init_genome()'s result device resident (pssgpu_genome_upload). */
 int pss_upload_genome(pssgpu_ctx *ctx, const Genome *genome);
+/* init_genome(fasta_fn) + pss_upload_genome(), or -- when $PSSGPU_GENOME_CACHE is set -- the packed-genome cache:
+ * "1" keeps it beside the FASTA as <fasta>.pssgpu, any other value names a directory for <basename>.pssgpu.  A cache
+ * at least as new as the FASTA is loaded instead of parsing the FASTA (read_fasta's fgetc loop is the reference's
+ * ~150 s for 3.1 Gb, fasta-genome-io.c:105-148); otherwise it is (re)written after the upload.  *n_seqs receives
+ * the number of FASTA records.  Exits with a message when the FASTA cannot be read. */
+void pss_resident_genome(pssgpu_ctx *ctx, const char *fasta_fn, unsigned long *n_seqs);
 /* popen("samtools view [-r RG] <bam>") -- the reference's only source of SAM text (pss-bam.c:148-162). */
 FILE *pss_bam_to_sam(const char *bam_fn, const char *read_group);
 /* Pump a SAM text stream into the open tally: fread into pinned memory, pssgpu_feed, flush at EOF.

@@ -68,3 +68,30 @@ def test_genome_kmer_count_cli(env, case):
                        cwd=d, env=e, capture_output=True)
     assert r.returncode == 0, r.stderr[-2000:]
     assert r.stdout == _gold(case["out"])
+
+
+def test_cli_with_packed_genome_cache(env):
+    """$PSSGPU_GENOME_CACHE: the first run writes <dir>/genome.fa.pssgpu, the second one loads it instead of parsing the
+    FASTA (made unreadable garbage in between would be noticed: the cache must be newer than the FASTA) -- same bytes."""
+    d, e = env
+    case = MAN["pss"][0]
+    cdir = os.path.join(d, "cache")
+    os.makedirs(cdir, exist_ok=True)
+    e2 = dict(e, PSSGPU_GENOME_CACHE=cdir)
+    cmd = [os.path.join(BIN, "pss-bam"), "-F", "genome.fa", "-B", case["sam"] + ".sam", "-o", "out", *case["args"]]
+    for rnd in range(2):
+        r = subprocess.run(cmd, cwd=d, env=e2, capture_output=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert os.path.exists(os.path.join(cdir, "genome.fa.pssgpu"))
+        assert open(os.path.join(d, "out.pss.counts.txt"), "rb").read() == _gold(case["counts"])
+        assert open(os.path.join(d, "out.pss.rates.txt"), "rb").read() == _gold(case["rates"])
+    gk = MAN["gkc"][0]
+    r = subprocess.run([os.path.join(BIN, "genome-kmer-count"), "-f", "genome.fa", "-k", str(gk["k"])], cwd=d, env=e2, capture_output=True)
+    assert r.returncode == 0 and r.stdout == _gold(gk["out"])
+    # a damaged cache is refused (with a warning) and the FASTA is parsed again
+    with open(os.path.join(cdir, "genome.fa.pssgpu"), "r+b") as f:
+        f.truncate(1000)
+    os.utime(os.path.join(cdir, "genome.fa.pssgpu"))
+    r = subprocess.run(cmd, cwd=d, env=e2, capture_output=True)
+    assert r.returncode == 0 and b"ignoring genome cache" in r.stderr
+    assert open(os.path.join(d, "out.pss.counts.txt"), "rb").read() == _gold(case["counts"])

@@ -204,6 +204,37 @@ def test_device_resident_input_and_reuse(small):
     ctx2.close()
 
 
+def test_packed_genome_save_and_load(small, tmp_path):
+    g, ora, ctx = small
+    sam = Synth.sam(reads_cfg_config2(seed=12), g, 0, 5000)
+    f, r, st = ora.pss(sam, PssParams())
+    path = str(tmp_path / "genome.pssgpu")
+    ctx.save_genome(path)
+    ctx2 = pkg.Context(0)
+    ctx2.load_genome(path)
+    assert ctx2.genome_info() == ctx.genome_info()
+    gf, gr = ctx2.pss(sam)
+    assert ctx2.stats() == st and np.array_equal(gf, f) and np.array_equal(gr, r)
+    for k in (4, 8, 11):
+        assert np.array_equal(ctx2.kmer_spectrum(k), ora.kmer_spectrum(k))
+    p = PssParams(up_ctx=b"*-.X", down_ctx=b"ACGT*")                        # needs the exception list of the cache
+    f2, r2, _ = ora.pss(sam, p)
+    gf2, gr2 = ctx2.pss(sam, _opts(p))
+    assert np.array_equal(gf2, f2) and np.array_equal(gr2, r2)
+    # not a cache / truncated cache: refused, no genome resident afterwards
+    bad = str(tmp_path / "bad.pssgpu")
+    with open(path, "rb") as src, open(bad, "wb") as dst:
+        dst.write(src.read()[:-8])
+    for pth in (bad, __file__, str(tmp_path / "missing")):
+        with pytest.raises(pkg.PssGpuError) as e:
+            ctx2.load_genome(pth)
+        assert e.value.code == -1
+    with pytest.raises(pkg.PssGpuError) as e:
+        ctx2.pss_begin(pkg.PssOptions())
+    assert e.value.code == -4
+    ctx2.close()
+
+
 def test_error_codes(small):
     g, ora, ctx = small
     with pytest.raises(pkg.PssGpuError) as e:
