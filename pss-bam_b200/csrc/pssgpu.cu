@@ -71,6 +71,8 @@ struct pssgpu_ctx {
     size_t    carry_len = 0;
     uint64_t  fed_bytes = 0;                  // bytes handed to pssgpu_feed* since *_begin
     cudaEvent_t copy_done = nullptr;
+    cudaStream_t copy_stream = nullptr;       // H2D staging copies run here, so that the tally of piece i overlaps the copy of piece i + 1
+    cudaEvent_t ev_copied[2] = { nullptr, nullptr }, ev_tallied[2] = { nullptr, nullptr };
 
     // timing
     bool      timing = false;
@@ -457,6 +459,11 @@ int pssgpu_init(int device, pssgpu_ctx **out)
     c->sm_count = prop.multiProcessorCount;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->copy_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2; i++) {
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_tallied[i], cudaEventDisableTiming);
+    }
     {   // every instantiation needs its dynamic shared memory raised above the 48 KB default
         const void *kernels[] = {
             (const void *)tally_kernel<kModePss, 9, 17>, (const void *)tally_kernel<kModePss, 9, 0>, (const void *)tally_kernel<kModePss, 16, 0>,
@@ -472,6 +479,8 @@ int pssgpu_init(int device, pssgpu_ctx **out)
         fail(nullptr, PSSGPU_ECUDA, "pssgpu_init: %s (occupancy %d/%d)", cudaGetErrorString(e), occ_p, occ_f);
         if (c->stream) cudaStreamDestroy(c->stream);
         if (c->copy_done) cudaEventDestroy(c->copy_done);
+        if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+        for (int i = 0; i < 2; i++) { if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); if (c->ev_tallied[i]) cudaEventDestroy(c->ev_tallied[i]); }
         delete c;
         return PSSGPU_ECUDA;
     }
@@ -494,6 +503,8 @@ void pssgpu_destroy(pssgpu_ctx *ctx)
     for (auto &p : ctx->ev) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (int i = 0; i < 2; i++) { if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]); if (ctx->ev_tallied[i]) cudaEventDestroy(ctx->ev_tallied[i]); }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -743,6 +754,9 @@ int pssgpu_feed(pssgpu_ctx *ctx, const char *sam, size_t len, int last)
     Bind bind(ctx);
     for (int s = 0; s < 2; s++)
         if (!ctx->d_stage[s]) CU(cudaMalloc(&ctx->d_stage[s], kStageCap + 64));
+    // Two staging buffers, two streams: the copies queue up on copy_stream, the tallies on the context's stream; a
+    // tally waits for its copy (ev_copied), a copy into a buffer waits for the tally that last read it (ev_tallied).
+    // The PCIe link then never idles behind a kernel launch.
     size_t off = 0;
     bool   copied = false;
     while (off < len) {
@@ -751,19 +765,25 @@ int pssgpu_feed(pssgpu_ctx *ctx, const char *sam, size_t len, int last)
         const size_t plen = std::min(std::min(len - off, kFeedPiece), room);
         const char  *piece = sam + off;
         const char  *nl = (const char *)memrchr(piece, '\n', plen);
-        uint8_t     *slot = ctx->d_stage[ctx->cur];
+        const int    cur = ctx->cur;
+        uint8_t     *slot = ctx->d_stage[cur];
         if (!nl) {                       // no line ends in this piece: it only grows the carry
-            CU(cudaMemcpyAsync(slot + ctx->carry_len, piece, plen, cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaMemcpyAsync(slot + ctx->carry_len, piece, plen, cudaMemcpyHostToDevice, ctx->copy_stream));
             ctx->carry_len += plen;
         } else {
             const size_t cut = (size_t)(nl - piece) + 1, tail = plen - cut;
-            CU(cudaMemcpyAsync(slot + ctx->carry_len, piece, cut, cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaMemcpyAsync(slot + ctx->carry_len, piece, cut, cudaMemcpyHostToDevice, ctx->copy_stream));
+            CU(cudaEventRecord(ctx->ev_copied[cur], ctx->copy_stream));
             const size_t   klen = ctx->carry_len + cut;
             const uint64_t soff = ctx->fed_bytes + off - ctx->carry_len;
+            CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[cur], 0));
             int rc = launch_tally_mode(ctx, slot, klen, soff);
             if (rc != PSSGPU_OK) return rc;
+            CU(cudaEventRecord(ctx->ev_tallied[cur], ctx->stream));
             ctx->cur ^= 1;
-            if (tail) CU(cudaMemcpyAsync(ctx->d_stage[ctx->cur], piece + cut, tail, cudaMemcpyHostToDevice, ctx->stream));
+            // the other buffer: free once the tally that read it (two pieces ago) is done
+            CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_tallied[ctx->cur], 0));
+            if (tail) CU(cudaMemcpyAsync(ctx->d_stage[ctx->cur], piece + cut, tail, cudaMemcpyHostToDevice, ctx->copy_stream));
             ctx->carry_len = tail;
         }
         ctx->h2d_bytes += plen;
@@ -773,14 +793,20 @@ int pssgpu_feed(pssgpu_ctx *ctx, const char *sam, size_t len, int last)
     ctx->fed_bytes += len;
     if (last && ctx->carry_len) {        // final line without '\n' (fgets hands it out as is)
         const uint64_t soff = ctx->fed_bytes - ctx->carry_len;
-        int rc = launch_tally_mode(ctx, ctx->d_stage[ctx->cur], ctx->carry_len, soff);
+        const int      cur = ctx->cur;
+        CU(cudaEventRecord(ctx->ev_copied[cur], ctx->copy_stream));
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[cur], 0));
+        int rc = launch_tally_mode(ctx, ctx->d_stage[cur], ctx->carry_len, soff);
         if (rc != PSSGPU_OK) return rc;
+        CU(cudaEventRecord(ctx->ev_tallied[cur], ctx->stream));
         ctx->cur ^= 1;
+        CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_tallied[ctx->cur], 0));
         ctx->carry_len = 0;
     }
     if (copied) {                        // the caller may reuse `sam` as soon as we return
+        CU(cudaStreamSynchronize(ctx->copy_stream));
+        // the tallies are waited for as well: keeps the contract simple (errors surface here, not at finish)
         CU(cudaEventRecord(ctx->copy_done, ctx->stream));
-        // the record sits behind the last tally launch too; waiting for it keeps the contract simple
         CU(cudaEventSynchronize(ctx->copy_done));
     }
     return PSSGPU_OK;
