@@ -117,6 +117,28 @@ def test_control_bytes_that_look_like_newlines(small):
     _check(ctx, ora, b"\r\n".join(lines[:2000]) + b"\r\n")        # CRLF text
 
 
+def test_high_bytes_next_to_separators(small):
+    """SWAR classification next to bytes >= 0x80 (UTF-8 names, binary junk): no carry may leak into a neighbouring
+    space, tab or newline."""
+    g, ora, ctx = small
+    good = Synth.sam(reads_cfg_config2(seed=51, min_len=30, max_len=150), g, 0, 6000).split(b"\n")[:-1]
+    rng = random.Random(23)
+    lines = []
+    for i, ln in enumerate(good):
+        if 1000 <= i < 5000 and rng.random() < 0.03:
+            f = ln.split(b"\t")
+            k = rng.randrange(6)
+            if k == 0: f[0] = b"r\xc3\xa9ad" + f[0]                         # UTF-8 in QNAME
+            elif k == 1: f[-1] = f[-1] + b"\tCO:Z:caf\xff comment \xa1 x"     # 0xff / 0xa1 right before a space
+            elif k == 2: f[0] = f[0] + b"\xa1"                                # high byte right before a tab
+            elif k == 3: f[-1] = f[-1] + b"\xfe"                              # ... right before the newline
+            elif k == 4: f[9] = f[9][:5] + b"\x80" + f[9][6:]                 # 0x80: no carry, still not ASCII
+            elif k == 5: ln = b"\xff " + ln; f = None                         # 0xff then the space that sscanf skips
+            if f is not None: ln = b"\t".join(f)
+        lines.append(ln)
+    _check(ctx, ora, b"\n".join(lines) + b"\n", fk=FkParams(klen=6))
+
+
 def test_tiny_ranges(small, monkeypatch):
     """Ranges of 1 KiB and 3 KiB (a developer switch of the library): a handful of records per range, so every kind of
     range boundary occurs -- inside a record, right after a newline, inside a line longer than the range or a tile."""
