@@ -51,7 +51,7 @@ def test_random_reads_default_options(world, seed):
 
 
 @pytest.mark.parametrize("p", [
-    PssParams(region_len=0), PssParams(region_len=1), PssParams(region_len=4), PssParams(region_len=16),
+    PssParams(region_len=0), PssParams(region_len=1), PssParams(region_len=4), PssParams(region_len=7), PssParams(region_len=16),
     PssParams(region_len=29), PssParams(region_len=30), PssParams(region_len=31), PssParams(region_len=47),
     PssParams(region_len=150), PssParams(min_len=35, max_len=90), PssParams(min_mq=37),
     PssParams(min_mq=-1), PssParams(up_ctx=b"C", down_ctx=b"G"), PssParams(up_ctx=b"ACGTN", down_ctx=b"acgt"),
