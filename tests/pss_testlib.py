@@ -54,7 +54,7 @@ class _ReadsCfg(C.Structure):
         ("p_badflag", C.c_double), ("p_paired", C.c_double), ("p_qualstar", C.c_double),
         ("p_unknown_contig", C.c_double), ("p_edge", C.c_double), ("p_read_n", C.c_double),
         ("damage5", C.c_double), ("damage3", C.c_double), ("err", C.c_double),
-        ("max_mapq", C.c_uint32), ("with_tags", C.c_uint32),
+        ("max_mapq", C.c_uint32), ("with_tags", C.c_uint32), ("sorted_total", C.c_uint64),
     ]
 
 

@@ -40,6 +40,7 @@ typedef struct synth_reads_cfg {
     double   err;                   /* uniform substitution error per base        */
     uint32_t max_mapq;              /* MAPQ uniform 0..max_mapq                   */
     uint32_t with_tags;             /* append NM:i / MD:Z                         */
+    uint64_t sorted_total;          /* > 0: coordinate-sorted output -- read idx of sorted_total sits at that fraction of the genome */
 } synth_reads_cfg;
 
 /* Thread count for the generators (torchrun exports OMP_NUM_THREADS=1 to every rank). */
@@ -142,6 +143,8 @@ static size_t one_read(const synth_reads_cfg *C, uint64_t idx,
     rng_t    r = rng_at(C->seed, 7, idx);
     uint32_t n = C->min_len + (uint32_t)rng_below(&r, (uint64_t)(C->max_len - C->min_len) + 1);
     double   u = rng_unit(&r);
+    const int sorted = C->sorted_total > 0;
+    if (sorted) u = ((double)idx + 0.5) / (double)C->sorted_total;   /* contigs are picked by cumulative length: monotone in idx */
     uint32_t ci = 0;
     int      reverse, kind_indel, kind_clip, kind_badflag, kind_paired, kind_qstar, kind_unk, kind_edge;
     uint64_t L, start;     /* 0-based start */
@@ -176,6 +179,11 @@ static size_t one_read(const synth_reads_cfg *C, uint64_t idx,
         if (start + n > L) start = L - n;         /* tiny contigs */
     } else if (L >= (uint64_t)n + 64) {
         start = 32 + rng_below(&r, L - n - 64);
+        if (sorted) {                      /* position within the contig follows idx as well (ties broken by the read length) */
+            const double lo = ci ? ccum[ci - 1] : 0.0, hi = ccum[ci];
+            const double f = hi > lo ? (u - lo) / (hi - lo) : 0.0;
+            start = 32 + (uint64_t)(f * (double)(L - n - 64));
+        }
     } else {
         start = rng_below(&r, L - n + 1);         /* tiny contig: anywhere, edges included */
     }
