@@ -1,7 +1,7 @@
 // pss_kernels.cuh -- the sm_100a kernels of the pss-bam hot path.
 //
 //   pack_kernel      K6  ASCII contig -> 4-bit packed genome groups
-//   spectrum_kernel  K5  genome-kmer-count.c:68-79 + kmer.c:43-110 as a flat 4^k histogram
+//   spectrum_kernel / spectrum_smem_kernel  K5  genome-kmer-count.c:68-79 + kmer.c:43-110 as a flat 4^k histogram
 //   tally_kernel     K1-K4  SAM text tile -> records -> filters -> genome gather
 //                           -> pss-bam count tables / fragkon end-context histograms
 //
@@ -641,8 +641,8 @@ __device__ __forceinline__ void cta_epilogue(const TallyShared &T, const TallyAr
     if (MODE == kModeBoth && tid < kStN && T.stats_fk[tid]) atomicAdd(A.stats_fk + tid, (unsigned long long)T.stats_fk[tid]);
 }
 
-// Generic newline listing (a tile in which some 32-byte chunk holds two or more
-// newlines: lines shorter than 32 bytes, never real SAM): every thread walks
+// Exact newline listing (a tile in which some 64-byte slot holds two or more newline candidates -- lines shorter than
+// 64 bytes, never real SAM -- or a false candidate): every thread walks
 // 2 * kIters consecutive chunks, a block scan orders the counts, a second walk
 // stores the first kThreads + 1 positions.  Returns the number of newlines.
 __device__ __noinline__ uint32_t list_newlines_generic(TallySmem *Sp, int n_valid, uint32_t one)
@@ -780,10 +780,12 @@ __device__ __forceinline__ void process_batch(const TallyArgs &A, TallyShared &T
 // idle).  Per tile:
 //   stage     one cp.async.bulk (TMA engine) of as many bytes as kThreads
 //             records are expected to take (running estimate), on an mbarrier
-//   pass A    32 bytes per thread and step: SWAR classification into the
-//             "<= 0x20" mask word (stored, the record phase walks it) and the
-//             newline mask word, which is ranked on the spot with one ballot
-//             and one popcount and kept in a register
+//   pass A    a 64-byte slot per thread and step (bank-conflict free quad
+//             order): SWAR classification into the "<= 0x20" mask words
+//             (stored, the record phase walks them) and newline candidates
+//             ("<= 0x20 and bit 1", checked against the byte), ranked on the
+//             spot with one ballot and one popcount and kept in a register;
+//             two candidates in a slot or a false one: exact listing
 //   pass B    scan of the kSegs ballot counts (two shuffles deep), newline
 //             positions of ordinals 0..kThreads to shared memory
 //   records   one thread per record (process_batch)
