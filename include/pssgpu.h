@@ -104,7 +104,7 @@ int pssgpu_genome_info(const pssgpu_ctx *ctx, uint64_t *n_contigs, uint64_t *n_b
  * Mirrors the file-scope options of pss-bam.c:12-18 (same defaults via
  * pssgpu_pss_default_params). */
 typedef struct pssgpu_pss_params {
-    int           region_len;   /* -r  REGION_LEN   (default 15)          */
+    int           region_len;   /* -r  REGION_LEN   (default 15); 0..2045 */
     unsigned long min_len;      /* -l  MIN_READ_LEN (default 0)           */
     unsigned long max_len;      /* -L  MAX_READ_LEN (default 250000000)   */
     int           min_mq;       /* -q  MIN_MQ       (default 0)           */
@@ -139,7 +139,10 @@ int pssgpu_feed(pssgpu_ctx *ctx, const char *sam_bytes, size_t len, int last);
 
 /* Same for SAM text already resident in device memory.  `d_sam` must be
  * 16-byte aligned and hold WHOLE lines (last byte '\n'); it must stay valid
- * until the next pssgpu_*_finish / pssgpu_sync.  No copy is made. */
+ * until the next pssgpu_*_finish / pssgpu_sync.  No copy is made.  The bulk
+ * copies of the kernel move 16-byte units: up to 15 bytes past `len` are
+ * read (never interpreted) -- inside the allocation granule of any buffer that
+ * came from cudaMalloc. */
 int pssgpu_feed_device(pssgpu_ctx *ctx, const void *d_sam, size_t len);
 
 /* Wait for all fed bytes to be tallied. */
