@@ -75,7 +75,7 @@ for rep in range(2):
     print(f"host feed (pinned): {dt * 1e3:.1f} ms  {n / dt / 1e9:.2f} GB/s  {a.reads / dt / 1e6:.2f} M reads/s  kernels {tm['kernel_ms']:.3f} ms in {tm['launches']} launches")
     print(ctx.stats())
 
-for k in (8, 12):
+for k in (7, 8, 9, 10, 12):
     ctx.timing_reset(True)
     c = ctx.kmer_spectrum(k)
     tm = ctx.timing()
