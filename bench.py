@@ -228,6 +228,64 @@ def main_reference(a):
     print(json.dumps(line), flush=True)
 
 
+def config0_case(pkg, device, torch, with_reference):
+    """BASELINE.json configs[0], the case the reference runs as is: 10 Mb genome (4 x 2.5 Mb), 1 M unpaired 50-bp reads
+    with 5' C->T / 3' G->A damage.  Whole-program view on both sides: genome made resident + tally + tables, against the
+    unmodified reference binary on one core (it has no threads) -- with its FASTA load also given separately."""
+    from pss_testlib import Synth, reads_cfg_config1
+    g = Synth.genome(GENOME_SEED + 2, [2_500_000] * 4, n_frac=0.01, lower_frac=0.03)
+    n = 1_000_000
+    cfg = reads_cfg_config1(seed=READS_SEED + 1)
+    cap = Synth.sam_bound(cfg, 0, n)
+    host = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+    nb = Synth.sam_into(cfg, g, 0, n, host.data_ptr(), cap)
+    out = {"reads": n, "sam_bytes": int(nb), "genome_bases": 10_000_000}
+    c2 = pkg.Context(device)
+    try:
+        best = {}
+        for _ in range(3):
+            t0 = time.perf_counter()
+            c2.upload_genome(list(zip(g.names, g.seqs)))
+            t1 = time.perf_counter()
+            c2.pss_begin(pkg.PssOptions())
+            c2.timing_reset(True)
+            c2.feed_ptr(host.data_ptr(), nb, last=True)
+            fwd, rev = c2.pss_finish()
+            t2 = time.perf_counter()
+            cur = {"gpu_genome_upload_ms": (t1 - t0) * 1e3, "gpu_tally_from_host_ms": (t2 - t1) * 1e3,
+                   "gpu_kernel_ms": c2.timing()["kernel_ms"]}
+            if not best or cur["gpu_tally_from_host_ms"] < best["gpu_tally_from_host_ms"]:
+                best = cur
+        out.update(best)
+        out["gpu_reads_per_s_from_host"] = n / (best["gpu_tally_from_host_ms"] * 1e-3)
+        out["counted"] = c2.stats()["counted"]
+    finally:
+        c2.close()
+    d, exe, shim = ref_paths()
+    if with_reference and os.path.exists(exe) and os.path.exists(shim):
+        work = tempfile.mkdtemp(prefix="pssbench_cfg0_")
+        try:
+            with open(os.path.join(work, "genome.fa"), "wb") as f:
+                f.write(g.fasta_bytes())
+            with open(os.path.join(work, "reads.sam"), "wb") as f:
+                f.write(bytes(host[:nb].numpy()))
+            open(os.path.join(work, "empty.sam"), "wb").close()
+            env = dict(os.environ)
+            env["PATH"] = d + os.pathsep + env.get("PATH", "")
+            def run(sam):
+                t0 = time.perf_counter()
+                subprocess.run([exe, "-F", "genome.fa", "-B", sam, "-o", "out"], cwd=work, env=env, check=True,
+                               stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                return time.perf_counter() - t0
+            load = run("empty.sam")
+            total = run("reads.sam")
+            out.update({"reference_1core_total_s": total, "reference_1core_fasta_load_s": load,
+                        "reference_reads_per_s": n / max(total - load, 1e-9)})
+        finally:
+            shutil.rmtree(work, ignore_errors=True)
+    return out
+
+
 # ----------------------------------------------------------------------------------------------- B200 arm
 def main_b200(a):
     import torch
@@ -391,6 +449,8 @@ def main_b200(a):
                                                  "bound": "shared-memory atomics / instruction issue (not HBM)" if k <= 9
                                                  else "L2 atomics (not HBM)"} for k, ms in spec.items()}}
         del counts
+        if rank == 0:
+            other["config0_10Mb_1M_50bp"] = config0_case(pkg, local, torch, not a.no_cpu_baseline)
     except Exception as ex:                                   # never let the side measurements break the contract line
         other = {"error": f"{type(ex).__name__}: {ex}"}
 
