@@ -23,13 +23,15 @@ ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--mode", default="pss")
 ap.add_argument("--k", type=int, default=8)
 ap.add_argument("--tally-only", action="store_true")
+ap.add_argument("--min-len", type=int, default=30)
+ap.add_argument("--max-len", type=int, default=150)
 ap.add_argument("--sorted", action="store_true", help="coordinate-sorted reads (a real BAM): genome gathers hit L2")
 a = ap.parse_args()
 
 t = time.time()
 nc = 8
 g = Synth.genome(1, [a.genome_mb * 1_000_000 // nc] * nc, n_frac=0.01, lower_frac=0.03)
-cfg = reads_cfg_config1(3) if a.config == 1 else reads_cfg_config2(4)
+cfg = reads_cfg_config1(3) if a.config == 1 else reads_cfg_config2(4, min_len=a.min_len, max_len=a.max_len)
 if a.sorted:
     cfg.sorted_total = a.reads
 cap = Synth.sam_bound(cfg, 0, a.reads)
