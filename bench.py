@@ -449,7 +449,7 @@ def main_b200(a):
                                                  "bound": "shared-memory atomics / instruction issue (not HBM)" if k <= 9
                                                  else "L2 atomics (not HBM)"} for k, ms in spec.items()}}
         del counts
-        if rank == 0:
+        if rank == 0 and world == 1:
             other["config0_10Mb_1M_50bp"] = config0_case(pkg, local, torch, not a.no_cpu_baseline)
     except Exception as ex:                                   # never let the side measurements break the contract line
         other = {"error": f"{type(ex).__name__}: {ex}"}
