@@ -33,22 +33,41 @@ class PssGpuError(RuntimeError):
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/pssgpu.cu for sm_100a into lib/libpssgpu.so (nvcc cross-compiles without a GPU)."""
+    """Compile csrc/pssgpu.cu for sm_100a into lib/libpssgpu.so (nvcc cross-compiles without a GPU).
+
+    Safe under torchrun: one process builds (file lock), into a temporary file that is renamed into place, so no other
+    rank ever dlopens a half-written library."""
+    import fcntl
     srcs = [os.path.join(CSRC, f) for f in ("pssgpu.cu", "pss_kernels.cuh", "pss_record.h")]
     srcs.append(os.path.join(ROOT, "include", "pssgpu.h"))
     newest = max(os.path.getmtime(s) for s in srcs)
-    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:
+
+    def fresh():
+        return os.path.exists(LIB_PATH) and os.path.getsize(LIB_PATH) > 0 and os.path.getmtime(LIB_PATH) >= newest
+
+    if not force and fresh():
         return LIB_PATH
     os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB_PATH, os.path.join(CSRC, "pssgpu.cu")]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
-    if verbose:
-        print(r.stderr)
+    with open(os.path.join(os.path.dirname(LIB_PATH), ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and fresh():                         # another process built it while we waited
+                return LIB_PATH
+            nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+            tmp = LIB_PATH + f".tmp{os.getpid()}"
+            cmd = [nvcc, *NVCC_FLAGS, "-o", tmp, os.path.join(CSRC, "pssgpu.cu")]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+            os.replace(tmp, LIB_PATH)
+            if verbose:
+                print(r.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 

@@ -29,11 +29,32 @@ def _run(cmd, **kw):
     return r
 
 
+def _locked_build(target, newest, force, make_cmd):
+    """Build `target` unless it is up to date: one process at a time (torchrun ranks, pytest-xdist workers), into a
+    temporary file that is renamed into place -- nobody ever dlopens a half-written library."""
+    import fcntl
+
+    def fresh():
+        return os.path.exists(target) and os.path.getsize(target) > 0 and os.path.getmtime(target) >= newest
+
+    if not force and fresh():
+        return target
+    with open(target + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if force or not fresh():
+                tmp = target + f".tmp{os.getpid()}"
+                _run(make_cmd(tmp))
+                os.replace(tmp, target)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+    return target
+
+
 def build_synth(force=False):
     src = os.path.join(ROOT, "tests", "synth", "pss_synth.c")
-    if force or not os.path.exists(SYNTH_SO) or os.path.getmtime(SYNTH_SO) < os.path.getmtime(src):
-        _run(["gcc", "-O2", "-g", "-fopenmp", "-fPIC", "-shared", "-o", SYNTH_SO, src, "-lm"])
-    return SYNTH_SO
+    return _locked_build(SYNTH_SO, os.path.getmtime(src), force,
+                         lambda out: ["gcc", "-O2", "-g", "-fopenmp", "-fPIC", "-shared", "-o", out, src, "-lm"])
 
 
 def build_oracle(force=False):
@@ -446,9 +467,8 @@ def build_emul(force=False):
     src = os.path.join(ROOT, "tests", "host_emul", "pss_emul.cpp")
     hdr = os.path.join(ROOT, "pss-bam_b200", "csrc", "pss_record.h")
     newest = max(os.path.getmtime(src), os.path.getmtime(hdr))
-    if force or not os.path.exists(EMUL_SO) or os.path.getmtime(EMUL_SO) < newest:
-        _run(["g++", "-O2", "-g", "-std=c++17", "-Wno-unknown-pragmas", "-fPIC", "-shared", "-o", EMUL_SO, src])
-    return EMUL_SO
+    return _locked_build(EMUL_SO, newest, force,
+                         lambda out: ["g++", "-O2", "-g", "-std=c++17", "-Wno-unknown-pragmas", "-fPIC", "-shared", "-o", out, src])
 
 
 class Emul:
