@@ -447,7 +447,8 @@ def main_b200(a):
                                            "vs_two_passes": (tm["kernel_ms"] / max(1, int(tm["launches"])) + fk_ms) / both_ms},
                  "genome_kmer_count": {f"k{k}": {"kernel_ms": ms, "gbase_per_s_per_gpu": ginfo["n_bases"] / (ms * 1e-3) / 1e9,
                                                  "bound": "shared-memory atomics / instruction issue (not HBM)" if k <= 9
-                                                 else "L2 atomics (not HBM)"} for k, ms in spec.items()}}
+                                                 else "radix partition: instruction issue of the in-tile sort (not HBM)"}
+                                       for k, ms in spec.items()}}
         del counts
         if rank == 0 and world == 1:
             other["config0_10Mb_1M_50bp"] = config0_case(pkg, local, torch, not a.no_cpu_baseline)

@@ -199,6 +199,157 @@ __global__ void __launch_bounds__(kSpecSmemThreads, 1) spectrum_smem_kernel(cons
         if (v) atomicAdd(counts + ((size_t)pass << kSpecSmemLog) + i, (CT)v);
     }
 }
+// k = 10 .. 12: one global atomic per k-mer is bound by the rate at which the SMs can send requests to L2 (16 ms for the
+// 3.1 Gb genome, 4^12 bins resident in L2).  Instead: (1) count the k-mers per bucket = high 2k-15 bits of the index
+// (<= 512 buckets), (2) scatter the low 15 bits of every k-mer, as u16, into its bucket's stretch of a scratch buffer
+// -- tile by tile, a tile's k-mers sorted by bucket in shared memory first, so that a bucket needs one global atomic
+// per tile and the stores leave in runs -- (3) per bucket, a 32 768-bin histogram in shared memory.  32 bytes of
+// scratch per packed group; the k-mers cross HBM twice (2 bytes each) instead of crossing the L2 atomics once.
+constexpr int kRadixThreads = 512;                            // = groups per tile = most buckets
+template <int K>
+__device__ __forceinline__ bool radix_kmers(const uint64_t *__restrict__ groups, uint64_t gi, uint64_t &msb, uint64_t &bad)
+{
+    const uint64_t g0 = __ldg(groups + gi), g1 = __ldg(groups + gi + 1);
+    const uint64_t codes = (uint64_t)(uint32_t)g0 | ((uint64_t)(uint32_t)g1 << 32);
+    const uint64_t cls = (g0 >> 32) | (g1 & 0xffffffff00000000ull);
+    bad = (cls | (cls >> 1)) & kEvenBits;
+    msb = rev_fields64(codes, 32);
+    return (uint32_t)bad != 0x55555555u;
+}
+template <int K>
+__global__ void __launch_bounds__(kRadixThreads) radix_count_kernel(const uint64_t *__restrict__ groups, uint64_t g_begin, uint64_t g_end,
+                                                                     unsigned long long *__restrict__ bucket_cnt)
+{
+    constexpr uint32_t nb = 1u << (2 * K - kSpecSmemLog);
+    constexpr uint64_t kmask = (1ull << (2 * K)) - 1ull;
+    __shared__ uint32_t s_cnt[nb];
+    for (uint32_t i = threadIdx.x; i < nb; i += kRadixThreads) s_cnt[i] = 0;
+    __syncthreads();
+    for (uint64_t gi = g_begin + (uint64_t)blockIdx.x * kRadixThreads + threadIdx.x; gi < g_end; gi += (uint64_t)gridDim.x * kRadixThreads) {
+        uint64_t msb, bad;
+        if (!radix_kmers<K>(groups, gi, msb, bad)) continue;
+#pragma unroll
+        for (int o = 0; o < 16; o++) {
+            if (((bad >> (2 * o)) & kmask) != 0) continue;
+            const uint32_t idx = (uint32_t)(msb >> (2 * (32 - o - K))) & (uint32_t)kmask;
+            atomicAdd(&s_cnt[idx >> kSpecSmemLog], 1u);
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < nb; i += kRadixThreads)
+        if (s_cnt[i]) atomicAdd(bucket_cnt + i, (unsigned long long)s_cnt[i]);
+}
+// exclusive scan of the bucket counts (one block): off[0..nb], cursor[b] = off[b]
+__global__ void __launch_bounds__(kRadixThreads) radix_scan_kernel(const unsigned long long *__restrict__ cnt, unsigned long long *__restrict__ off,
+                                                                    unsigned long long *__restrict__ cursor, uint32_t nb)
+{
+    __shared__ unsigned long long s[kRadixThreads];
+    const uint32_t t = threadIdx.x;
+    s[t] = t < nb ? cnt[t] : 0ull;
+    __syncthreads();
+    for (uint32_t d = 1; d < kRadixThreads; d <<= 1) {
+        const unsigned long long v = t >= d ? s[t - d] : 0ull;
+        __syncthreads();
+        s[t] += v;
+        __syncthreads();
+    }
+    if (t < nb) { const unsigned long long ex = s[t] - cnt[t]; off[t] = ex; cursor[t] = ex; }
+    if (t == nb - 1) off[nb] = s[t];
+}
+template <int K>
+__global__ void __launch_bounds__(kRadixThreads) radix_scatter_kernel(const uint64_t *__restrict__ groups, uint64_t g_begin, uint64_t g_end,
+                                                                       unsigned long long *__restrict__ cursor, uint16_t *__restrict__ payload)
+{
+    constexpr uint32_t nb = 1u << (2 * K - kSpecSmemLog);
+    constexpr uint64_t kmask = (1ull << (2 * K)) - 1ull;
+    __shared__ uint32_t s_cnt[kRadixThreads], s_toff[kRadixThreads + 1], s_warp[kRadixThreads / 32];
+    __shared__ unsigned long long s_goff[kRadixThreads];
+    __shared__ uint16_t s_pay[16 * kRadixThreads], s_bkt[16 * kRadixThreads];
+    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    const uint64_t n_tiles = (g_end - g_begin + kRadixThreads - 1) / kRadixThreads;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t gi = g_begin + tile * kRadixThreads + t;
+        s_cnt[t] = 0;
+        __syncthreads();
+        uint64_t msb = 0, bad = ~0ull;
+        const bool any = gi < g_end && radix_kmers<K>(groups, gi, msb, bad);
+        if (any) {
+#pragma unroll
+            for (int o = 0; o < 16; o++) {
+                if (((bad >> (2 * o)) & kmask) != 0) continue;
+                const uint32_t idx = (uint32_t)(msb >> (2 * (32 - o - K))) & (uint32_t)kmask;
+                atomicAdd(&s_cnt[idx >> kSpecSmemLog], 1u);
+            }
+        }
+        __syncthreads();
+        // exclusive scan of the per-bucket counts of this tile (t = bucket); global stretch for each bucket
+        const uint32_t c = t < nb ? s_cnt[t] : 0u;
+        uint32_t inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d);
+            if ((int)lane >= d) inc += v;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        uint32_t base = 0;
+        for (uint32_t w = 0; w < warp; w++) base += s_warp[w];
+        s_toff[t] = base + inc - c;
+        if (t == kRadixThreads - 1) s_toff[kRadixThreads] = base + inc;
+        if (c) s_goff[t] = atomicAdd(cursor + t, (unsigned long long)c);
+        s_cnt[t] = 0;                                          // now: next free slot of the bucket within the tile
+        __syncthreads();
+        if (any) {
+#pragma unroll
+            for (int o = 0; o < 16; o++) {
+                if (((bad >> (2 * o)) & kmask) != 0) continue;
+                const uint32_t idx = (uint32_t)(msb >> (2 * (32 - o - K))) & (uint32_t)kmask;
+                const uint32_t b = idx >> kSpecSmemLog;
+                const uint32_t pos = s_toff[b] + atomicAdd(&s_cnt[b], 1u);
+                s_pay[pos] = (uint16_t)(idx & (uint32_t)(kSpecSmemBins - 1));
+                s_bkt[pos] = (uint16_t)b;
+            }
+        }
+        __syncthreads();
+        const uint32_t n_tile = s_toff[kRadixThreads];
+        for (uint32_t i = t; i < n_tile; i += kRadixThreads) {
+            const uint32_t b = s_bkt[i];
+            payload[s_goff[b] + (i - s_toff[b])] = s_pay[i];
+        }
+        __syncthreads();
+    }
+}
+// bucket (blockIdx.x / parts), part (blockIdx.x % parts): 32 768-bin shared-memory histogram of a stretch of payloads
+template <typename CT>
+__global__ void __launch_bounds__(kSpecSmemThreads, 1) radix_hist_kernel(const uint16_t *__restrict__ payload, const unsigned long long *__restrict__ off,
+                                                                          uint32_t parts, CT *__restrict__ counts)
+{
+    extern __shared__ uint32_t s_bins[];
+    const uint32_t b = blockIdx.x / parts, part = blockIdx.x % parts;
+    for (uint32_t i = threadIdx.x; i < (uint32_t)kSpecSmemBins; i += kSpecSmemThreads) s_bins[i] = 0;
+    __syncthreads();
+    const unsigned long long lo0 = off[b], n = off[b + 1] - lo0;
+    const unsigned long long lo = lo0 + n * part / parts, hi = lo0 + n * (part + 1) / parts;
+    // head up to a 16-byte boundary, body as uint4 (8 payloads), tail
+    unsigned long long a = (lo + 7ull) & ~7ull;
+    if (a > hi) a = hi;
+    for (unsigned long long i = lo + threadIdx.x; i < a; i += kSpecSmemThreads) atomicAdd(&s_bins[payload[i]], 1u);
+    const unsigned long long body = (hi - a) / 8;
+    const uint4 *p4 = reinterpret_cast<const uint4 *>(payload + a);
+    for (unsigned long long i = threadIdx.x; i < body; i += kSpecSmemThreads) {
+        const uint4 v = __ldg(p4 + i);
+        atomicAdd(&s_bins[v.x & 0xffffu], 1u); atomicAdd(&s_bins[v.x >> 16], 1u);
+        atomicAdd(&s_bins[v.y & 0xffffu], 1u); atomicAdd(&s_bins[v.y >> 16], 1u);
+        atomicAdd(&s_bins[v.z & 0xffffu], 1u); atomicAdd(&s_bins[v.z >> 16], 1u);
+        atomicAdd(&s_bins[v.w & 0xffffu], 1u); atomicAdd(&s_bins[v.w >> 16], 1u);
+    }
+    for (unsigned long long i = a + body * 8 + threadIdx.x; i < hi; i += kSpecSmemThreads) atomicAdd(&s_bins[payload[i]], 1u);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < (uint32_t)kSpecSmemBins; i += kSpecSmemThreads) {
+        const uint32_t v = s_bins[i];
+        if (v) atomicAdd(counts + ((size_t)b << kSpecSmemLog) + i, (CT)v);
+    }
+}
 // u32 spectrum -> u64 output
 __global__ void __launch_bounds__(256) widen_kernel(const unsigned int *__restrict__ in, unsigned long long *__restrict__ out, uint64_t n)
 {

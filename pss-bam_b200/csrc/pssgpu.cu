@@ -967,8 +967,39 @@ int pssgpu_kmer_spectrum_shard_device(pssgpu_ctx *ctx, int k, int shard, int n_s
     } else {
         CU(cudaMemsetAsync(d_counts, 0, bins * sizeof(uint64_t), ctx->stream));
     }
+    // k = 10 .. 12: radix partition through a scratch buffer (32 bytes per group); without the memory for it, L2 atomics
+    uint16_t *d_payload = nullptr;
+    unsigned long long *d_rad = nullptr;                   // bucket counts | offsets (nb + 1) | cursors
+    const uint32_t rad_nb = (k >= 10 && k <= 12) ? (1u << (2 * k - kSpecSmemLog)) : 0u;
+    if (rad_nb && g1 > g0 && !getenv("PSSGPU_SPECTRUM_ATOMICS")) {
+        if (cudaMalloc(&d_payload, (g1 - g0) * 16 * sizeof(uint16_t) + 64) != cudaSuccess) { cudaGetLastError(); d_payload = nullptr; }
+        else if (cudaMalloc(&d_rad, (3 * (size_t)rad_nb + 2) * sizeof(unsigned long long)) != cudaSuccess) {
+            cudaGetLastError(); cudaFree(d_payload); d_payload = nullptr; d_rad = nullptr;
+        }
+    }
     time_begin(ctx, (g1 - g0) * sizeof(uint64_t));
-    if (g1 > g0 && k >= 7 && k <= 9) {           // shared-memory bins, one CTA per SM and (slice, pass)
+    if (d_payload) {
+        unsigned long long *cnt = d_rad, *off = d_rad + rad_nb, *cur = d_rad + 2 * (size_t)rad_nb + 1;
+        cudaMemsetAsync(d_rad, 0, (3 * (size_t)rad_nb + 2) * sizeof(unsigned long long), ctx->stream);
+        const unsigned rgrid = (unsigned)std::min<uint64_t>((g1 - g0 + kRadixThreads - 1) / kRadixThreads, (uint64_t)ctx->sm_count * 4);
+        const uint32_t parts = std::max<uint32_t>(1u, (2u * (uint32_t)ctx->sm_count + rad_nb - 1) / rad_nb);
+        const size_t   hsmem = (size_t)kSpecSmemBins * sizeof(uint32_t);
+#define PSS_RADIX(K_)                                                                                                  \
+        do {                                                                                                           \
+            radix_count_kernel<K_><<<rgrid, kRadixThreads, 0, ctx->stream>>>(ctx->d_groups, g0, g1, cnt);             \
+            radix_scan_kernel<<<1, kRadixThreads, 0, ctx->stream>>>(cnt, off, cur, rad_nb);                           \
+            radix_scatter_kernel<K_><<<rgrid, kRadixThreads, 0, ctx->stream>>>(ctx->d_groups, g0, g1, cur, d_payload); \
+        } while (0)
+        if (k == 10) PSS_RADIX(10); else if (k == 11) PSS_RADIX(11); else PSS_RADIX(12);
+#undef PSS_RADIX
+        if (narrow) {
+            cudaFuncSetAttribute(radix_hist_kernel<unsigned int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem);
+            radix_hist_kernel<unsigned int><<<rad_nb * parts, kSpecSmemThreads, hsmem, ctx->stream>>>(d_payload, off, parts, d_narrow);
+        } else {
+            cudaFuncSetAttribute(radix_hist_kernel<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem);
+            radix_hist_kernel<unsigned long long><<<rad_nb * parts, kSpecSmemThreads, hsmem, ctx->stream>>>(d_payload, off, parts, (unsigned long long *)d_counts);
+        }
+    } else if (g1 > g0 && k >= 7 && k <= 9) {    // shared-memory bins, one CTA per SM and (slice, pass)
         const uint32_t n_slices = (uint32_t)std::min<uint64_t>((uint64_t)ctx->sm_count, (g1 - g0 + kSpecSmemThreads - 1) / kSpecSmemThreads);
         const uint32_t passes = (uint32_t)std::max<size_t>(1, bins >> kSpecSmemLog);
         const size_t   smem = std::min<size_t>(bins, kSpecSmemBins) * sizeof(uint32_t);
@@ -1002,6 +1033,8 @@ int pssgpu_kmer_spectrum_shard_device(pssgpu_ctx *ctx, int k, int shard, int n_s
     cudaError_t le = cudaGetLastError();
     cudaError_t se = cudaStreamSynchronize(ctx->stream);
     cudaFree(d_narrow);
+    cudaFree(d_payload);
+    cudaFree(d_rad);
     if (le != cudaSuccess || se != cudaSuccess)
         return fail(ctx, PSSGPU_ECUDA, "kmer_spectrum: %s", cudaGetErrorString(le != cudaSuccess ? le : se));
     time_collect(ctx);

@@ -94,7 +94,7 @@ def test_fragkon_matches_oracle(world, K):
     assert np.array_equal(gtp, tp)
 
 
-@pytest.mark.parametrize("k", [1, 3, 6, 7, 8, 9, 10, 12])
+@pytest.mark.parametrize("k", [1, 3, 6, 7, 8, 9, 10, 11, 12, 13])
 def test_kmer_spectrum_matches_oracle(world, k):
     g, ora, ctx = world
     want = ora.kmer_spectrum(k)
