@@ -273,12 +273,18 @@ __global__ void __launch_bounds__(kRadixThreads) radix_scatter_kernel(const uint
         __syncthreads();
         uint64_t msb = 0, bad = ~0ull;
         const bool any = gi < g_end && radix_kmers<K>(groups, gi, msb, bad);
+        // bucket and rank within (tile, bucket) of each of the 16 k-mers, kept in registers for the second step
+        uint32_t br[16];
+        uint32_t vm = 0;
         if (any) {
 #pragma unroll
             for (int o = 0; o < 16; o++) {
+                br[o] = 0;
                 if (((bad >> (2 * o)) & kmask) != 0) continue;
                 const uint32_t idx = (uint32_t)(msb >> (2 * (32 - o - K))) & (uint32_t)kmask;
-                atomicAdd(&s_cnt[idx >> kSpecSmemLog], 1u);
+                const uint32_t b = idx >> kSpecSmemLog;
+                br[o] = b | (atomicAdd(&s_cnt[b], 1u) << 9);
+                vm |= 1u << o;
             }
         }
         __syncthreads();
@@ -296,26 +302,22 @@ __global__ void __launch_bounds__(kRadixThreads) radix_scatter_kernel(const uint
         for (uint32_t w = 0; w < warp; w++) base += s_warp[w];
         s_toff[t] = base + inc - c;
         if (t == kRadixThreads - 1) s_toff[kRadixThreads] = base + inc;
-        if (c) s_goff[t] = atomicAdd(cursor + t, (unsigned long long)c);
-        s_cnt[t] = 0;                                          // now: next free slot of the bucket within the tile
+        if (c) s_goff[t] = atomicAdd(cursor + t, (unsigned long long)c) - (unsigned long long)(base + inc - c);   // global - tile offset
         __syncthreads();
-        if (any) {
+        if (vm) {
 #pragma unroll
             for (int o = 0; o < 16; o++) {
-                if (((bad >> (2 * o)) & kmask) != 0) continue;
+                if (!((vm >> o) & 1u)) continue;
                 const uint32_t idx = (uint32_t)(msb >> (2 * (32 - o - K))) & (uint32_t)kmask;
-                const uint32_t b = idx >> kSpecSmemLog;
-                const uint32_t pos = s_toff[b] + atomicAdd(&s_cnt[b], 1u);
+                const uint32_t b = br[o] & 511u;
+                const uint32_t pos = s_toff[b] + (br[o] >> 9);
                 s_pay[pos] = (uint16_t)(idx & (uint32_t)(kSpecSmemBins - 1));
                 s_bkt[pos] = (uint16_t)b;
             }
         }
         __syncthreads();
         const uint32_t n_tile = s_toff[kRadixThreads];
-        for (uint32_t i = t; i < n_tile; i += kRadixThreads) {
-            const uint32_t b = s_bkt[i];
-            payload[s_goff[b] + (i - s_toff[b])] = s_pay[i];
-        }
+        for (uint32_t i = t; i < n_tile; i += kRadixThreads) payload[s_goff[s_bkt[i]] + i] = s_pay[i];
         __syncthreads();
     }
 }
