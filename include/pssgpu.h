@@ -97,6 +97,21 @@ int pssgpu_genome_upload_device(pssgpu_ctx *ctx, const pssgpu_contig *contigs, u
  * resident. */
 int pssgpu_genome_save(pssgpu_ctx *ctx, const char *path);
 int pssgpu_genome_load(pssgpu_ctx *ctx, const char *path);
+/* The same with a fingerprint of what the genome was built from, so that a
+ * cache of another FASTA (or of an older version of this one) is never taken
+ * for the right one: save stores the tag in the file, load compares all four
+ * fields with `expect` and fails with PSSGPU_EINVAL when any differs.  The
+ * host programs fill it from stat() and realpath() of the FASTA
+ * (host/pss_host.c).  On load, every contig / hash / exception-list entry is
+ * range checked before the genome becomes resident. */
+typedef struct pssgpu_genome_tag {
+    uint64_t source_size;        /* st_size of the FASTA                       */
+    int64_t  source_mtime_ns;    /* st_mtim of the FASTA, nanoseconds          */
+    uint64_t source_path_hash;   /* FNV-1a of realpath(FASTA)                  */
+    uint64_t user;               /* caller defined (0 in the host programs)    */
+} pssgpu_genome_tag;
+int pssgpu_genome_save_tagged(pssgpu_ctx *ctx, const char *path, const pssgpu_genome_tag *tag);
+int pssgpu_genome_load_tagged(pssgpu_ctx *ctx, const char *path, const pssgpu_genome_tag *expect);
 /* Total bases resident / bytes of HBM used by the packed genome. */
 int pssgpu_genome_info(const pssgpu_ctx *ctx, uint64_t *n_contigs, uint64_t *n_bases, uint64_t *hbm_bytes);
 
@@ -133,8 +148,13 @@ int pssgpu_pss_begin(pssgpu_ctx *ctx, const pssgpu_pss_params *p);
 /* Feed SAM text (what `samtools view` writes: pss-bam.c:148-162), any
  * chunking; partial trailing lines are carried to the next call; `last` != 0
  * flushes a final line without '\n'.  Host memory; pinned memory from
- * pssgpu_host_alloc is copied without an extra staging pass.  Asynchronous:
- * returns once the bytes are staged, kernels may still be running. */
+ * pssgpu_host_alloc is copied without an extra staging pass.  Returns once the
+ * bytes have been COPIED to the device (the caller may overwrite `sam_bytes`
+ * right away, also after an error return); the tally kernels may still be
+ * running -- they are waited for by pssgpu_sync, *_finish and get_stats, and a
+ * kernel fault is reported there.  Lines of any length are accepted: one that
+ * does not fit the staging buffer is tallied in the 200000-byte stretches
+ * fgets() would hand to line2saml (pss-bam.c:761-764). */
 int pssgpu_feed(pssgpu_ctx *ctx, const char *sam_bytes, size_t len, int last);
 
 /* Same for SAM text already resident in device memory.  `d_sam` must be

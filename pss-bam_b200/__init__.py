@@ -76,6 +76,11 @@ class _Contig(C.Structure):
     _fields_ = [("id", C.c_char_p), ("seq", C.c_void_p), ("len", C.c_uint64)]
 
 
+class _GenomeTag(C.Structure):
+    _fields_ = [("source_size", C.c_uint64), ("source_mtime_ns", C.c_int64), ("source_path_hash", C.c_uint64),
+                ("user", C.c_uint64)]
+
+
 class _PssParams(C.Structure):
     _fields_ = [("region_len", C.c_int), ("min_len", C.c_ulong), ("max_len", C.c_ulong), ("min_mq", C.c_int),
                 ("up_ctx", C.c_char_p), ("down_ctx", C.c_char_p), ("merged_only", C.c_uint)]
@@ -99,7 +104,8 @@ class _Timing(C.Structure):
 ABI_SYMBOLS = (
     "pssgpu_abi_version", "pssgpu_device_count", "pssgpu_init", "pssgpu_destroy", "pssgpu_last_error",
     "pssgpu_cuda_stream", "pssgpu_host_alloc", "pssgpu_host_free",
-    "pssgpu_genome_upload", "pssgpu_genome_upload_device", "pssgpu_genome_save", "pssgpu_genome_load", "pssgpu_genome_info",
+    "pssgpu_genome_upload", "pssgpu_genome_upload_device", "pssgpu_genome_save", "pssgpu_genome_load", "pssgpu_genome_save_tagged", "pssgpu_genome_load_tagged",
+    "pssgpu_genome_info",
     "pssgpu_pss_default_params", "pssgpu_pss_begin", "pssgpu_feed", "pssgpu_feed_device", "pssgpu_sync",
     "pssgpu_pss_finish", "pssgpu_pss_finish_device", "pssgpu_get_stats", "pssgpu_both_begin", "pssgpu_get_fragkon_stats",
     "pssgpu_fragkon_default_params", "pssgpu_fragkon_begin", "pssgpu_fragkon_finish", "pssgpu_fragkon_finish_device",
@@ -138,6 +144,8 @@ def load_library():
     lib.pssgpu_genome_info.argtypes = [P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.pssgpu_genome_save.argtypes = [P, C.c_char_p]
     lib.pssgpu_genome_load.argtypes = [P, C.c_char_p]
+    lib.pssgpu_genome_save_tagged.argtypes = [P, C.c_char_p, C.POINTER(_GenomeTag)]
+    lib.pssgpu_genome_load_tagged.argtypes = [P, C.c_char_p, C.POINTER(_GenomeTag)]
     lib.pssgpu_pss_default_params.argtypes = [C.POINTER(_PssParams)]
     lib.pssgpu_pss_default_params.restype = None
     lib.pssgpu_pss_begin.argtypes = [P, C.POINTER(_PssParams)]
@@ -254,13 +262,21 @@ class Context:
             arr[i] = _Contig(cid, ptr, n)
         self._ck(self.lib.pssgpu_genome_upload_device(self.h, arr, len(contigs)))
 
-    def save_genome(self, path):
-        """Write the resident packed genome to `path` (pssgpu_genome_save)."""
-        self._ck(self.lib.pssgpu_genome_save(self.h, os.fsencode(path)))
+    def save_genome(self, path, tag=None):
+        """Write the resident packed genome to `path` (pssgpu_genome_save[_tagged]); tag = (size, mtime_ns, path_hash, user)."""
+        if tag is None:
+            self._ck(self.lib.pssgpu_genome_save(self.h, os.fsencode(path)))
+        else:
+            t = _GenomeTag(*tag)
+            self._ck(self.lib.pssgpu_genome_save_tagged(self.h, os.fsencode(path), C.byref(t)))
 
-    def load_genome(self, path):
-        """Make the packed genome of `path` resident (pssgpu_genome_load) instead of upload_genome()."""
-        self._ck(self.lib.pssgpu_genome_load(self.h, os.fsencode(path)))
+    def load_genome(self, path, tag=None):
+        """Make the packed genome of `path` resident (pssgpu_genome_load[_tagged]) instead of upload_genome()."""
+        if tag is None:
+            self._ck(self.lib.pssgpu_genome_load(self.h, os.fsencode(path)))
+        else:
+            t = _GenomeTag(*tag)
+            self._ck(self.lib.pssgpu_genome_load_tagged(self.h, os.fsencode(path), C.byref(t)))
 
     def genome_info(self):
         a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()

@@ -7,6 +7,7 @@
 #include "../../include/pssgpu.h"
 
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cstdarg>
@@ -531,8 +532,9 @@ struct CacheHeader {
     char     magic[8];            // "PSSGPUG" + layout version
     uint64_t n_contigs, n_groups, n_bases, names_bytes, n_exc, hash_size;
     uint32_t cc_seed, cc_ok, exc_overflow, pad_bases;
+    pssgpu_genome_tag tag;        // what the genome was built from (all zero: untagged)
 };
-const char kCacheMagic[8] = { 'P', 'S', 'S', 'G', 'P', 'U', 'G', 1 };
+const char kCacheMagic[8] = { 'P', 'S', 'S', 'G', 'P', 'U', 'G', 2 };
 constexpr size_t kCachePiece = 64ull << 20;
 
 bool write_dev(FILE *f, const void *d, size_t bytes, std::vector<char> &buf)
@@ -553,22 +555,30 @@ bool read_dev(FILE *f, void *d, size_t bytes, std::vector<char> &buf)
     }
     return true;
 }
-}  // namespace
+#define PSS_READ_HOST(f, v, n) ((v).resize(n), (n) == 0 || fread((v).data(), sizeof((v)[0]), (n), (f)) == (size_t)(n))
+bool same_tag(const pssgpu_genome_tag &a, const pssgpu_genome_tag &b)
+{
+    return a.source_size == b.source_size && a.source_mtime_ns == b.source_mtime_ns && a.source_path_hash == b.source_path_hash
+        && a.user == b.user;
+}
 
-int pssgpu_genome_save(pssgpu_ctx *ctx, const char *path)
+int genome_save_impl(pssgpu_ctx *ctx, const char *path, const pssgpu_genome_tag *tag)
 {
     if (!ctx || !path) return fail(ctx, PSSGPU_EINVAL, "genome_save: null argument");
     if (!ctx->have_genome) return fail(ctx, PSSGPU_ENOGENOME, "genome_save: no genome resident");
     Bind bind(ctx);
     CU(cudaStreamSynchronize(ctx->stream));
-    FILE *f = fopen(path, "wb");
-    if (!f) return fail(ctx, PSSGPU_EINVAL, "genome_save: cannot create %s", path);
+    // written under a temporary name and renamed: a reader never sees a half-written cache
+    const std::string tmp = std::string(path) + ".tmp" + std::to_string((long)getpid());
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f) return fail(ctx, PSSGPU_EINVAL, "genome_save: cannot create %s", tmp.c_str());
     CacheHeader h;
     memset(&h, 0, sizeof h);
     memcpy(h.magic, kCacheMagic, 8);
     h.n_contigs = ctx->n_contigs; h.n_groups = ctx->n_groups; h.n_bases = ctx->n_bases; h.names_bytes = ctx->names_bytes;
     h.n_exc = ctx->n_exc; h.hash_size = (uint64_t)ctx->hash_mask + 1; h.cc_seed = ctx->cc_seed; h.cc_ok = ctx->cc_ok;
     h.exc_overflow = ctx->exc_overflow ? 1u : 0u; h.pad_bases = (uint32_t)kPadBases;
+    if (tag) h.tag = *tag;
     std::vector<char> buf(kCachePiece);
     bool ok = fwrite(&h, sizeof h, 1, f) == 1
            && write_dev(f, ctx->d_contigs, h.n_contigs * sizeof(DevContig), buf)
@@ -578,12 +588,13 @@ int pssgpu_genome_save(pssgpu_ctx *ctx, const char *path)
            && write_dev(f, ctx->d_exc_chr, h.n_exc, buf)
            && write_dev(f, ctx->d_groups, h.n_groups * sizeof(uint64_t), buf);
     ok = (fclose(f) == 0) && ok;
-    if (!ok) { remove(path); return fail(ctx, PSSGPU_EINVAL, "genome_save: writing %s failed", path); }
+    if (ok && rename(tmp.c_str(), path) != 0) ok = false;
+    if (!ok) { remove(tmp.c_str()); return fail(ctx, PSSGPU_EINVAL, "genome_save: writing %s failed", path); }
     ctx->d2h_bytes += h.n_groups * sizeof(uint64_t);
     return PSSGPU_OK;
 }
 
-int pssgpu_genome_load(pssgpu_ctx *ctx, const char *path)
+int genome_load_impl(pssgpu_ctx *ctx, const char *path, const pssgpu_genome_tag *expect)
 {
     if (!ctx || !path) return fail(ctx, PSSGPU_EINVAL, "genome_load: null argument");
     Bind bind(ctx);
@@ -596,12 +607,43 @@ int pssgpu_genome_load(pssgpu_ctx *ctx, const char *path)
     uint64_t want = 0;
     if (ok) {
         ok = h.n_contigs <= 0x7fffffffull && h.names_bytes <= 0xfffffff0ull && h.n_exc <= kExcCap && h.n_groups >= 2
-          && h.n_groups < (1ull << 40) && h.hash_size >= 16 && (h.hash_size & (h.hash_size - 1)) == 0 && h.hash_size <= (1ull << 32);
+          && h.n_groups < (1ull << 40) && h.hash_size >= 16 && (h.hash_size & (h.hash_size - 1)) == 0 && h.hash_size <= (1ull << 32)
+          && h.hash_size > 2 * h.n_contigs;
         want = sizeof h + h.n_contigs * sizeof(DevContig) + h.names_bytes + h.hash_size * sizeof(uint32_t) + h.n_exc * 9
              + h.n_groups * sizeof(uint64_t);
         if (ok && (fseek(f, 0, SEEK_END) != 0 || (uint64_t)ftell(f) != want || fseek(f, (long)sizeof h, SEEK_SET) != 0)) ok = false;
     }
     if (!ok) { fclose(f); return fail(ctx, PSSGPU_EINVAL, "genome_load: %s is not a packed genome of this library version", path); }
+    if (expect && !same_tag(h.tag, *expect)) {
+        fclose(f);
+        return fail(ctx, PSSGPU_EINVAL, "genome_load: %s was built from a different source (size / mtime / path tag differs)", path);
+    }
+    // the small tables are checked on the host before anything is made resident: the kernels index the packed genome
+    // with them unchecked
+    std::vector<DevContig> tab;
+    std::vector<char>      names;
+    std::vector<uint32_t>  hash;
+    std::vector<uint64_t>  exc_pos;
+    std::vector<uint8_t>   exc_chr;
+    ok = PSS_READ_HOST(f, tab, h.n_contigs) && PSS_READ_HOST(f, names, h.names_bytes) && PSS_READ_HOST(f, hash, h.hash_size)
+      && PSS_READ_HOST(f, exc_pos, h.n_exc) && PSS_READ_HOST(f, exc_chr, h.n_exc);
+    const uint64_t total_bases = (h.n_groups - 2) * 16;
+    uint64_t sum_len = 0;
+    for (uint64_t i = 0; ok && i < h.n_contigs; i++) {
+        const DevContig &c = tab[i];
+        ok = (c.base_off & 15u) == 0 && c.base_off >= (uint64_t)kPadBases && c.len <= total_bases
+          && c.base_off + c.len + (uint64_t)kPadBases <= total_bases + 16
+          && (uint64_t)c.name_off + c.name_len <= h.names_bytes;
+        if (ok && i > 0) ok = c.base_off >= tab[i - 1].base_off + ((tab[i - 1].len + 15) / 16) * 16 + (uint64_t)kPadBases;
+        sum_len += c.len;
+    }
+    ok = ok && sum_len == h.n_bases;
+    uint64_t used = 0;
+    for (uint64_t i = 0; ok && i < h.hash_size; i++) { ok = hash[i] <= h.n_contigs; used += hash[i] != 0; }
+    ok = ok && used == h.n_contigs;
+    for (uint64_t i = 0; ok && i < h.n_exc; i++) ok = exc_pos[i] < total_bases + 32 && (i == 0 || exc_pos[i - 1] < exc_pos[i]);
+    if (!ok) { fclose(f); return fail(ctx, PSSGPU_EINVAL, "genome_load: %s is damaged (a table entry is out of range)", path); }
+
     std::vector<char> buf(kCachePiece);
     cudaError_t e = cudaMalloc(&ctx->d_contigs, std::max<size_t>(1, h.n_contigs) * sizeof(DevContig));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_names, h.names_bytes + 16);
@@ -609,13 +651,12 @@ int pssgpu_genome_load(pssgpu_ctx *ctx, const char *path)
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_exc_pos, kExcCap * sizeof(uint64_t));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_exc_chr, kExcCap);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_groups, h.n_groups * sizeof(uint64_t));
-    ok = e == cudaSuccess
-      && read_dev(f, ctx->d_contigs, h.n_contigs * sizeof(DevContig), buf)
-      && read_dev(f, ctx->d_names, h.names_bytes, buf)
-      && read_dev(f, ctx->d_hash, h.hash_size * sizeof(uint32_t), buf)
-      && read_dev(f, ctx->d_exc_pos, h.n_exc * sizeof(uint64_t), buf)
-      && read_dev(f, ctx->d_exc_chr, h.n_exc, buf)
-      && read_dev(f, ctx->d_groups, h.n_groups * sizeof(uint64_t), buf);
+    if (e == cudaSuccess && h.n_contigs) e = cudaMemcpy(ctx->d_contigs, tab.data(), h.n_contigs * sizeof(DevContig), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && h.names_bytes) e = cudaMemcpy(ctx->d_names, names.data(), h.names_bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(ctx->d_hash, hash.data(), h.hash_size * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && h.n_exc) e = cudaMemcpy(ctx->d_exc_pos, exc_pos.data(), h.n_exc * sizeof(uint64_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && h.n_exc) e = cudaMemcpy(ctx->d_exc_chr, exc_chr.data(), h.n_exc, cudaMemcpyHostToDevice);
+    ok = e == cudaSuccess && read_dev(f, ctx->d_groups, h.n_groups * sizeof(uint64_t), buf);
     fclose(f);
     if (!ok) {
         free_genome(ctx);
@@ -631,6 +672,20 @@ int pssgpu_genome_load(pssgpu_ctx *ctx, const char *path)
     ctx->h2d_bytes += h.n_groups * sizeof(uint64_t);
     ctx->have_genome = true;
     return PSSGPU_OK;
+}
+}  // namespace
+
+int pssgpu_genome_save(pssgpu_ctx *ctx, const char *path) { return genome_save_impl(ctx, path, nullptr); }
+int pssgpu_genome_load(pssgpu_ctx *ctx, const char *path) { return genome_load_impl(ctx, path, nullptr); }
+int pssgpu_genome_save_tagged(pssgpu_ctx *ctx, const char *path, const pssgpu_genome_tag *tag)
+{
+    if (!tag) return fail(ctx, PSSGPU_EINVAL, "genome_save_tagged: null tag");
+    return genome_save_impl(ctx, path, tag);
+}
+int pssgpu_genome_load_tagged(pssgpu_ctx *ctx, const char *path, const pssgpu_genome_tag *expect)
+{
+    if (!expect) return fail(ctx, PSSGPU_EINVAL, "genome_load_tagged: null tag");
+    return genome_load_impl(ctx, path, expect);
 }
 
 int pssgpu_genome_info(const pssgpu_ctx *ctx, uint64_t *n_contigs, uint64_t *n_bases, uint64_t *hbm_bytes)
@@ -747,68 +802,86 @@ int pssgpu_both_begin(pssgpu_ctx *ctx, const pssgpu_pss_params *p, const pssgpu_
     return PSSGPU_OK;
 }
 
-int pssgpu_feed(pssgpu_ctx *ctx, const char *sam, size_t len, int last)
+namespace {
+// One piece of the staging buffer `cur` is complete ([0, klen) holds whole lines, or a stretch of one over-long line):
+// tally it once its copy has landed, and make the other buffer wait for the tally that last read it.
+int stage_launch(pssgpu_ctx *ctx, size_t klen, uint64_t soff)
 {
-    if (!ctx || (!sam && len)) return fail(ctx, PSSGPU_EINVAL, "feed: null argument");
-    if (ctx->mode < 0) return fail(ctx, PSSGPU_EINVAL, "feed: no tally open (call *_begin first)");
-    Bind bind(ctx);
+    const int cur = ctx->cur;
+    CU(cudaEventRecord(ctx->ev_copied[cur], ctx->copy_stream));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[cur], 0));
+    int rc = launch_tally_mode(ctx, ctx->d_stage[cur], klen, soff);
+    if (rc != PSSGPU_OK) return rc;
+    CU(cudaEventRecord(ctx->ev_tallied[cur], ctx->stream));
+    ctx->cur ^= 1;
+    CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_tallied[ctx->cur], 0));
+    return PSSGPU_OK;
+}
+
+int feed_impl(pssgpu_ctx *ctx, const char *sam, size_t len, int last)
+{
     for (int s = 0; s < 2; s++)
         if (!ctx->d_stage[s]) CU(cudaMalloc(&ctx->d_stage[s], kStageCap + 64));
     // Two staging buffers, two streams: the copies queue up on copy_stream, the tallies on the context's stream; a
     // tally waits for its copy (ev_copied), a copy into a buffer waits for the tally that last read it (ev_tallied).
     // The PCIe link then never idles behind a kernel launch.
     size_t off = 0;
-    bool   copied = false;
     while (off < len) {
+        if (ctx->carry_len == kStageCap) {
+            // A "line" longer than the staging buffer.  fgets(buf, MAX_LINE_LEN + 1) hands such a line to line2saml in
+            // stretches of 200000 bytes (pss-bam.c:761-764), so it may be cut at any multiple of that from its start:
+            // the stretches before the cut are tallied now (the kernel's long_record path), the rest stays carried.
+            const size_t   cut = (kStageCap / (size_t)kMaxLine) * (size_t)kMaxLine, tail = kStageCap - cut;
+            const uint64_t soff = ctx->fed_bytes + off - ctx->carry_len;
+            uint8_t       *from = ctx->d_stage[ctx->cur];
+            int rc = stage_launch(ctx, cut, soff);
+            if (rc != PSSGPU_OK) return rc;
+            CU(cudaMemcpyAsync(ctx->d_stage[ctx->cur], from + cut, tail, cudaMemcpyDeviceToDevice, ctx->copy_stream));
+            ctx->carry_len = tail;
+        }
         const size_t room = kStageCap - ctx->carry_len;
-        if (room == 0) return fail(ctx, PSSGPU_EUNSUPP, "feed: a line longer than %zu bytes", kStageCap);
         const size_t plen = std::min(std::min(len - off, kFeedPiece), room);
         const char  *piece = sam + off;
         const char  *nl = (const char *)memrchr(piece, '\n', plen);
-        const int    cur = ctx->cur;
-        uint8_t     *slot = ctx->d_stage[cur];
+        uint8_t     *slot = ctx->d_stage[ctx->cur];
         if (!nl) {                       // no line ends in this piece: it only grows the carry
             CU(cudaMemcpyAsync(slot + ctx->carry_len, piece, plen, cudaMemcpyHostToDevice, ctx->copy_stream));
             ctx->carry_len += plen;
         } else {
             const size_t cut = (size_t)(nl - piece) + 1, tail = plen - cut;
             CU(cudaMemcpyAsync(slot + ctx->carry_len, piece, cut, cudaMemcpyHostToDevice, ctx->copy_stream));
-            CU(cudaEventRecord(ctx->ev_copied[cur], ctx->copy_stream));
-            const size_t   klen = ctx->carry_len + cut;
-            const uint64_t soff = ctx->fed_bytes + off - ctx->carry_len;
-            CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[cur], 0));
-            int rc = launch_tally_mode(ctx, slot, klen, soff);
+            int rc = stage_launch(ctx, ctx->carry_len + cut, ctx->fed_bytes + off - ctx->carry_len);
             if (rc != PSSGPU_OK) return rc;
-            CU(cudaEventRecord(ctx->ev_tallied[cur], ctx->stream));
-            ctx->cur ^= 1;
-            // the other buffer: free once the tally that read it (two pieces ago) is done
-            CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_tallied[ctx->cur], 0));
+            // (the other buffer is free once the tally that read it, two pieces ago, is done: stage_launch queued the wait)
             if (tail) CU(cudaMemcpyAsync(ctx->d_stage[ctx->cur], piece + cut, tail, cudaMemcpyHostToDevice, ctx->copy_stream));
             ctx->carry_len = tail;
         }
         ctx->h2d_bytes += plen;
-        copied = true;
         off += plen;
     }
     ctx->fed_bytes += len;
     if (last && ctx->carry_len) {        // final line without '\n' (fgets hands it out as is)
-        const uint64_t soff = ctx->fed_bytes - ctx->carry_len;
-        const int      cur = ctx->cur;
-        CU(cudaEventRecord(ctx->ev_copied[cur], ctx->copy_stream));
-        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[cur], 0));
-        int rc = launch_tally_mode(ctx, ctx->d_stage[cur], ctx->carry_len, soff);
+        int rc = stage_launch(ctx, ctx->carry_len, ctx->fed_bytes - ctx->carry_len);
         if (rc != PSSGPU_OK) return rc;
-        CU(cudaEventRecord(ctx->ev_tallied[cur], ctx->stream));
-        ctx->cur ^= 1;
-        CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_tallied[ctx->cur], 0));
         ctx->carry_len = 0;
     }
-    if (copied) {                        // the caller may reuse `sam` as soon as we return
-        CU(cudaStreamSynchronize(ctx->copy_stream));
-        // the tallies are waited for as well: keeps the contract simple (errors surface here, not at finish)
-        CU(cudaEventRecord(ctx->copy_done, ctx->stream));
-        CU(cudaEventSynchronize(ctx->copy_done));
-    }
+    return PSSGPU_OK;
+}
+}  // namespace
+
+int pssgpu_feed(pssgpu_ctx *ctx, const char *sam, size_t len, int last)
+{
+    if (!ctx || (!sam && len)) return fail(ctx, PSSGPU_EINVAL, "feed: null argument");
+    if (ctx->mode < 0) return fail(ctx, PSSGPU_EINVAL, "feed: no tally open (call *_begin first)");
+    Bind bind(ctx);
+    const int rc = feed_impl(ctx, sam, len, last);
+    // The caller may reuse `sam` as soon as we return -- on success and on every error path alike -- so the copies
+    // that read it are waited for.  The tallies are not: they drain at pssgpu_sync / *_finish / get_stats, which is
+    // where a kernel fault would surface.  A caller that alternates two pinned buffers (host/pss_host.c) thus
+    // overlaps its own reading of the next chunk with the tally of this one.
+    const cudaError_t e = cudaStreamSynchronize(ctx->copy_stream);
+    if (rc != PSSGPU_OK) return rc;
+    if (e != cudaSuccess) return fail(ctx, PSSGPU_ECUDA, "feed: %s", cudaGetErrorString(e));
     return PSSGPU_OK;
 }
 

@@ -149,11 +149,14 @@ Fa_Src *init_fasta_src(const char fn[])
 Seq *get_next_fa(Fa_Src *fa_source, Genome *genome)
 {
     Seq *s;
-    (void)genome;
     if (!fa_source) return NULL;
+    /* like the reference (fasta-genome-io.c:60-83), the record is appended to genome->seqs, which the caller sized
+     * for MAX_GENOME_SEQS pointers (init_genome does); a full table ends the iteration */
+    if (genome && genome->n_seqs >= MAX_GENOME_SEQS) return NULL;
     s = (Seq *)calloc(1, sizeof *s);
     if (next_record((blockreader *)fa_source->seq_buffer, s) != 0) { free(s); return NULL; }
     fa_source->n++;
+    if (genome) genome->seqs[genome->n_seqs++] = s;
     return s;
 }
 
@@ -231,16 +234,12 @@ Genome *init_genome(const char fn[])
 {
     Fa_Src *src = init_fasta_src(fn);
     Genome *g;
-    size_t  cap = 64;
-    Seq    *s;
     if (!src) return NULL;
     g = (Genome *)calloc(1, sizeof *g);
-    g->seqs = (Seq **)malloc(cap * sizeof *g->seqs);
+    /* the reference's table size (fasta-genome-io.c:226): 8 MB of address space, touched only as far as it is used */
+    g->seqs = (Seq **)malloc((size_t)MAX_GENOME_SEQS * sizeof *g->seqs);
     g->dummy = (Seq *)calloc(1, sizeof *g->dummy);
-    while (g->n_seqs < MAX_GENOME_SEQS && (s = get_next_fa(src, g)) != NULL) {
-        if (g->n_seqs == cap) { cap *= 2; g->seqs = (Seq **)realloc(g->seqs, cap * sizeof *g->seqs); }
-        g->seqs[g->n_seqs++] = s;
-    }
+    while (get_next_fa(src, g) != NULL) { }
     close_fasta_src(src);
     qsort(g->seqs, g->n_seqs, sizeof *g->seqs, chr_cmp);
     return g;

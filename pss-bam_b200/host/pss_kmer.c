@@ -8,6 +8,7 @@ KSP init_KSP(int k)
     ks = (KSP)malloc(sizeof *ks);
     ks->k = (size_t)k;
     ks->k_ar_size = K_AR_SIZE;
+    ks->ka = NULL;
     ks->counts = (unsigned int *)calloc((size_t)1 << (2 * k), sizeof(unsigned int));
     if (!ks->counts) { free(ks); return NULL; }
     return ks;

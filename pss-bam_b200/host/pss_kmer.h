@@ -22,9 +22,21 @@
 #define K_AR_SIZE (8)
 #define PSS_KMER_MAX_K (15)       /* 4^15 counters = 4 GiB of unsigned int */
 
+/* The reference's trie node (kmer.h:9-16).  Declared so that code written against the reference header compiles; this
+ * implementation never allocates one. */
+typedef struct kmer_tree_node {
+    struct kmer_tree_node *Ap, *Cp, *Gp, *Tp;
+    unsigned int count;
+} ktn;
+typedef struct kmer_tree_node *ktnP;
+
+/* First three members: the reference's `Kmers` (kmer.h:18-23), same names, types and offsets.  `ka` is always NULL
+ * here -- the counts live in the flat table that follows, so code that walks ka[]/the tries itself (nothing in the
+ * reference does outside kmer.c) must go through kmer2count() instead; see INTEGRATION.md "API deviations". */
 typedef struct kmers {
     size_t        k;              /* k-mer length */
-    size_t        k_ar_size;      /* kept for source compatibility (always K_AR_SIZE) */
+    size_t        k_ar_size;      /* always K_AR_SIZE, as in the reference */
+    ktnP         *ka;             /* reference: 4^8 trie roots; here: NULL */
     unsigned int *counts;         /* 4^k saturating counters */
 } Kmers;
 typedef struct kmers *KSP;

@@ -3,6 +3,7 @@ same command lines, byte-identical files / stdout."""
 import json
 import os
 import subprocess
+import time
 
 import pytest
 
@@ -71,27 +72,65 @@ def test_genome_kmer_count_cli(env, case):
 
 
 def test_cli_with_packed_genome_cache(env):
-    """$PSSGPU_GENOME_CACHE: the first run writes <dir>/genome.fa.pssgpu, the second one loads it instead of parsing the
-    FASTA (made unreadable garbage in between would be noticed: the cache must be newer than the FASTA) -- same bytes."""
+    """$PSSGPU_GENOME_CACHE: the first run writes <dir>/genome.fa.<hash of realpath>.pssgpu, the second one loads it
+    instead of parsing the FASTA -- same bytes.  A damaged cache, a cache whose FASTA changed since (size / mtime tag)
+    and a cache of another FASTA of the same basename are all refused and the FASTA is parsed again."""
+    import glob
+    import shutil
     d, e = env
     case = MAN["pss"][0]
     cdir = os.path.join(d, "cache")
-    os.makedirs(cdir, exist_ok=True)
+    shutil.rmtree(cdir, ignore_errors=True)
+    os.makedirs(cdir)
     e2 = dict(e, PSSGPU_GENOME_CACHE=cdir)
     cmd = [os.path.join(BIN, "pss-bam"), "-F", "genome.fa", "-B", case["sam"] + ".sam", "-o", "out", *case["args"]]
+
+    def caches():
+        return sorted(glob.glob(os.path.join(cdir, "genome.fa.*.pssgpu")))
+
+    def check_outputs(where=d):
+        assert open(os.path.join(where, "out.pss.counts.txt"), "rb").read() == _gold(case["counts"])
+        assert open(os.path.join(where, "out.pss.rates.txt"), "rb").read() == _gold(case["rates"])
+
     for rnd in range(2):
         r = subprocess.run(cmd, cwd=d, env=e2, capture_output=True)
         assert r.returncode == 0, r.stderr[-2000:]
-        assert os.path.exists(os.path.join(cdir, "genome.fa.pssgpu"))
-        assert open(os.path.join(d, "out.pss.counts.txt"), "rb").read() == _gold(case["counts"])
-        assert open(os.path.join(d, "out.pss.rates.txt"), "rb").read() == _gold(case["rates"])
+        assert len(caches()) == 1 and b"ignoring genome cache" not in r.stderr
+        check_outputs()
+    cache = caches()[0]
     gk = MAN["gkc"][0]
     r = subprocess.run([os.path.join(BIN, "genome-kmer-count"), "-f", "genome.fa", "-k", str(gk["k"])], cwd=d, env=e2, capture_output=True)
     assert r.returncode == 0 and r.stdout == _gold(gk["out"])
+    # the FASTA is touched (newer mtime): the tag no longer matches, the cache is refused and rewritten
+    os.utime(os.path.join(d, "genome.fa"), ns=(time.time_ns(), time.time_ns() + 5_000_000_000))
+    r = subprocess.run(cmd, cwd=d, env=e2, capture_output=True)
+    assert r.returncode == 0 and b"ignoring genome cache" in r.stderr and b"different source" in r.stderr
+    check_outputs()
+    r = subprocess.run(cmd, cwd=d, env=e2, capture_output=True)
+    assert r.returncode == 0 and b"ignoring genome cache" not in r.stderr
     # a damaged cache is refused (with a warning) and the FASTA is parsed again
-    with open(os.path.join(cdir, "genome.fa.pssgpu"), "r+b") as f:
+    with open(cache, "r+b") as f:
         f.truncate(1000)
-    os.utime(os.path.join(cdir, "genome.fa.pssgpu"))
     r = subprocess.run(cmd, cwd=d, env=e2, capture_output=True)
     assert r.returncode == 0 and b"ignoring genome cache" in r.stderr
-    assert open(os.path.join(d, "out.pss.counts.txt"), "rb").read() == _gold(case["counts"])
+    check_outputs()
+    # a table entry out of range (contig 0's base offset) is caught by the range checks, not by a kernel fault
+    r = subprocess.run(cmd, cwd=d, env=e2, capture_output=True)
+    assert r.returncode == 0 and b"ignoring genome cache" not in r.stderr
+    with open(cache, "r+b") as f:
+        f.seek(8 + 6 * 8 + 4 * 4 + 4 * 8)         # CacheHeader: magic, six u64, four u32, the tag -> first DevContig
+        f.write((1 << 50).to_bytes(8, "little"))
+    r = subprocess.run(cmd, cwd=d, env=e2, capture_output=True)
+    assert r.returncode == 0 and b"damaged" in r.stderr
+    check_outputs()
+    # another FASTA with the same basename in another directory gets its own cache file (the path hash keys the name)
+    d2 = os.path.join(d, "other")
+    os.makedirs(d2, exist_ok=True)
+    with open(os.path.join(d2, "genome.fa"), "wb") as f:
+        f.write(b">zz\n" + b"ACGT" * 100 + b"\n")
+    shutil.copy(os.path.join(d, case["sam"] + ".sam"), d2)
+    r = subprocess.run(cmd, cwd=d2, env=e2, capture_output=True)
+    assert r.returncode == 0 and len(caches()) == 2
+    r = subprocess.run(cmd, cwd=d, env=e2, capture_output=True)
+    assert r.returncode == 0 and b"ignoring genome cache" not in r.stderr
+    check_outputs()
