@@ -1031,7 +1031,8 @@ int pssgpu_kmer_spectrum_shard_device(pssgpu_ctx *ctx, int k, int shard, int n_s
     const uint64_t g1 = usable * (uint64_t)(shard + 1) / (uint64_t)n_shards;
     const unsigned grid = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (g1 - g0 + 255) / 256), (uint64_t)ctx->sm_count * 8);
     // 32-bit bins while no bin can overflow them (fewer than 2^32 positions in the shard)
-    const bool narrow = (g1 - g0) * 16 < 0xffffffffull;
+    // (PSSGPU_SPECTRUM_WIDE: test switch -- run the 64-bit-bin instantiations on a genome that would not need them)
+    const bool narrow = (g1 - g0) * 16 < 0xffffffffull && !getenv("PSSGPU_SPECTRUM_WIDE");
     unsigned int *d_narrow = nullptr;
     if (narrow) {
         CU(cudaMalloc(&d_narrow, bins * sizeof(unsigned int)));

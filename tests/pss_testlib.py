@@ -373,6 +373,62 @@ class Oracle:
         return counts
 
 
+def _newline_cuts(a: np.ndarray, parts: int):
+    """Cut points of a SAM byte array into `parts` pieces that end after a newline."""
+    n = a.size
+    cuts = [0]
+    for i in range(1, parts):
+        pos = max(cuts[-1], n * i // parts)
+        while pos < n:
+            nl = np.flatnonzero(a[pos:min(n, pos + (1 << 20))] == 10)
+            if nl.size:
+                pos += int(nl[0]) + 1
+                break
+            pos = min(n, pos + (1 << 20))
+        cuts.append(min(pos, n))
+    cuts.append(n)
+    return cuts
+
+
+def oracle_parallel(ora: "Oracle", sam, what: str, params, threads: int):
+    """The oracle over `sam` on `threads` host threads (ctypes releases the GIL; the oracle's tally is re-entrant and
+    the genome is shared, read only): the text is cut after newlines, every piece tallied on its own, tables and
+    outcome counters summed -- integer sums, so the result equals one sequential pass.  what: "pss" | "fragkon".
+    Returns (table_a, table_b, stats)."""
+    from concurrent.futures import ThreadPoolExecutor
+    a = sam if isinstance(sam, np.ndarray) else np.frombuffer(sam, dtype=np.uint8)
+    threads = max(1, int(threads))
+    cuts = _newline_cuts(a, threads * 4)
+    fn = ora.pss if what == "pss" else ora.fragkon
+    with ThreadPoolExecutor(threads) as ex:
+        res = list(ex.map(lambda i: fn(a[cuts[i]:cuts[i + 1]], params), range(len(cuts) - 1)))
+    ta = sum(r[0] for r in res)
+    tb = sum(r[1] for r in res)
+    st = {k: sum(r[2][k] for r in res) for k in res[0][2]}
+    return ta, tb, st
+
+
+def oracle_spectrum_parallel(ora: "Oracle", k: int, threads: int):
+    """ora_kmer_spectrum contig by contig on `threads` host threads (k-mers never span contigs,
+    genome-kmer-count.c:56-58), summed."""
+    from concurrent.futures import ThreadPoolExecutor
+    lib = ora.lib()
+    n = ora.n_contigs
+    order = sorted(range(n), key=lambda i: -int(ora.g.contents.ctg[i].len))        # longest first
+
+    def one(i):
+        sub = _OraGenome(C.cast(C.byref(ora.g.contents.ctg[i]), C.POINTER(_OraContig)), 1)
+        counts = np.zeros(1 << (2 * k), dtype=np.uint64)
+        lib.ora_kmer_spectrum(C.byref(sub), k, counts.ctypes.data)
+        return counts
+
+    total = np.zeros(1 << (2 * k), dtype=np.uint64)
+    with ThreadPoolExecutor(max(1, int(threads))) as ex:
+        for c in ex.map(one, order):
+            total += c
+    return total
+
+
 def _as_ptr(buf):
     """bytes / bytearray / np.uint8 array -> (void*, len, keepalive)."""
     if isinstance(buf, np.ndarray):

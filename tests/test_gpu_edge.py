@@ -303,3 +303,23 @@ def test_fused_pss_and_fragkon_pass(small):
         assert ctx.stats() == st and ctx.fragkon_stats() == fst
         assert np.array_equal(gf, f) and np.array_equal(gr, r)
         assert np.array_equal(gfp, fp) and np.array_equal(gtp, tp)
+
+
+def test_line_longer_than_the_staging_buffer(small):
+    """pssgpu_feed stages 68 MiB at a time; a longer "line" is cut at a multiple of fgets' 200000 bytes
+    (pss-bam.c:761-764) so that the stretches the kernel tallies are the ones line2saml would have been handed --
+    among them one that happens to be a good record."""
+    g, ora, ctx = small
+    good = Synth.sam(reads_cfg_config1(seed=9), g, 0, 50).split(b"\n")[:-1]
+    n_pad = 360 * 200000                                                      # 72 MB, a multiple of the fgets stretch
+    monster = b"q" * n_pad + good[3] + b"\tXX:Z:" + b"t" * 1000               # ... so this tail parses as a record
+    sam = b"\n".join(good[:10]) + b"\n" + monster + b"\n" + b"\n".join(good[10:]) + b"\n"
+    f, r, st = ora.pss(sam, PssParams())
+    assert st["lines"] == 50 + 360 + 1 and st["counted"] >= 45
+    for chunk in (len(sam), 50_000_001):
+        ctx.pss_begin(pkg.PssOptions())
+        for off in range(0, len(sam), chunk):
+            ctx.feed(sam[off:off + chunk], last=(off + chunk >= len(sam)))
+        gf, gr = ctx.pss_finish()
+        assert ctx.stats() == st
+        assert np.array_equal(gf, f) and np.array_equal(gr, r)
