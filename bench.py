@@ -63,6 +63,10 @@ def parse_args():
     ap.add_argument("--cpu-genome-mb", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="skip the oracle check of the benchmarked shard's tables")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --reads-per-gpu on every GPU (the default; 8 GPUs = the 200 M reads of configs[1]); "
+                         "strong: the 8 x --reads-per-gpu reads of configs[1] split over the GPUs in use")
     return ap.parse_args()
 
 
@@ -70,12 +74,30 @@ def contig_plan(scale):
     return [(n, max(1000, int(l * scale))) for n, l in HUMAN_CONTIGS]
 
 
-def workload_name(a):
-    s = "configs[1] shard: 3.1 Gb synthetic genome replica + %d of the 200 M variable-length (30-150 bp) reads " \
-        "(200 M / 8 GPUs, read-sharded)" % a.reads_per_gpu
+def reads_per_rank(a, world):
+    return a.reads_per_gpu if a.scaling == "weak" else (8 * a.reads_per_gpu) // max(1, world)
+
+
+def workload_name(a, world=1):
+    if a.scaling == "weak":
+        s = "configs[1] shard: 3.1 Gb synthetic genome replica + %d of the 200 M variable-length (30-150 bp) reads " \
+            "(200 M / 8 GPUs, read-sharded)" % a.reads_per_gpu
+    else:
+        s = "configs[1] whole: 3.1 Gb synthetic genome replica per GPU + all %d variable-length (30-150 bp) reads split " \
+            "over %d GPU(s), %d each" % (8 * a.reads_per_gpu, world, reads_per_rank(a, world))
     if a.genome_scale != 1.0:
         s += " [genome scaled x%g]" % a.genome_scale
     return s
+
+
+def reference_workload_name(a, cores, per):
+    """What --impl reference really runs (BASELINE.md "Scale": a bounded prefix, extrapolated linearly)."""
+    return ("EXTRAPOLATED, reduced config: the unmodified reference program on configs[1]-distributed reads (same generator, "
+            "same seed, same reject mix, 30-150 bp), %d reads per process x %d single-threaded processes, against a %d Mb "
+            "4-contig genome instead of the 3.1 Gb one (its FASTA loader needs ~150 s per process for 3.1 Gb; load time is "
+            "measured with an empty SAM and subtracted); reads/s is per-read streaming cost (pss-bam.c:764-783), linear in reads; "
+            "a one-off run on the full 3.1 Gb genome with >= 10 M reads is in profiles/r2_reference_fullscale.json"
+            % (per, cores, a.cpu_genome_mb))
 
 
 # ----------------------------------------------------------------------------------------------- clocks
@@ -201,8 +223,11 @@ def main_reference(a):
     # bounded: about 1 s of tally per step on every core, so that any --steps/--warmup ends within minutes
     per = max(20_000, min(a.cpu_sample_reads // 4, 400_000))
     line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "higher_is_better": True, "n_gpus": a.gpus,
-            "steps": a.steps, "warmup": a.warmup, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
-            "data": "synthetic", "config": {"workload": workload_name(a)}, "gpu_launches": 0}
+            "steps": a.steps, "warmup": a.warmup, "scaling": a.scaling, "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic", "config": {"workload": reference_workload_name(a, cores, per), "extrapolated": True,
+                                            "b200_arm_workload": workload_name(a, a.gpus), "reads_per_process": per,
+                                            "processes": cores, "genome_mb": a.cpu_genome_mb},
+            "gpu_launches": 0}
     ref = None
     try:
         ref = ReferenceSample(cores, per, a.cpu_genome_mb, READS_SEED)
@@ -333,16 +358,26 @@ def main_b200(a):
     ginfo = ctx.genome_info()
     t_genome = time.perf_counter() - t0
     cfg = reads_cfg_config2(seed=READS_SEED)
-    n_reads = a.reads_per_gpu
+    n_reads = reads_per_rank(a, world)
     lo, hi = rank * n_reads, (rank + 1) * n_reads
-    cap = Synth.sam_bound(cfg, lo, hi)
+    # the shard is generated in pieces of at most 25 M reads through one pinned buffer; the host keeps the whole shard
+    # (for the host-fed e2e run and the oracle check) while it is at most 25 M reads, else only the device does
+    piece = min(n_reads, 25_000_000)
+    cap = Synth.sam_bound(cfg, 0, piece)
     host = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
-    n_bytes = Synth.sam_into(cfg, g, lo, hi, host.data_ptr(), cap)
-    dev = torch.empty(n_bytes + 64, dtype=torch.uint8, device="cuda")
-    dev[:n_bytes].copy_(host[:n_bytes])
+    host_has_all = n_reads <= piece
+    dev = torch.empty(int(n_reads * 252) + (1 << 20), dtype=torch.uint8, device="cuda")
+    n_bytes = 0
+    for p0 in range(lo, hi, piece):
+        nb = Synth.sam_into(cfg, g, p0, min(hi, p0 + piece), host.data_ptr(), cap)
+        assert n_bytes + nb + 64 <= dev.numel(), "device text buffer too small"
+        dev[n_bytes:n_bytes + nb].copy_(host[:nb])
+        n_bytes += nb
     torch.cuda.synchronize()
     t_setup = time.perf_counter() - t0
-    del g.seqs[:]
+    verify = not a.no_verify
+    if not verify:
+        del g.seqs[:]
 
     R = 15
     opts = pkg.PssOptions()
@@ -401,7 +436,7 @@ def main_b200(a):
     check_tables = tables_host.clone()
 
     e2e = None
-    if not a.no_e2e:
+    if not a.no_e2e and host_has_all:
         e2e_steps = max(1, min(a.steps, 5))
         step_e2e()
         ctx.timing_reset(False)
@@ -412,6 +447,12 @@ def main_b200(a):
                "h2d_bytes_per_step": int(n_bytes), "d2h_bytes_per_step": int(tables_host.numel() * 8),
                "ms_per_step": ms_e2e / e2e_steps, "sam_gb_per_s": n_bytes * world * e2e_steps / (ms_e2e * 1e-3) / 1e9,
                "launches_per_step": int(tm2["launches"] // e2e_steps) if tm2["launches"] else None}
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        PEAK = (float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)")
+    else:
+        PEAK = (6650.0, "fallback (B200_PROFILING.md)")
 
     # ---- the sibling hot paths on the same resident data (configs[2], configs[3]); reported, not the headline
     other = None
@@ -425,6 +466,7 @@ def main_b200(a):
         ctx.feed_device(dev.data_ptr(), n_bytes)
         ctx.sync()
         fk_ms = ctx.timing()["kernel_ms"]
+        fk_stats = ctx.stats()
         ctx.both_begin(opts, fko)                             # pss-bam + fragkon from one scan (configs[4] workflow)
         ctx.feed_device(dev.data_ptr(), n_bytes)
         ctx.sync()
@@ -441,19 +483,111 @@ def main_b200(a):
             ctx.kmer_spectrum_device(k, counts.data_ptr())
             spec[k] = ctx.timing()["kernel_ms"]
         ctx.timing_reset(False)
+        # configs[3] over N GPUs: every rank counts its slice of the packed genome, then one NCCL all-reduce of the 4^k
+        # u64 counters (128 MiB at k = 12 -- the only bandwidth-relevant collective of the project)
+        sharded = None
+        if world > 1:
+            sharded = {}
+            for k in (8, 12):
+                nb = 1 << (2 * k)
+                best = None
+                for _ in range(3):
+                    barrier()
+                    ctx.timing_reset(True)
+                    ctx.kmer_spectrum_device(k, counts.data_ptr(), rank, world)      # synchronous: returns when the shard is counted
+                    k_ms = ctx.timing()["kernel_ms"]
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    barrier()
+                    e0.record()
+                    dist.all_reduce(counts[:nb])
+                    e1.record()
+                    torch.cuda.synchronize()
+                    t = torch.tensor([k_ms, e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    cur = [float(x) for x in t.tolist()]
+                    if best is None or sum(cur) < sum(best):
+                        best = cur
+                sharded[f"k{k}"] = {"count_ms_max_rank": best[0], "allreduce_ms": best[1], "allreduce_bytes": nb * 8,
+                                    "allreduce_busbw_gb_per_s": 2 * (world - 1) / world * nb * 8 / (best[1] * 1e-3) / 1e9,
+                                    "gbase_per_s": ginfo["n_bases"] / ((best[0] + best[1]) * 1e-3) / 1e9,
+                                    "total_kmers": int(counts[:nb].sum().item())}
+            ctx.timing_reset(False)
+        # configs[4]: both programs over one scan with -q 30 -l 30 -L 150 (pss-bam.c:96-103,409; fragkon.c:52-58,139)
+        o4 = pkg.PssOptions(min_len=30, max_len=150, min_mq=30)
+        f4 = pkg.FragkonOptions(klen=8, min_len=30, max_len=150, min_mq=30)
+        ctx.both_begin(o4, f4)
+        ctx.feed_device(dev.data_ptr(), n_bytes)
+        ctx.sync()
+        ctx.both_begin(o4, f4)
+        ctx.timing_reset(True)
+        ctx.feed_device(dev.data_ptr(), n_bytes)
+        ctx.sync()
+        c4_ms = ctx.timing()["kernel_ms"]
+        c4_counted, c4_counted_fk = ctx.stats()["counted"], ctx.fragkon_stats()["counted"]
+        ctx.timing_reset(False)
+
+        def roof(alg_bytes, ms, bound="hbm"):
+            ach = alg_bytes / (ms * 1e-3) / 1e9
+            return {"bound": bound, "achieved": ach, "peak": PEAK[0], "unit": "GB/s", "frac": ach / PEAK[0], "traffic": None,
+                    "kernel_ms": ms, "algorithmic_bytes_per_launch": int(alg_bytes)}
+
+        fk_counted = fk_stats["counted"]
         other = {"fragkon_k8": {"reads_per_s_per_gpu": n_reads / (fk_ms * 1e-3), "sam_gb_per_s_per_gpu": n_bytes / (fk_ms * 1e-3) / 1e9,
-                                "kernel_ms": fk_ms},
+                                "kernel_ms": fk_ms, "kernel": "tally_kernel<fragkon>",
+                                # record bytes + accepted x 2 x ceil(2K / 8)
+                                "roofline": roof(n_bytes + fk_counted * 2 * 2, fk_ms)},
                  "pss_and_fragkon_fused": {"reads_per_s_per_gpu": n_reads / (both_ms * 1e-3), "kernel_ms": both_ms,
-                                           "vs_two_passes": (tm["kernel_ms"] / max(1, int(tm["launches"])) + fk_ms) / both_ms},
+                                           "kernel": "tally_kernel<both>",
+                                           "vs_two_passes": (tm["kernel_ms"] / max(1, int(tm["launches"])) + fk_ms) / both_ms,
+                                           "roofline": roof(n_bytes + stats["counted"] * 9 + fk_counted * 4, both_ms)},
+                 "config4_q30_l30_L150_fused": {"workload": "configs[4] per-GPU share: pss-bam + fragkon (K = 8) from one scan of this "
+                                                            "rank's reads with -q 30 -l 30 -L 150",
+                                                "reads_per_s_per_gpu": n_reads / (c4_ms * 1e-3), "kernel_ms": c4_ms,
+                                                "counted_pss": c4_counted, "counted_fragkon": c4_counted_fk,
+                                                "roofline": roof(n_bytes + c4_counted * 9 + c4_counted_fk * 4, c4_ms)},
                  "genome_kmer_count": {f"k{k}": {"kernel_ms": ms, "gbase_per_s_per_gpu": ginfo["n_bases"] / (ms * 1e-3) / 1e9,
+                                                 "kernels": "spectrum_smem_kernel<8>, widen_kernel" if k <= 9
+                                                 else "radix_count / radix_scan / radix_scatter / radix_hist, widen_kernel",
+                                                 # packed genome in (0.5 B per base) + 4^k x 8 B table out
+                                                 "roofline": roof(ginfo["hbm_bytes"] + (1 << (2 * k)) * 8, ms),
                                                  "bound": "shared-memory atomics / instruction issue (not HBM)" if k <= 9
                                                  else "radix partition: instruction issue of the in-tile sort (not HBM)"}
                                        for k, ms in spec.items()}}
+        if sharded:
+            other["genome_kmer_count_sharded_allreduce"] = sharded
         del counts
         if rank == 0 and world == 1:
             other["config0_10Mb_1M_50bp"] = config0_case(pkg, local, torch, not a.no_cpu_baseline)
     except Exception as ex:                                   # never let the side measurements break the contract line
         other = {"error": f"{type(ex).__name__}: {ex}"}
+
+    # ---- parity gate on what was benchmarked: this rank's exact shard through the oracle on the host cores; with
+    #      N > 1 the sum of the ranks' oracle tables against the all-reduced device tables
+    verify_result = "skipped (--no-verify)"
+    verify_s = None
+    if verify and not host_has_all:
+        verify_result = "skipped (shard larger than the host keeps; run with the default --scaling weak)"
+    elif verify:
+        from pss_testlib import Oracle, PssParams, oracle_parallel
+        tv = time.perf_counter()
+        ora = Oracle(contigs=list(zip(g.names, g.seqs)))
+        threads = max(1, min(mine, cores // max(1, world)))
+        of, orv, ost = oracle_parallel(ora, host[:n_bytes].numpy(), "pss", PssParams(), threads)
+        ora.close()
+        del g.seqs[:]
+        want = torch.from_numpy(np.concatenate([of.reshape(-1), orv.reshape(-1)]).astype(np.int64)).cuda()
+        ost_t = torch.tensor([ost[k] for k in ("lines", "counted", "no_contig", "filtered", "parse_fail", "undefined")],
+                             dtype=torch.int64, device="cuda")
+        gst_t = torch.tensor([stats[k] for k in ("lines", "counted", "no_contig", "filtered", "parse_fail", "undefined")],
+                             dtype=torch.int64, device="cuda")
+        if world > 1:
+            dist.all_reduce(want)
+            dist.all_reduce(ost_t)
+            dist.all_reduce(gst_t)
+        same = bool(torch.equal(want.cpu(), check_tables)) and bool(torch.equal(ost_t, gst_t))
+        verify_s = time.perf_counter() - tv
+        verify_result = "oracle-equal" if same else "MISMATCH"
+        assert same, "benchmarked tables differ from the oracle"
 
     # ---- gather totals
     tot = torch.tensor([float(n_bytes), float(stats["counted"]), float(stats["lines"])], dtype=torch.float64, device="cuda")
@@ -464,19 +598,17 @@ def main_b200(a):
             dist.destroy_process_group()
         return
     total_bytes, total_counted, total_lines = (float(x) for x in tot.tolist())
-    # with N > 1 the all-reduced tables hold every rank's reads
+    # with N > 1 the all-reduced tables hold every rank's reads; the tables are reset at every step (pssgpu_pss_begin),
+    # so one step's worth: row 1 of the 5' table holds at most one increment per counted read
     fwd = check_tables[: (R + 2) * 16].view(R + 2, 16)
-    assert int(fwd[1].sum()) <= int(total_counted) * a.steps + 1
+    assert 0 < int(fwd[1].sum()) <= int(total_counted)
+    assert int(total_lines) == world * n_reads
 
     value = world * n_reads * a.steps / (ms_total * 1e-3)
     launches = int(tm["launches"])
     kern_ms = tm["kernel_ms"] / max(1, launches)
     alg_bytes = n_bytes + stats["counted"] * 9          # record bytes + accepted x ceil(2*(R+2)*2 bit / 8)
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    peak, peak_src = PEAK
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "tally_traffic.json")
@@ -489,14 +621,17 @@ def main_b200(a):
             traffic = None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
-        "config": {"workload": workload_name(a), "reads_per_gpu": n_reads, "sam_bytes_per_gpu": int(n_bytes),
+        "verify": verify_result,
+        "config": {"workload": workload_name(a, world), "reads_per_gpu": n_reads, "sam_bytes_per_gpu": int(n_bytes),
                    "bytes_per_read": n_bytes / n_reads, "genome_bases": ginfo["n_bases"], "genome_hbm_bytes": ginfo["hbm_bytes"],
                    "region_len": R, "l2": "input (%.1f GB/GPU) larger than L2, no flush needed" % (n_bytes / 1e9),
                    "seeds": {"genome": GENOME_SEED, "reads": READS_SEED},
                    "accepted_fraction": total_counted / max(1.0, total_lines),
-                   "setup_s": {"genome_synth_upload_pack": t_genome, "total": t_setup}},
+                   "setup_s": {"genome_synth_upload_pack": t_genome, "total": t_setup, "oracle_verify": verify_s},
+                   "verify": "after the timed loop every rank's exact shard is tallied by the CPU oracle (oracle/liboracle.so, all "
+                             "host cores) and the (all-reduced) tables and outcome counters must be equal"},
         "sam_gb_per_s": total_bytes * a.steps / (ms_total * 1e-3) / 1e9,
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
