@@ -165,6 +165,34 @@ int pssgpu_feed(pssgpu_ctx *ctx, const char *sam_bytes, size_t len, int last);
  * came from cudaMalloc. */
 int pssgpu_feed_device(pssgpu_ctx *ctx, const void *d_sam, size_t len);
 
+/* ---- BAM input ----------------------------------------------------------------
+ * The reference reads its BAM through popen("samtools view [-r RG] <bam>")
+ * (pss-bam.c:148-162, fragkon.c:84-93).  pssgpu_feed_bam takes the BYTES OF THE BAM
+ * FILE instead (BGZF blocks, any chunking, partial blocks are carried to the
+ * next call; `last` != 0 marks the end of the file) and does on the device what
+ * the samtools child did: BGZF inflate, BAM record framing, and the rendering of
+ * every alignment as the SAM line the reference's fgets loop would have seen --
+ * reduced to the fields line2saml / process_aln read (sam-parse.c:36-50) -- which
+ * then goes through the same tally kernel as pssgpu_feed's text.  Tables are
+ * identical to feeding `samtools view` output of the same file.  Returns once
+ * the bytes have been copied to the device, like pssgpu_feed.  Malformed input
+ * (bad BGZF / BAM structure, a file that ends inside a record) is reported by
+ * pssgpu_sync / *_finish as PSSGPU_EINVAL.  CRC32s are not verified.  Do not mix
+ * with pssgpu_feed within one tally. */
+int pssgpu_feed_bam(pssgpu_ctx *ctx, const void *bgzf_bytes, size_t len, int last);
+/* `samtools view -r RG`, natively (pss-bam.c:153-155 `-R`): only alignments
+ * whose RG:Z tag equals `read_group` are tallied; NULL switches the filter off.
+ * Applies to pssgpu_feed_bam; sticky across tallies. */
+int pssgpu_bam_read_group(pssgpu_ctx *ctx, const char *read_group);
+typedef struct pssgpu_bam_stats {
+    uint64_t records;                 /* alignment records seen since *_begin      */
+    uint64_t dropped_by_read_group;   /* ... of which the -R filter dropped         */
+    uint64_t references;              /* n_ref of the BAM header                   */
+    uint64_t batches;                 /* device batches                            */
+    uint64_t blocks_rewalked;         /* BGZF blocks whose first-record guess had to be corrected */
+} pssgpu_bam_stats;
+int pssgpu_bam_info(pssgpu_ctx *ctx, pssgpu_bam_stats *out);
+
 /* Wait for all fed bytes to be tallied. */
 int pssgpu_sync(pssgpu_ctx *ctx);
 

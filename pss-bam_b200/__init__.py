@@ -38,7 +38,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     Safe under torchrun: one process builds (file lock), into a temporary file that is renamed into place, so no other
     rank ever dlopens a half-written library."""
     import fcntl
-    srcs = [os.path.join(CSRC, f) for f in ("pssgpu.cu", "pss_kernels.cuh", "pss_record.h")]
+    srcs = [os.path.join(CSRC, f) for f in ("pssgpu.cu", "pssgpu_bam.cu", "pssgpu_internal.h", "pss_kernels.cuh", "pss_record.h",
+                                            "pss_inflate.h", "pss_bamrec.h")]
     srcs.append(os.path.join(ROOT, "include", "pssgpu.h"))
     newest = max(os.path.getmtime(s) for s in srcs)
 
@@ -55,7 +56,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
                 return LIB_PATH
             nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
             tmp = LIB_PATH + f".tmp{os.getpid()}"
-            cmd = [nvcc, *NVCC_FLAGS, "-o", tmp, os.path.join(CSRC, "pssgpu.cu")]
+            cmd = [nvcc, *NVCC_FLAGS, "--threads", "2", "-o", tmp, os.path.join(CSRC, "pssgpu.cu"), os.path.join(CSRC, "pssgpu_bam.cu")]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             r = subprocess.run(cmd, capture_output=True, text=True)
@@ -95,6 +96,10 @@ class _Stats(C.Structure):
     _fields_ = [(k, C.c_uint64) for k in ("lines", "counted", "no_contig", "filtered", "parse_fail", "undefined")]
 
 
+class _BamStats(C.Structure):
+    _fields_ = [(k, C.c_uint64) for k in ("records", "dropped_by_read_group", "references", "batches", "blocks_rewalked")]
+
+
 class _Timing(C.Structure):
     _fields_ = [("launches", C.c_uint64), ("kernel_ms", C.c_double), ("bytes_scanned", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
@@ -107,6 +112,7 @@ ABI_SYMBOLS = (
     "pssgpu_genome_upload", "pssgpu_genome_upload_device", "pssgpu_genome_save", "pssgpu_genome_load", "pssgpu_genome_save_tagged", "pssgpu_genome_load_tagged",
     "pssgpu_genome_info",
     "pssgpu_pss_default_params", "pssgpu_pss_begin", "pssgpu_feed", "pssgpu_feed_device", "pssgpu_sync",
+    "pssgpu_feed_bam", "pssgpu_bam_read_group", "pssgpu_bam_info",
     "pssgpu_pss_finish", "pssgpu_pss_finish_device", "pssgpu_get_stats", "pssgpu_both_begin", "pssgpu_get_fragkon_stats",
     "pssgpu_fragkon_default_params", "pssgpu_fragkon_begin", "pssgpu_fragkon_finish", "pssgpu_fragkon_finish_device",
     "pssgpu_kmer_spectrum", "pssgpu_kmer_spectrum_shard", "pssgpu_kmer_spectrum_shard_device",
@@ -152,6 +158,9 @@ def load_library():
     lib.pssgpu_feed.argtypes = [P, P, C.c_size_t, C.c_int]
     lib.pssgpu_feed_device.argtypes = [P, P, C.c_size_t]
     lib.pssgpu_sync.argtypes = [P]
+    lib.pssgpu_feed_bam.argtypes = [P, P, C.c_size_t, C.c_int]
+    lib.pssgpu_bam_read_group.argtypes = [P, C.c_char_p]
+    lib.pssgpu_bam_info.argtypes = [P, C.POINTER(_BamStats)]
     lib.pssgpu_pss_finish.argtypes = [P, P, P]
     lib.pssgpu_pss_finish_device.argtypes = [P, P]
     lib.pssgpu_get_stats.argtypes = [P, C.POINTER(_Stats)]
@@ -315,6 +324,24 @@ class Context:
 
     def feed_ptr(self, host_ptr: int, nbytes: int, last: bool = False):
         self._ck(self.lib.pssgpu_feed(self.h, host_ptr, nbytes, 1 if last else 0))
+
+    def feed_bam(self, bam, last: bool = False):
+        """Bytes of a BAM file (BGZF), any chunking (pssgpu_feed_bam)."""
+        addr, n, keep = _host_view(bam)
+        self._ck(self.lib.pssgpu_feed_bam(self.h, addr, n, 1 if last else 0))
+        del keep
+
+    def feed_bam_ptr(self, host_ptr: int, nbytes: int, last: bool = False):
+        self._ck(self.lib.pssgpu_feed_bam(self.h, host_ptr, nbytes, 1 if last else 0))
+
+    def bam_read_group(self, rg):
+        """samtools view -r RG, natively; None switches the filter off."""
+        self._ck(self.lib.pssgpu_bam_read_group(self.h, None if rg is None else (rg.encode() if isinstance(rg, str) else bytes(rg))))
+
+    def bam_info(self):
+        s = _BamStats()
+        self._ck(self.lib.pssgpu_bam_info(self.h, C.byref(s)))
+        return {k: int(getattr(s, k)) for k, _ in _BamStats._fields_}
 
     def feed_device(self, dev_ptr: int, nbytes: int):
         self._ck(self.lib.pssgpu_feed_device(self.h, dev_ptr, nbytes))

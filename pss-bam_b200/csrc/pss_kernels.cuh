@@ -425,7 +425,9 @@ struct TallySmem {
 
 struct TallyArgs {
     const uint8_t *sam;          // device, 16-byte aligned
-    uint64_t       len;
+    uint64_t       len;          // bytes of text (an upper bound when len_dev is set)
+    const unsigned long long *len_dev;   // non-null: the length is read from device memory when the kernel starts (text produced
+                                         // by an earlier kernel of the stream, e.g. the BAM renderer)
     uint64_t       stream_off;   // offset of sam[0] within everything fed (debug log only)
     uint64_t       range_bytes;  // the text is handed out in ranges of this many bytes (multiple of 32)
     unsigned int  *range_ctr;    // next range (zero before the launch)
@@ -627,13 +629,13 @@ __device__ __forceinline__ int lookup_contig(const ContigCache &C, const DevGeno
 // shared-memory atomics.  Returns the offset of the byte after the record.
 // Rare by construction.
 template <int MODE>
-__device__ __noinline__ uint64_t long_record(const TallyArgs *Ap, TallyShared *Sp, uint64_t gstart)
+__device__ __noinline__ uint64_t long_record(const TallyArgs *Ap, TallyShared *Sp, uint64_t gstart, uint64_t text_len)
 {
     const TallyArgs &A = *Ap;
     TallyShared     &S = *Sp;
     uint64_t p = gstart;
-    while (p < A.len && __ldg(A.sam + p) != '\n') p++;
-    uint64_t total = p - gstart + (p < A.len ? 1u : 0u);
+    while (p < text_len && __ldg(A.sam + p) != '\n') p++;
+    uint64_t total = p - gstart + (p < text_len ? 1u : 0u);
     const uint64_t g_end = gstart + total;
     uint64_t c0 = gstart;
     while (total > 0) {
@@ -968,7 +970,8 @@ __global__ void __launch_bounds__(kThreads, PSS_TALLY_CTAS_PER_SM) tally_kernel(
     uint32_t       st_acc = 0, st_acc_fk = 0;                 // lane k: outcome counter k of this warp
 #pragma unroll
     for (int i = 0; i < (NACC ? NACC : 1); i++) acc[i] = 0;
-    const uint64_t len16 = (A.len + 15) & ~15ull;
+    const uint64_t text_len = A.len_dev ? (uint64_t)__ldg(A.len_dev) : A.len;
+    const uint64_t len16 = (text_len + 15) & ~15ull;
     int            est = kStageMax;                           // bytes the next kThreads records are expected to take
 
     for (;;) {
@@ -977,8 +980,8 @@ __global__ void __launch_bounds__(kThreads, PSS_TALLY_CTAS_PER_SM) tally_kernel(
         if (tid == 0) S.ctl[0] = atomicAdd(A.range_ctr, 1u);
         __syncthreads();
         const uint64_t range_begin = (uint64_t)S.ctl[0] * A.range_bytes;
-        if (range_begin >= A.len) break;
-        const uint64_t range_end = (range_begin + A.range_bytes < A.len) ? range_begin + A.range_bytes : A.len;
+        if (range_begin >= text_len) break;
+        const uint64_t range_end = (range_begin + A.range_bytes < text_len) ? range_begin + A.range_bytes : text_len;
         uint64_t       pos = range_begin;                     // everything that starts before pos is somebody's business
         bool           want_full = false;
 
@@ -994,7 +997,7 @@ __global__ void __launch_bounds__(kThreads, PSS_TALLY_CTAS_PER_SM) tally_kernel(
             const bool     sees_end = left <= (uint64_t)want;                     // the copy reaches the end of the text
             const int      nb = sees_end ? (int)left : want;
             const bool     is_full = sees_end || want >= kStageMax;
-            const int      data_end = sees_end ? (int)((int64_t)A.len - gbase) : kPrefix + nb;
+            const int      data_end = sees_end ? (int)((int64_t)text_len - gbase) : kPrefix + nb;
             if (tid == 0) {
                 fence_proxy_async();
                 mbar_expect_tx(&S.bar, (uint32_t)nb);
@@ -1106,7 +1109,7 @@ __global__ void __launch_bounds__(kThreads, PSS_TALLY_CTAS_PER_SM) tally_kernel(
                     next = first; next_full = true;           // stage again from the record start, as much as fits
                 } else {                                       // a record longer than a tile
                     __syncthreads();
-                    if (tid == 0) S.long_end = (first < range_end) ? long_record<MODE>(&A, &S.sh, first) : first;
+                    if (tid == 0) S.long_end = (first < range_end) ? long_record<MODE>(&A, &S.sh, first, text_len) : first;
                     __syncthreads();
                     next = S.long_end;
                     if (first >= range_end) next = range_end;

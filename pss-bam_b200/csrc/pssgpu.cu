@@ -4,93 +4,25 @@
 // stream ordered on that stream: H2D staging copies, pack / tally / spectrum
 // kernels and the final D2H of the tables.  There is no CPU implementation of
 // any entry point in this library.
-#include "../../include/pssgpu.h"
+#include "pssgpu_internal.h"
 
-#include <cuda_runtime.h>
 #include <unistd.h>
 
 #include <algorithm>
-#include <cstdarg>
-#include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <string>
-#include <utility>
-#include <vector>
 
 #include "pss_kernels.cuh"
 
 using namespace pssgpu;
 
 namespace {
-
-constexpr size_t kFeedPiece   = 64ull << 20;     // bytes of SAM text per tally launch when fed from the host
-constexpr size_t kCarryCap    = 4ull << 20;      // longest partial line carried between feeds
-constexpr size_t kStageCap    = kFeedPiece + kCarryCap;
 constexpr size_t kPackPiece   = 128ull << 20;    // ASCII bases per pack launch when uploading from the host
 constexpr uint64_t kExcCap    = 4ull << 20;      // logged "other" symbols (beyond: -U/-D with such bytes unsupported)
-
 thread_local std::string g_init_error;
-
 }  // namespace
 
-struct pssgpu_ctx {
-    int          device = -1;
-    int          sm_count = 0;
-    cudaStream_t stream = nullptr;
-    std::string  err;
-
-    // genome
-    uint64_t  *d_groups = nullptr;
-    uint64_t   n_groups = 0, n_bases = 0, n_contigs = 0, genome_bytes = 0;
-    DevContig *d_contigs = nullptr;
-    char      *d_names = nullptr;
-    uint32_t  *d_hash = nullptr;
-    uint32_t   hash_mask = 0;
-    uint32_t   names_bytes = 0;
-    uint32_t   cc_seed = 0, cc_ok = 0;        // collision-free hash of the contig names for the kernels' shared-memory table
-    uint64_t  *d_exc_pos = nullptr;
-    uint8_t   *d_exc_chr = nullptr;
-    uint32_t   n_exc = 0;
-    bool       exc_overflow = false;
-    bool       have_genome = false;
-
-    // tally
-    int       mode = -1;
-    TallyCfg  cfg{};
-    TallyCfg  cfg_fk{};                       // fragkon options of the fused mode
-    unsigned long long *d_tables = nullptr;   // pss: 2*(R+2)*16
-    unsigned long long *d_fk = nullptr;       // fragkon: 2*4^K
-    size_t    fk_elems = 0;
-    unsigned long long *d_stats = nullptr;    // 2 x kStN: outcomes, and fragkon's outcomes in the fused mode
-    int       tally_grid_pss = 0, tally_grid_fk = 0;
-    unsigned int *d_range_ctr = nullptr;      // work counter of the tally kernel (zeroed before every launch)
-
-    // host feed staging
-    uint8_t  *d_stage[2] = { nullptr, nullptr };
-    int       cur = 0;
-    size_t    carry_len = 0;
-    uint64_t  fed_bytes = 0;                  // bytes handed to pssgpu_feed* since *_begin
-    cudaEvent_t copy_done = nullptr;
-    cudaStream_t copy_stream = nullptr;       // H2D staging copies run here, so that the tally of piece i overlaps the copy of piece i + 1
-    cudaEvent_t ev_copied[2] = { nullptr, nullptr }, ev_tallied[2] = { nullptr, nullptr };
-
-    // timing
-    bool      timing = false;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
-    std::vector<cudaEvent_t> ev_pool;
-    uint64_t  launches = 0, bytes_scanned = 0, h2d_bytes = 0, d2h_bytes = 0;
-    double    kernel_ms = 0.0;
-
-    // debug log
-    bool      dbg = false;
-    uint64_t *d_dbg_off = nullptr;
-    int8_t   *d_dbg_code = nullptr;
-    unsigned long long *d_dbg_n = nullptr;
-    uint64_t  dbg_cap = 0;
-};
-
-namespace {
+namespace pssgpu {
 
 int fail(pssgpu_ctx *c, int code, const char *fmt, ...)
 {
@@ -103,21 +35,7 @@ int fail(pssgpu_ctx *c, int code, const char *fmt, ...)
     return code;
 }
 
-#define CU(call)                                                                                   \
-    do {                                                                                           \
-        cudaError_t e_ = (call);                                                                   \
-        if (e_ != cudaSuccess)                                                                     \
-            return fail(ctx, e_ == cudaErrorMemoryAllocation ? PSSGPU_ENOMEM : PSSGPU_ECUDA,       \
-                        "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);      \
-    } while (0)
-
-struct Bind {          // make the context's device current for the duration of a call
-    int prev = -1;
-    explicit Bind(const pssgpu_ctx *c) { cudaGetDevice(&prev); if (prev != c->device) cudaSetDevice(c->device); else prev = -1; }
-    ~Bind() { if (prev >= 0) cudaSetDevice(prev); }
-};
-
-cudaEvent_t take_event(pssgpu_ctx *c)
+static cudaEvent_t take_event(pssgpu_ctx *c)
 {
     cudaEvent_t e = nullptr;
     if (!c->ev_pool.empty()) { e = c->ev_pool.back(); c->ev_pool.pop_back(); return e; }
@@ -148,6 +66,10 @@ void time_collect(pssgpu_ctx *c)       // stream must be idle
     }
     c->ev.clear();
 }
+
+}  // namespace pssgpu
+
+namespace {
 
 void free_genome(pssgpu_ctx *c)
 {
@@ -364,11 +286,12 @@ int ctx_string(pssgpu_ctx *ctx, const char *s, uint32_t *mask, uint32_t *other, 
 }
 
 template <int MODE>
-int launch_tally(pssgpu_ctx *ctx, const uint8_t *d_sam, size_t len, uint64_t stream_off)
+int launch_tally(pssgpu_ctx *ctx, const uint8_t *d_sam, size_t len, uint64_t stream_off, const unsigned long long *len_dev)
 {
     if (len == 0) return PSSGPU_OK;
     TallyArgs a;
     a.sam = d_sam; a.len = len; a.stream_off = stream_off;
+    a.len_dev = len_dev;
     a.g = dev_genome(ctx);
     a.cfg = ctx->cfg;
     a.cfg_fk = ctx->cfg_fk;
@@ -407,12 +330,16 @@ int launch_tally(pssgpu_ctx *ctx, const uint8_t *d_sam, size_t len, uint64_t str
     return PSSGPU_OK;
 }
 
-int launch_tally_mode(pssgpu_ctx *ctx, const uint8_t *d_sam, size_t len, uint64_t stream_off)
+}  // namespace
+
+int pssgpu::launch_tally_mode(pssgpu_ctx *ctx, const uint8_t *d_sam, size_t len, uint64_t stream_off, const unsigned long long *len_dev)
 {
-    return ctx->mode == kModePss  ? launch_tally<kModePss>(ctx, d_sam, len, stream_off)
-         : ctx->mode == kModeBoth ? launch_tally<kModeBoth>(ctx, d_sam, len, stream_off)
-                                  : launch_tally<kModeFragkon>(ctx, d_sam, len, stream_off);
+    return ctx->mode == kModePss  ? launch_tally<kModePss>(ctx, d_sam, len, stream_off, len_dev)
+         : ctx->mode == kModeBoth ? launch_tally<kModeBoth>(ctx, d_sam, len, stream_off, len_dev)
+                                  : launch_tally<kModeFragkon>(ctx, d_sam, len, stream_off, len_dev);
 }
+
+namespace {
 
 int begin_common(pssgpu_ctx *ctx)
 {
@@ -424,6 +351,7 @@ int begin_common(pssgpu_ctx *ctx)
     ctx->carry_len = 0;
     ctx->cur = 0;
     ctx->fed_bytes = 0;
+    bam_reset(ctx);
     return PSSGPU_OK;
 }
 
@@ -497,6 +425,7 @@ void pssgpu_destroy(pssgpu_ctx *ctx)
     if (!ctx) return;
     Bind bind(ctx);
     cudaStreamSynchronize(ctx->stream);
+    bam_destroy(ctx);
     free_genome(ctx);
     cudaFree(ctx->d_tables); cudaFree(ctx->d_fk); cudaFree(ctx->d_stats); cudaFree(ctx->d_range_ctr);
     cudaFree(ctx->d_stage[0]); cudaFree(ctx->d_stage[1]);
@@ -902,6 +831,7 @@ int pssgpu_sync(pssgpu_ctx *ctx)
     if (!ctx) return PSSGPU_EINVAL;
     Bind bind(ctx);
     CU(cudaStreamSynchronize(ctx->stream));
+    { const int brc = bam_check(ctx, false); if (brc != PSSGPU_OK) return brc; }
     time_collect(ctx);
     return PSSGPU_OK;
 }
@@ -916,6 +846,7 @@ int pssgpu_pss_finish(pssgpu_ctx *ctx, uint64_t *fwd, uint64_t *rev)
     CU(cudaMemcpyAsync(fwd, ctx->d_tables, half, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(rev, (const char *)ctx->d_tables + half, half, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    { const int brc = bam_check(ctx, true); if (brc != PSSGPU_OK) return brc; }
     ctx->d2h_bytes += 2 * half;
     time_collect(ctx);
     return PSSGPU_OK;
@@ -930,6 +861,7 @@ int pssgpu_pss_finish_device(pssgpu_ctx *ctx, void *d_tables)
     const size_t bytes = 2 * (size_t)(ctx->cfg.R + 2) * 16 * sizeof(uint64_t);
     CU(cudaMemcpyAsync(d_tables, ctx->d_tables, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    { const int brc = bam_check(ctx, true); if (brc != PSSGPU_OK) return brc; }
     time_collect(ctx);
     return PSSGPU_OK;
 }
@@ -943,6 +875,7 @@ int read_stats(pssgpu_ctx *ctx, pssgpu_stats *out, int which)
     unsigned long long h[kStN];
     CU(cudaMemcpyAsync(h, ctx->d_stats + which * kStN, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    { const int brc = bam_check(ctx, false); if (brc != PSSGPU_OK) return brc; }
     time_collect(ctx);
     out->lines = h[kStLines];
     out->counted = h[kStCounted];
@@ -998,6 +931,7 @@ int pssgpu_fragkon_finish(pssgpu_ctx *ctx, uint64_t *fp, uint64_t *tp)
     CU(cudaMemcpyAsync(fp, ctx->d_fk, half, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(tp, (const char *)ctx->d_fk + half, half, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    { const int brc = bam_check(ctx, true); if (brc != PSSGPU_OK) return brc; }
     ctx->d2h_bytes += 2 * half;
     time_collect(ctx);
     return PSSGPU_OK;
@@ -1011,6 +945,7 @@ int pssgpu_fragkon_finish_device(pssgpu_ctx *ctx, void *d_out)
     Bind bind(ctx);
     CU(cudaMemcpyAsync(d_out, ctx->d_fk, ctx->fk_elems * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    { const int brc = bam_check(ctx, true); if (brc != PSSGPU_OK) return brc; }
     time_collect(ctx);
     return PSSGPU_OK;
 }

@@ -1,0 +1,647 @@
+// pssgpu_bam.cu -- BGZF / BAM ingest on the device: replaces the reference's
+// popen("samtools view [-r RG] <bam>") (pss-bam.c:148-162, fragkon.c:84-93).
+//
+// pssgpu_feed_bam takes the bytes of a BAM file as they are on disk.  The host only frames BGZF blocks (an 18-byte
+// header every ~20 KB); everything else runs on the GPU, batch by batch, stream ordered, without a host round trip:
+//
+//   H2D        the compressed blocks of a batch (<= 32 MiB), double buffered on the copy stream
+//   inflate    one warp per BGZF block (pss_inflate.h), persistent warps pulling blocks from a queue
+//   prepare    (first batch) BAM header: magic, l_text, the reference dictionary -> device table
+//   guess      one warp per block: where does the first record of this block start?  (records ignore block boundaries
+//              and carry no sync marks: 32 lanes test 32 offsets at a time for three plausible records in a row), then
+//              the chain from there to the end of the block: record starts -> loc[]
+//   fix        one warp: verifies every guess against the exit of the chain before it, exactly, starting from the one
+//              known entry; a wrong or missing guess is re-walked from the true entry (rare, serial).  Finds the
+//              unfinished record at the end of the batch
+//   render     one CTA per block: every record -> the SAM line the reference would have parsed (pss_bamrec.h), the RG
+//              filter of `samtools view -r`; CTA-level allocation in the text buffer (line order is irrelevant to a tally)
+//   carry      the unfinished tail moves in front of the next batch
+//   tally      the tally kernel of pss_kernels.cuh over the rendered text; its length comes from device memory
+#include "pssgpu_internal.h"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "pss_bamrec.h"
+#include "pss_inflate.h"
+
+namespace pssgpu {
+
+constexpr size_t   kBamCarryCap  = 16ull << 20;   // front of the inflated buffer: header / record carried between batches
+constexpr size_t   kBamBatchComp = 32ull << 20;   // compressed bytes per batch
+constexpr size_t   kBamBatchU    = 160ull << 20;  // inflated bytes per batch
+constexpr uint32_t kBamMaxBlocks = 16384;
+constexpr uint32_t kBamLocCap    = 2048;          // record starts per block: 65536 / 38 bytes < 1725, + the carried one
+constexpr uint32_t kBamMaxRefs   = 1u << 21;
+constexpr uint32_t kBamNone      = 0xffffffffu;
+constexpr int      kInfWarps     = 16;            // warps per CTA of the inflate kernel
+
+enum : unsigned {
+    kBamOk = 0, kBamErrInflate = 100 /* + pss_inflate.h code */, kBamErrMagic = 200, kBamErrHeaderTooLarge, kBamErrTooManyRefs,
+    kBamErrRecord, kBamErrRecordTooLarge, kBamErrTextOverflow, kBamErrTruncated, kBamErrLocOverflow
+};
+
+struct BamDesc { uint32_t src_off, c_len, dst_off, isize; };
+
+struct BamState {                     // device resident
+    unsigned long long entry;         // offset in ubuf of the first byte not consumed yet
+    unsigned long long u_end;         // end of the inflated data of the current batch
+    unsigned long long text_len;      // bytes rendered for the current batch (the tally kernel's length)
+    unsigned long long n_records, n_dropped;      // rendered / dropped by the RG filter, all batches
+    unsigned long long carry_len;
+    unsigned long long rewalked;      // blocks whose guess was missing or wrong
+    unsigned int hdr_done, error, error_arg, work_ctr;
+    int          n_ref;
+    unsigned int hdr_len;
+};
+
+struct BamIngest {
+    // host side framing
+    std::vector<uint8_t> carry;       // bytes of an incomplete BGZF block from the previous call
+    bool      finished = false;       // `last` seen
+    std::string read_group;
+    bool      use_rg = false;
+    // device
+    BamState *d_state = nullptr;
+    uint8_t  *d_ubuf = nullptr;       // [0, kBamCarryCap) carry, then the inflated batch
+    uint8_t  *d_text = nullptr;
+    size_t    text_cap = 0;
+    uint32_t *d_loc = nullptr;        // kBamMaxBlocks x kBamLocCap record starts (offsets in ubuf)
+    uint32_t *d_s = nullptr, *d_e = nullptr, *d_n = nullptr;     // per block: guessed start, chain exit, records
+    BamDesc  *d_desc[2] = { nullptr, nullptr };
+    BamDesc  *h_desc[2] = { nullptr, nullptr };                  // pinned
+    uint8_t  *d_hdr = nullptr;        // copy of the BAM header (reference names)
+    uint32_t *d_ref_off = nullptr, *d_ref_len = nullptr;
+    char     *d_rg = nullptr;
+    int       rg_len = -1;
+    int       inflate_grid = 0, inflate_minb = 3;
+    uint64_t  batches = 0;
+};
+
+// ------------------------------------------------------------------------------------------------------------ kernels
+__device__ __forceinline__ void bam_fail(BamState *st, unsigned code, unsigned arg)
+{
+    if (atomicCAS(&st->error, 0u, code) == 0u) st->error_arg = arg;
+}
+
+// MINB = CTAs per SM the register allocation aims at: 3 (48 warps, <= 42 registers) or 2 (32 warps, <= 64 registers)
+template <int MINB>
+__global__ void __launch_bounds__(kInfWarps * 32, MINB)
+bgzf_inflate_kernel(const BamDesc *__restrict__ desc, uint32_t n_blocks, const uint8_t *__restrict__ comp, uint8_t *udata, BamState *st)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    InflateTables &T = reinterpret_cast<InflateTables *>(smem)[threadIdx.x >> 5];
+    const uint32_t lane = threadIdx.x & 31u;
+    for (;;) {
+        uint32_t b = 0;
+        if (lane == 0) b = atomicAdd(&st->work_ctr, 1u);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (b >= n_blocks) break;
+        const BamDesc d = desc[b];
+        int rc = kInfOk;
+        if (d.isize) rc = inflate_block(comp + d.src_off, d.c_len, udata + d.dst_off, d.isize, T);
+        if (rc != kInfOk && lane == 0) bam_fail(st, kBamErrInflate + (unsigned)rc, b);
+        __syncwarp();
+    }
+}
+
+// One warp.  New batch: data end, text cursor; the BAM header if it has not been seen in full yet.
+__global__ void __launch_bounds__(32)
+bam_prepare_kernel(BamState *st, const uint8_t *ubuf, uint64_t total_u, uint8_t *hdr, uint32_t *ref_off, uint32_t *ref_len)
+{
+    const uint32_t lane = threadIdx.x;
+    const uint64_t u_end = kBamCarryCap + total_u;
+    if (lane == 0) { st->u_end = u_end; st->text_len = 0; }
+    if (st->hdr_done || st->error) return;
+    const uint64_t e0 = st->entry;
+    const uint64_t avail = u_end - e0;
+    const uint8_t *p = ubuf + e0;
+    if (avail < 12) return;
+    if (bam_u32(p) != 0x014d4142u) { if (lane == 0) bam_fail(st, kBamErrMagic, bam_u32(p)); return; }      // "BAM\1"
+    const uint64_t l_text = bam_u32(p + 4);
+    if (12 + l_text > kBamCarryCap) { if (lane == 0) bam_fail(st, kBamErrHeaderTooLarge, (unsigned)l_text); return; }
+    if (avail < 12 + l_text) return;
+    const uint32_t n_ref = bam_u32(p + 8 + l_text);
+    if (n_ref > kBamMaxRefs) { if (lane == 0) bam_fail(st, kBamErrTooManyRefs, n_ref); return; }
+    uint64_t q = 12 + l_text;
+    for (uint32_t i = 0; i < n_ref; i++) {                         // warp uniform walk of the dictionary
+        if (q + 4 > avail) return;
+        const uint64_t l_name = bam_u32(p + q);
+        if (q + 8 + l_name > avail) return;
+        if (q + 8 + l_name > kBamCarryCap) { if (lane == 0) bam_fail(st, kBamErrHeaderTooLarge, i); return; }
+        if (lane == 0) { ref_off[i] = (uint32_t)(q + 4); ref_len[i] = l_name ? (uint32_t)(l_name - 1) : 0u; }
+        q += 8 + l_name;
+    }
+    for (uint64_t i = lane; i < q; i += 32) hdr[i] = p[i];
+    __syncwarp();
+    if (lane == 0) { st->n_ref = (int)n_ref; st->hdr_len = (unsigned)q; st->entry = e0 + q; st->hdr_done = 1u; }
+}
+
+// chain of records from x while they start before u1; starts go to loc (at most kBamLocCap).  Returns the exit: the
+// start of the first record at or after u1 -- or the start of a record that is not complete within [.., end), or
+// kBamNone when a record is malformed (which ends a chain that began at a wrong guess; on the true chain it is an
+// error the caller reports).
+__device__ __forceinline__ uint32_t bam_chain(const uint8_t *ubuf, uint64_t x, uint64_t u1, uint64_t end, uint32_t *loc, uint32_t &n_out,
+                                              bool write)
+{
+    uint32_t n = 0;
+    while (x < u1) {
+        if (x + 4 > end) break;
+        const uint32_t bs = bam_u32(ubuf + x);
+        if (bs < kBamFixed || bs > kBamMaxRecord) { n_out = n; return kBamNone; }
+        if (x + 4 + bs > end) break;
+        if (write && n < kBamLocCap) loc[n] = (uint32_t)x;
+        n++;
+        x += 4ull + bs;
+    }
+    n_out = n;
+    return (uint32_t)x;
+}
+
+// One warp per BGZF block.
+__global__ void __launch_bounds__(128)
+bam_guess_kernel(const BamDesc *__restrict__ desc, uint32_t n_blocks, const uint8_t *__restrict__ ubuf, const BamState *st,
+                 uint32_t *__restrict__ loc, uint32_t *__restrict__ S, uint32_t *__restrict__ E, uint32_t *__restrict__ N)
+{
+    const uint32_t b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
+    if (b >= n_blocks) return;
+    if (!st->hdr_done || st->error) { if (lane == 0) { S[b] = kBamNone; E[b] = 0; N[b] = 0; } return; }
+    const uint64_t end = st->u_end, entry = st->entry;
+    const int32_t  n_ref = st->n_ref;
+    const BamDesc  d = desc[b];
+    const uint64_t u0 = kBamCarryCap + d.dst_off, u1 = u0 + d.isize;
+    uint64_t s = ~0ull;
+    if (entry < u1 && (entry >= u0 || b == 0)) s = entry;          // the known entry lies in this block (or in the carry before block 0)
+    else if (entry < u1) {
+        for (uint64_t base = u0; base < u1 && s == ~0ull; base += 32) {
+            const uint64_t x = base + lane;
+            const bool ok = x < u1 && bam_guess_at(ubuf, x, end, n_ref);
+            const uint32_t m = __ballot_sync(0xffffffffu, ok);
+            if (m) s = base + (uint32_t)__ffs((int)m) - 1u;
+        }
+    }
+    uint32_t n = 0, e = 0;
+    if (s != ~0ull) e = bam_chain(ubuf, s, u1, end, loc + (size_t)b * kBamLocCap, n, lane == 0);     // uniform walk, lane 0 writes
+    if (lane == 0) { S[b] = s == ~0ull ? kBamNone : (uint32_t)s; E[b] = e; N[b] = n; }
+}
+
+// One warp.  Exact verification of the per-block chains, carry of the unfinished tail.
+__global__ void __launch_bounds__(32)
+bam_fix_kernel(const BamDesc *__restrict__ desc, uint32_t n_blocks, const uint8_t *__restrict__ ubuf, BamState *st,
+               uint32_t *__restrict__ loc, uint32_t *__restrict__ S, uint32_t *__restrict__ E, uint32_t *__restrict__ N, int is_last)
+{
+    const uint32_t lane = threadIdx.x;
+    if (st->error) return;
+    const uint64_t end = st->u_end;
+    uint64_t expected = st->entry;
+    unsigned long long rewalked = 0;
+    if (st->hdr_done) {
+        for (uint32_t base = 0; base < n_blocks; base += 32) {
+            const uint32_t b = base + lane;
+            const bool     have = b < n_blocks;
+            const uint32_t s = have ? S[b] : kBamNone, e = have ? E[b] : 0u;
+            const uint32_t u1 = have ? (uint32_t)(kBamCarryCap + desc[b].dst_off + desc[b].isize) : 0u;
+            const uint32_t cnt = n_blocks - base < 32u ? n_blocks - base : 32u;
+            for (uint32_t i = 0; i < cnt; i++) {
+                const uint32_t si = __shfl_sync(0xffffffffu, s, (int)i), ei = __shfl_sync(0xffffffffu, e, (int)i);
+                const uint32_t u1i = __shfl_sync(0xffffffffu, u1, (int)i);
+                if (expected >= u1i) {                        // no record starts in this block (or the chain has ended)
+                    if (si != kBamNone && lane == 0) N[base + i] = 0;
+                    continue;
+                }
+                if (si != kBamNone && (uint64_t)si == expected && ei != kBamNone) { expected = ei; continue; }
+                // missing or wrong guess: the block is walked again from the true entry
+                uint32_t n = 0;
+                const uint32_t ee = bam_chain(ubuf, expected, u1i, end, loc + (size_t)(base + i) * kBamLocCap, n, lane == 0);
+                rewalked++;
+                if (ee == kBamNone) { if (lane == 0) bam_fail(st, kBamErrRecord, base + i); return; }
+                if (lane == 0) N[base + i] = n;
+                expected = ee;
+            }
+        }
+    }
+    // whatever lies between `expected` and the end of the data is an unfinished record (or header): carried over
+    const uint64_t carry = end - expected;
+    if (lane == 0) {
+        st->rewalked += rewalked;
+        st->carry_len = carry;
+        if (carry > kBamCarryCap) bam_fail(st, kBamErrRecordTooLarge, (unsigned)(carry >> 10));
+        else if (is_last && carry) bam_fail(st, kBamErrTruncated, (unsigned)carry);
+        st->entry = expected;                              // the carry kernel rebases it
+    }
+}
+
+// One CTA per BGZF block: records -> SAM lines.
+__global__ void __launch_bounds__(128)
+bam_render_kernel(const uint8_t *__restrict__ ubuf, BamState *st, const uint32_t *__restrict__ loc, const uint32_t *__restrict__ N,
+                  BamRefs refs, const char *__restrict__ rg, int rg_len, uint8_t *__restrict__ text, uint64_t text_cap)
+{
+    __shared__ uint32_t s_warp[4];
+    __shared__ unsigned long long s_base;
+    const uint32_t b = blockIdx.x, tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (!st->hdr_done || st->error) return;
+    const uint32_t n = N[b];
+    if (n > kBamLocCap) { if (tid == 0) bam_fail(st, kBamErrLocOverflow, b); return; }
+    refs.n_ref = st->n_ref;
+    const uint32_t *mine = loc + (size_t)b * kBamLocCap;
+    uint32_t dropped = 0;
+    for (uint32_t i0 = 0; i0 < n; i0 += 128) {
+        const uint32_t i = i0 + tid;
+        const uint8_t *r = nullptr;
+        BamCore        c{};
+        uint32_t       len = 0;
+        if (i < n) {
+            r = ubuf + mine[i];
+            c = bam_core(r);
+            if (!bam_wellformed(c)) { bam_fail(st, kBamErrRecord, b); r = nullptr; }
+            else if (rg_len >= 0 && !bam_has_read_group(r, c, rg, rg_len)) { dropped++; r = nullptr; }
+            else { BamCountSink cs; bam_render(r, c, refs, cs); len = cs.n; }
+        }
+        // exclusive scan of len over the CTA, one allocation per round
+        uint32_t inc = len;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+            if ((int)lane >= d) inc += t;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+        for (uint32_t w = 0; w < 4; w++) { const uint32_t v = s_warp[w]; if (w < warp) before += v; total += v; }
+        if (tid == 0) s_base = total ? atomicAdd(&st->text_len, (unsigned long long)total) : 0ull;
+        __syncthreads();
+        const unsigned long long at = s_base + before + inc - len;
+        if (s_base + total > text_cap) { if (tid == 0) bam_fail(st, kBamErrTextOverflow, b); return; }
+        if (r) { BamWriteSink ws{ text + at }; bam_render(r, c, refs, ws); }
+        __syncthreads();
+    }
+    // counters: one atomic per warp
+    const uint32_t kept = 0;
+    (void)kept;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) dropped += __shfl_xor_sync(0xffffffffu, dropped, d);
+    if (lane == 0 && dropped) atomicAdd(&st->n_dropped, (unsigned long long)dropped);
+    if (tid == 0) atomicAdd(&st->n_records, (unsigned long long)n);
+}
+
+// One CTA: the unfinished tail moves to the end of the carry region (an ascending copy to lower addresses: safe when
+// source and destination overlap), and the entry follows.
+__global__ void __launch_bounds__(256)
+bam_carry_kernel(uint8_t *ubuf, BamState *st)
+{
+    if (st->error) return;
+    const uint64_t len = st->carry_len, src = st->entry, dst = kBamCarryCap - len;
+    if (src != dst) {
+        for (uint64_t off = 0; off < len; off += 256) {
+            const uint64_t i = off + threadIdx.x;
+            uint8_t v = 0;
+            if (i < len) v = ubuf[src + i];
+            __syncthreads();
+            if (i < len) ubuf[dst + i] = v;
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) st->entry = dst;
+}
+
+// ------------------------------------------------------------------------------------------------------------ host side
+static const char *bam_error_text(unsigned code)
+{
+    if (code >= kBamErrInflate && code < kBamErrInflate + 16) {
+        static const char *inf[] = { "", "reserved block type", "stored block length check", "invalid code lengths", "invalid literal/length symbol",
+                                     "invalid distance", "more data than ISIZE", "compressed data ends early", "less data than ISIZE" };
+        const unsigned k = code - kBamErrInflate;
+        return k < 9 ? inf[k] : "inflate";
+    }
+    switch (code) {
+    case kBamErrMagic: return "not a BAM stream (magic)";
+    case kBamErrHeaderTooLarge: return "BAM header larger than 16 MiB";
+    case kBamErrTooManyRefs: return "more than 2 M reference sequences";
+    case kBamErrRecord: return "malformed alignment record";
+    case kBamErrRecordTooLarge: return "alignment record larger than 16 MiB";
+    case kBamErrTextOverflow: return "rendered text exceeds its buffer";
+    case kBamErrTruncated: return "file ends inside a record or the header";
+    case kBamErrLocOverflow: return "more record starts in one BGZF block than the format allows";
+    default: return "unknown";
+    }
+}
+
+void bam_reset(pssgpu_ctx *ctx)
+{
+    BamIngest *B = ctx->bam;
+    if (!B) return;
+    B->carry.clear();
+    B->finished = false;
+    B->batches = 0;
+    if (B->d_state) {
+        BamState z;
+        memset(&z, 0, sizeof z);
+        z.entry = kBamCarryCap;
+        cudaMemcpyAsync(B->d_state, &z, sizeof z, cudaMemcpyHostToDevice, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+    }
+}
+
+void bam_destroy(pssgpu_ctx *ctx)
+{
+    BamIngest *B = ctx->bam;
+    if (!B) return;
+    cudaFree(B->d_state); cudaFree(B->d_ubuf); cudaFree(B->d_text); cudaFree(B->d_loc);
+    cudaFree(B->d_s); cudaFree(B->d_e); cudaFree(B->d_n);
+    for (int i = 0; i < 2; i++) { cudaFree(B->d_desc[i]); if (B->h_desc[i]) cudaFreeHost(B->h_desc[i]); }
+    cudaFree(B->d_hdr); cudaFree(B->d_ref_off); cudaFree(B->d_ref_len); cudaFree(B->d_rg);
+    delete B;
+    ctx->bam = nullptr;
+}
+
+int bam_check(pssgpu_ctx *ctx, bool finishing)
+{
+    BamIngest *B = ctx->bam;
+    if (!B || !B->d_state || B->batches == 0) {
+        if (B && finishing && !B->carry.empty())
+            return fail(ctx, PSSGPU_EINVAL, "BAM ingest: %zu bytes of an incomplete BGZF block pending (feed with last=1)", B->carry.size());
+        return PSSGPU_OK;
+    }
+    BamState s;
+    if (cudaMemcpy(&s, B->d_state, sizeof s, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, PSSGPU_ECUDA, "BAM ingest: cannot read the device state");
+    }
+    if (s.error) {
+        const int rc = (s.error == kBamErrRecordTooLarge || s.error == kBamErrHeaderTooLarge || s.error == kBamErrTooManyRefs)
+                       ? PSSGPU_EUNSUPP : PSSGPU_EINVAL;
+        return fail(ctx, rc, "BAM ingest: %s (code %u, at %u)", bam_error_text(s.error), s.error, s.error_arg);
+    }
+    if (finishing) {
+        if (!B->carry.empty())
+            return fail(ctx, PSSGPU_EINVAL, "BAM ingest: %zu bytes of an incomplete BGZF block pending (feed with last=1)", B->carry.size());
+        if (s.carry_len)
+            return fail(ctx, PSSGPU_EINVAL, "BAM ingest: %llu bytes of an unfinished record pending (feed with last=1)", s.carry_len);
+    }
+    return PSSGPU_OK;
+}
+
+namespace {
+
+int bam_ensure(pssgpu_ctx *ctx)
+{
+    if (!ctx->bam) ctx->bam = new BamIngest();
+    BamIngest *B = ctx->bam;
+    if (B->d_state) return PSSGPU_OK;
+    B->text_cap = 4 * kBamBatchU + (64ull << 20);
+    CU(cudaMalloc(&B->d_state, sizeof(BamState)));
+    CU(cudaMalloc(&B->d_ubuf, kBamCarryCap + kBamBatchU + (1u << 20)));
+    CU(cudaMalloc(&B->d_text, B->text_cap + 4096));
+    CU(cudaMalloc(&B->d_loc, (size_t)kBamMaxBlocks * kBamLocCap * sizeof(uint32_t)));
+    CU(cudaMalloc(&B->d_s, kBamMaxBlocks * sizeof(uint32_t)));
+    CU(cudaMalloc(&B->d_e, kBamMaxBlocks * sizeof(uint32_t)));
+    CU(cudaMalloc(&B->d_n, kBamMaxBlocks * sizeof(uint32_t)));
+    for (int i = 0; i < 2; i++) {
+        CU(cudaMalloc(&B->d_desc[i], kBamMaxBlocks * sizeof(BamDesc)));
+        CU(cudaMallocHost(&B->h_desc[i], kBamMaxBlocks * sizeof(BamDesc)));
+    }
+    CU(cudaMalloc(&B->d_hdr, kBamCarryCap + 64));
+    CU(cudaMalloc(&B->d_ref_off, (size_t)kBamMaxRefs * sizeof(uint32_t)));
+    CU(cudaMalloc(&B->d_ref_len, (size_t)kBamMaxRefs * sizeof(uint32_t)));
+    CU(cudaMalloc(&B->d_rg, 256));
+    const size_t smem = (size_t)kInfWarps * sizeof(InflateTables);
+    if (const char *e = getenv("PSSGPU_INFLATE_CTAS")) B->inflate_minb = atoi(e) == 2 ? 2 : 3;      // tuning switch
+    CU(cudaFuncSetAttribute(bgzf_inflate_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(bgzf_inflate_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    if (B->inflate_minb == 2) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bgzf_inflate_kernel<2>, kInfWarps * 32, smem));
+    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bgzf_inflate_kernel<3>, kInfWarps * 32, smem));
+    if (occ < 1) return fail(ctx, PSSGPU_ECUDA, "BAM ingest: the inflate kernel does not fit an SM");
+    B->inflate_grid = occ * ctx->sm_count;
+    BamState z;
+    memset(&z, 0, sizeof z);
+    z.entry = kBamCarryCap;
+    CU(cudaMemcpy(B->d_state, &z, sizeof z, cudaMemcpyHostToDevice));
+    CU(cudaMemset(B->d_ubuf, 0, kBamCarryCap));
+    for (int s = 0; s < 2; s++)
+        if (!ctx->d_stage[s]) CU(cudaMalloc(&ctx->d_stage[s], kStageCap + 64));
+    return PSSGPU_OK;
+}
+
+// One BGZF block at p (n bytes available): its total size, payload offset / length and ISIZE.  Returns 0 when more
+// bytes are needed, -1 when p does not start a BGZF block.
+int bgzf_frame(const uint8_t *p, size_t n, uint32_t *total, uint32_t *pay_off, uint32_t *pay_len, uint32_t *isize)
+{
+    if (n < 12) return 0;
+    if (p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4)) return -1;
+    const uint32_t xlen = (uint32_t)p[10] | ((uint32_t)p[11] << 8);
+    if (n < 12 + (size_t)xlen) return 0;
+    uint32_t bsize = 0, at = 12;
+    bool     found = false;
+    while (at + 4 <= 12 + xlen) {
+        const uint32_t slen = (uint32_t)p[at + 2] | ((uint32_t)p[at + 3] << 8);
+        if (p[at] == 'B' && p[at + 1] == 'C' && slen == 2 && at + 6 <= 12 + xlen) {
+            bsize = (uint32_t)p[at + 4] | ((uint32_t)p[at + 5] << 8);
+            found = true;
+            break;
+        }
+        at += 4 + slen;
+    }
+    if (!found) return -1;
+    *total = bsize + 1;
+    if (*total < 12 + xlen + 8) return -1;
+    if (n < *total) return 0;
+    *pay_off = 12 + xlen;
+    *pay_len = *total - 12 - xlen - 8;
+    *isize = (uint32_t)p[*total - 4] | ((uint32_t)p[*total - 3] << 8) | ((uint32_t)p[*total - 2] << 16) | ((uint32_t)p[*total - 1] << 24);
+    if (*isize > 65536u) return -1;
+    return 1;
+}
+
+// Submit the blocks framed in h_desc[cur][0 .. n_blocks): compressed bytes [src, src + comp_len) -> staging, kernels.
+int bam_submit(pssgpu_ctx *ctx, const uint8_t *src, size_t comp_len, uint32_t n_blocks, uint64_t total_u, int is_last)
+{
+    BamIngest *B = ctx->bam;
+    const int  cur = ctx->cur;
+    if (n_blocks) {
+        CU(cudaMemcpyAsync(ctx->d_stage[cur], src, comp_len, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CU(cudaMemcpyAsync(B->d_desc[cur], B->h_desc[cur], n_blocks * sizeof(BamDesc), cudaMemcpyHostToDevice, ctx->copy_stream));
+        ctx->h2d_bytes += comp_len;
+    }
+    CU(cudaEventRecord(ctx->ev_copied[cur], ctx->copy_stream));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[cur], 0));
+    cudaStream_t st = ctx->stream;
+    BamState    *S = B->d_state;
+    CU(cudaMemsetAsync(&S->work_ctr, 0, sizeof(unsigned int), st));
+    if (n_blocks) {
+        const size_t smem = (size_t)kInfWarps * sizeof(InflateTables);
+        const unsigned grid = (unsigned)std::min<uint64_t>((n_blocks + kInfWarps - 1) / kInfWarps, (uint64_t)B->inflate_grid);
+        time_begin(ctx, comp_len);
+        if (B->inflate_minb == 2)
+            bgzf_inflate_kernel<2><<<grid, kInfWarps * 32, smem, st>>>(B->d_desc[cur], n_blocks, ctx->d_stage[cur], B->d_ubuf + kBamCarryCap, S);
+        else
+            bgzf_inflate_kernel<3><<<grid, kInfWarps * 32, smem, st>>>(B->d_desc[cur], n_blocks, ctx->d_stage[cur], B->d_ubuf + kBamCarryCap, S);
+        time_end(ctx);
+    }
+    bam_prepare_kernel<<<1, 32, 0, st>>>(S, B->d_ubuf, total_u, B->d_hdr, B->d_ref_off, B->d_ref_len);
+    if (n_blocks) {
+        bam_guess_kernel<<<(n_blocks + 3) / 4, 128, 0, st>>>(B->d_desc[cur], n_blocks, B->d_ubuf, S, B->d_loc, B->d_s, B->d_e, B->d_n);
+    }
+    bam_fix_kernel<<<1, 32, 0, st>>>(B->d_desc[cur], n_blocks, B->d_ubuf, S, B->d_loc, B->d_s, B->d_e, B->d_n, is_last);
+    if (n_blocks) {
+        BamRefs refs;
+        refs.blob = B->d_hdr; refs.name_off = B->d_ref_off; refs.name_len = B->d_ref_len; refs.n_ref = 0;
+        time_begin(ctx, total_u);
+        bam_render_kernel<<<n_blocks, 128, 0, st>>>(B->d_ubuf, S, B->d_loc, B->d_n, refs, B->d_rg, B->use_rg ? B->rg_len : -1,
+                                                    B->d_text, B->text_cap);
+        time_end(ctx);
+    }
+    bam_carry_kernel<<<1, 256, 0, st>>>(B->d_ubuf, S);
+    CU(cudaGetLastError());
+    if (n_blocks) {
+        // the text of this batch: at most text_cap bytes, the real length is in the device state
+        const size_t bound = std::min<size_t>(B->text_cap, (size_t)(total_u + kBamCarryCap) * 2 + (1u << 20));
+        int rc = launch_tally_mode(ctx, B->d_text, bound, ctx->fed_bytes, &S->text_len);
+        if (rc != PSSGPU_OK) return rc;
+    }
+    CU(cudaEventRecord(ctx->ev_tallied[cur], ctx->stream));
+    ctx->cur ^= 1;
+    // the other staging buffer (and its descriptor array) is free once the batch that used it has been inflated; the
+    // simple, sufficient condition: that whole batch is done
+    CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_tallied[ctx->cur], 0));
+    B->batches++;
+    return PSSGPU_OK;
+}
+
+int feed_bam_impl(pssgpu_ctx *ctx, const uint8_t *data, size_t len, int last)
+{
+    BamIngest *B = ctx->bam;
+    if (B->finished && len) return fail(ctx, PSSGPU_EINVAL, "feed_bam: data after last=1");
+    size_t off = 0;
+    // a block left incomplete by the previous call: completed in the carry buffer and submitted on its own
+    while (!B->carry.empty() && off < len) {
+        uint32_t total = 0, po = 0, pl = 0, isz = 0;
+        int fr = bgzf_frame(B->carry.data(), B->carry.size(), &total, &po, &pl, &isz);
+        if (fr < 0) return fail(ctx, PSSGPU_EINVAL, "feed_bam: not a BGZF block (at byte %llu)", (unsigned long long)ctx->fed_bytes);
+        if (fr == 1) break;
+        // how many more bytes are certainly needed
+        size_t need = 1;
+        if (B->carry.size() < 12) need = 12 - B->carry.size();
+        else {
+            const uint32_t xlen = (uint32_t)B->carry[10] | ((uint32_t)B->carry[11] << 8);
+            if (B->carry.size() < 12 + (size_t)xlen) need = 12 + xlen - B->carry.size();
+            else if (total > B->carry.size()) need = total - B->carry.size();
+        }
+        const size_t take = std::min(need, len - off);
+        B->carry.insert(B->carry.end(), data + off, data + off + take);
+        off += take;
+    }
+    if (!B->carry.empty()) {
+        uint32_t total = 0, po = 0, pl = 0, isz = 0;
+        int fr = bgzf_frame(B->carry.data(), B->carry.size(), &total, &po, &pl, &isz);
+        if (fr < 0) return fail(ctx, PSSGPU_EINVAL, "feed_bam: not a BGZF block (at byte %llu)", (unsigned long long)ctx->fed_bytes);
+        if (fr == 1) {
+            const int cur = ctx->cur;
+            CU(cudaEventSynchronize(ctx->ev_copied[cur]));          // h_desc[cur] is free again
+            B->h_desc[cur][0] = BamDesc{ po, pl, 0u, isz };
+            // cudaMemcpyAsync from the (pageable) carry vector: the copy is staged before the call returns
+            int rc = bam_submit(ctx, B->carry.data(), total, 1, isz, 0);
+            if (rc != PSSGPU_OK) return rc;
+            CU(cudaStreamSynchronize(ctx->copy_stream));
+            B->carry.clear();
+        }
+    }
+    // whole blocks in place
+    while (off < len) {
+        const int cur = ctx->cur;
+        CU(cudaEventSynchronize(ctx->ev_copied[cur]));              // h_desc[cur] is free again
+        BamDesc *desc = B->h_desc[cur];
+        const size_t start = off;
+        uint32_t n_blocks = 0;
+        uint64_t total_u = 0;
+        bool     more = true;
+        while (off < len && n_blocks < kBamMaxBlocks) {
+            uint32_t total = 0, po = 0, pl = 0, isz = 0;
+            int fr = bgzf_frame(data + off, len - off, &total, &po, &pl, &isz);
+            if (fr < 0) return fail(ctx, PSSGPU_EINVAL, "feed_bam: not a BGZF block (at byte %llu)", (unsigned long long)(ctx->fed_bytes + off));
+            if (fr == 0) { more = false; break; }
+            if ((off - start) + total > kBamBatchComp || total_u + isz > kBamBatchU) break;
+            desc[n_blocks++] = BamDesc{ (uint32_t)(off - start) + po, pl, (uint32_t)total_u, isz };
+            total_u += isz;
+            off += total;
+        }
+        if (n_blocks) {
+            int rc = bam_submit(ctx, data + start, off - start, n_blocks, total_u, 0);
+            if (rc != PSSGPU_OK) return rc;
+        }
+        if (!more) {                                     // an incomplete block at the end of this call
+            B->carry.assign(data + off, data + len);
+            off = len;
+        }
+    }
+    ctx->fed_bytes += len;
+    if (last) {
+        if (!B->carry.empty()) return fail(ctx, PSSGPU_EINVAL, "feed_bam: the stream ends inside a BGZF block (%zu bytes)", B->carry.size());
+        // an empty batch with the is_last mark: an unfinished record / header left in the carry is an error
+        int rc = bam_submit(ctx, nullptr, 0, 0, 0, 1);
+        if (rc != PSSGPU_OK) return rc;
+        B->finished = true;
+    }
+    return PSSGPU_OK;
+}
+
+}  // namespace
+}  // namespace pssgpu
+
+using namespace pssgpu;
+
+extern "C" {
+
+int pssgpu_bam_read_group(pssgpu_ctx *ctx, const char *read_group)
+{
+    if (!ctx) return PSSGPU_EINVAL;
+    Bind bind(ctx);
+    int rc = bam_ensure(ctx);
+    if (rc != PSSGPU_OK) return rc;
+    BamIngest *B = ctx->bam;
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (!read_group) { B->use_rg = false; B->read_group.clear(); B->rg_len = -1; return PSSGPU_OK; }
+    const size_t n = strlen(read_group);
+    if (n > 255) return fail(ctx, PSSGPU_EUNSUPP, "read group name longer than 255 bytes");
+    B->read_group = read_group;
+    B->use_rg = true;
+    B->rg_len = (int)n;
+    if (n) CU(cudaMemcpy(B->d_rg, read_group, n, cudaMemcpyHostToDevice));
+    return PSSGPU_OK;
+}
+
+int pssgpu_feed_bam(pssgpu_ctx *ctx, const void *bgzf_bytes, size_t len, int last)
+{
+    if (!ctx || (!bgzf_bytes && len)) return fail(ctx, PSSGPU_EINVAL, "feed_bam: null argument");
+    if (ctx->mode < 0) return fail(ctx, PSSGPU_EINVAL, "feed_bam: no tally open (call *_begin first)");
+    if (ctx->carry_len) return fail(ctx, PSSGPU_EINVAL, "feed_bam: a partial SAM line from pssgpu_feed is pending");
+    Bind bind(ctx);
+    int rc = bam_ensure(ctx);
+    if (rc == PSSGPU_OK) rc = feed_bam_impl(ctx, (const uint8_t *)bgzf_bytes, len, last);
+    // like pssgpu_feed: the caller's bytes have been copied when we return, the kernels may still run
+    const cudaError_t e = cudaStreamSynchronize(ctx->copy_stream);
+    if (rc != PSSGPU_OK) return rc;
+    if (e != cudaSuccess) return fail(ctx, PSSGPU_ECUDA, "feed_bam: %s", cudaGetErrorString(e));
+    return PSSGPU_OK;
+}
+
+int pssgpu_bam_info(pssgpu_ctx *ctx, pssgpu_bam_stats *out)
+{
+    if (!ctx || !out) return PSSGPU_EINVAL;
+    memset(out, 0, sizeof *out);
+    BamIngest *B = ctx->bam;
+    if (!B || !B->d_state) return PSSGPU_OK;
+    Bind bind(ctx);
+    CU(cudaStreamSynchronize(ctx->stream));
+    BamState s;
+    CU(cudaMemcpy(&s, B->d_state, sizeof s, cudaMemcpyDeviceToHost));
+    out->records = s.n_records;
+    out->dropped_by_read_group = s.n_dropped;
+    out->references = s.hdr_done ? (uint64_t)s.n_ref : 0;
+    out->batches = B->batches;
+    out->blocks_rewalked = s.rewalked;
+    return PSSGPU_OK;
+}
+
+}  // extern "C"

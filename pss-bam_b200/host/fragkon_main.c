@@ -70,9 +70,7 @@ int main(int argc, char *argv[])
     fprintf(stderr, "Finished loading genome.\nCounting kmer contexts for: %s\n", bam_fn);
 
     if (pssgpu_fragkon_begin(gpu, &par) != PSSGPU_OK) pss_die(gpu, "fragkon_begin");
-    FILE *sam = pss_bam_to_sam(bam_fn, NULL);
-    if (pss_stream_sam(gpu, sam) != PSSGPU_OK) pss_die(gpu, "tally");
-    pclose(sam);
+    if (pss_stream_input(gpu, bam_fn, NULL) != PSSGPU_OK) pss_die(gpu, "tally");
 
     const size_t bins = (size_t)1 << (2 * par.klen);
     uint64_t *fp = (uint64_t *)calloc(bins, sizeof *fp), *tp = (uint64_t *)calloc(bins, sizeof *tp);

@@ -82,9 +82,7 @@ int main(int argc, char *argv[])
     fprintf(stderr, "Finished loading genome.\nCounting matches/mismatches from:\n%s\n", bam_fn);
 
     if (pssgpu_pss_begin(gpu, &par) != PSSGPU_OK) pss_die(gpu, "pss_begin");
-    FILE *sam = pss_bam_to_sam(bam_fn, read_group);
-    if (pss_stream_sam(gpu, sam) != PSSGPU_OK) pss_die(gpu, "tally");
-    pclose(sam);
+    if (pss_stream_input(gpu, bam_fn, read_group) != PSSGPU_OK) pss_die(gpu, "tally");
 
     const int    R = par.region_len;
     const size_t cells = (size_t)(R + 2) * 16;

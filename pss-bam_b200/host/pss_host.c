@@ -142,7 +142,42 @@ static void *pump_reader(void *arg)
     }
 }
 
-int pss_stream_sam(pssgpu_ctx *ctx, FILE *sam)
+static int pump_run(pssgpu_ctx *ctx, FILE *in, int as_bam);
+
+int pss_stream_sam(pssgpu_ctx *ctx, FILE *sam) { return pump_run(ctx, sam, 0); }
+
+int pss_is_bgzf(const char *fn)
+{
+    unsigned char h[16];
+    FILE *f = fopen(fn, "rb");
+    size_t n;
+    if (!f) return 0;
+    n = fread(h, 1, sizeof h, f);
+    fclose(f);
+    return n == sizeof h && h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && (h[3] & 4) && h[12] == 'B' && h[13] == 'C';
+}
+
+int pss_stream_input(pssgpu_ctx *ctx, const char *bam_fn, const char *read_group)
+{
+    int rc;
+    if (pss_is_bgzf(bam_fn) && !getenv("PSSGPU_USE_SAMTOOLS")) {
+        /* the file's own bytes go to the GPU: BGZF inflate, BAM decoding and the -R filter run there */
+        FILE *f = fopen(bam_fn, "rb");
+        if (!f) { fprintf(stderr, "Error: Unable to open %s.\n", bam_fn); exit(1); }
+        rc = pssgpu_bam_read_group(ctx, read_group);
+        if (rc == PSSGPU_OK) rc = pump_run(ctx, f, 1);
+        fclose(f);
+        return rc;
+    }
+    {
+        FILE *sam = pss_bam_to_sam(bam_fn, read_group);
+        rc = pump_run(ctx, sam, 0);
+        pclose(sam);
+        return rc;
+    }
+}
+
+static int pump_run(pssgpu_ctx *ctx, FILE *sam, int as_bam)
 {
     pump      p;
     pthread_t th;
@@ -164,7 +199,8 @@ int pss_stream_sam(pssgpu_ctx *ctx, FILE *sam)
         const size_t got = p.got[k];
         pthread_mutex_unlock(&p.mu);
         if (got == 0) break;
-        if (rc == PSSGPU_OK) rc = pssgpu_feed(ctx, p.buf[k], got, 0);     /* after an error the pipe is still drained */
+        if (rc == PSSGPU_OK)                                               /* after an error the pipe is still drained */
+            rc = as_bam ? pssgpu_feed_bam(ctx, p.buf[k], got, 0) : pssgpu_feed(ctx, p.buf[k], got, 0);
         pthread_mutex_lock(&p.mu);
         p.full[k] = 0;
         pthread_cond_broadcast(&p.cv);
@@ -172,7 +208,8 @@ int pss_stream_sam(pssgpu_ctx *ctx, FILE *sam)
         k ^= 1;
     }
     pthread_join(th, NULL);
-    if (rc == PSSGPU_OK) rc = pssgpu_feed(ctx, p.buf[0], 0, 1);          /* a last line without '\n' */
+    if (rc == PSSGPU_OK)                                                  /* a last line without '\n' / the end of the BAM */
+        rc = as_bam ? pssgpu_feed_bam(ctx, p.buf[0], 0, 1) : pssgpu_feed(ctx, p.buf[0], 0, 1);
     if (rc == PSSGPU_OK) rc = pssgpu_sync(ctx);
     pthread_mutex_destroy(&p.mu);
     pthread_cond_destroy(&p.cv);

@@ -22,6 +22,11 @@ FILE *pss_bam_to_sam(const char *bam_fn, const char *read_group);
 /* Pump a SAM text stream into the open tally: fread into pinned memory, pssgpu_feed, flush at EOF.
  * Replaces the fgets + line2saml + process_aln loop (pss-bam.c:764-783, fragkon.c:342-363). */
 int pss_stream_sam(pssgpu_ctx *ctx, FILE *sam);
+/* The -B argument, whatever it is: a BGZF file (a real BAM) is read as it is and decoded on the GPU
+ * (pssgpu_feed_bam; -R through pssgpu_bam_read_group) -- no samtools needed; anything else goes through
+ * `samtools view [-r RG]` like in the reference (pss-bam.c:148-162).  $PSSGPU_USE_SAMTOOLS forces the pipe. */
+int pss_stream_input(pssgpu_ctx *ctx, const char *bam_fn, const char *read_group);
+int pss_is_bgzf(const char *fn);
 void pss_die(pssgpu_ctx *ctx, const char *what);
 
 #endif

@@ -54,7 +54,7 @@ def _locked_build(target, newest, force, make_cmd):
 def build_synth(force=False):
     src = os.path.join(ROOT, "tests", "synth", "pss_synth.c")
     return _locked_build(SYNTH_SO, os.path.getmtime(src), force,
-                         lambda out: ["gcc", "-O2", "-g", "-fopenmp", "-fPIC", "-shared", "-o", out, src, "-lm"])
+                         lambda out: ["gcc", "-O2", "-g", "-fopenmp", "-fPIC", "-shared", "-o", out, src, "-lm", "-lz"])
 
 
 def build_oracle(force=False):
@@ -139,6 +139,11 @@ class Synth:
             lib.synth_fasta_record.restype = C.c_size_t
             lib.synth_set_threads.argtypes = [C.c_int]
             lib.synth_set_threads.restype = None
+            lib.synth_bam_bound.argtypes = [C.c_size_t, C.c_uint32]
+            lib.synth_bam_bound.restype = C.c_size_t
+            lib.synth_sam_to_bam.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.c_uint32,
+                                             C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_size_t]
+            lib.synth_sam_to_bam.restype = C.c_size_t
             cls._lib = lib
         return cls._lib
 
@@ -169,6 +174,31 @@ class Synth:
         if n == 0 and end > begin:
             raise RuntimeError("synth_sam: output buffer too small")
         return n
+
+    @classmethod
+    def bam_into(cls, sam_ptr: int, sam_len: int, refs, out_ptr: int, out_cap: int, level=6, rg_mode=0, qual_mode=0,
+                 block_payload=0) -> int:
+        """SAM text (whole lines, as synth_sam writes them) at sam_ptr -> BAM file bytes at out_ptr.  refs: list of
+        (name, length) -- the @SQ dictionary; every RNAME of the text must be in it.  Returns the BAM size."""
+        lib = cls.lib()
+        n = len(refs)
+        names = (C.c_char_p * n)(*[r[0].encode() if isinstance(r[0], str) else r[0] for r in refs])
+        lens = (C.c_uint64 * n)(*[int(r[1]) for r in refs])
+        got = lib.synth_sam_to_bam(C.c_void_p(sam_ptr), sam_len, names, lens, n, level, rg_mode, qual_mode, block_payload,
+                                   C.c_void_p(out_ptr), out_cap)
+        if got == 0:
+            raise RuntimeError("synth_sam_to_bam: a line the writer cannot represent, or the output buffer is too small")
+        return got
+
+    @classmethod
+    def bam(cls, sam: bytes, refs, **kw) -> bytes:
+        a = np.frombuffer(sam, dtype=np.uint8)
+        cap = cls.lib().synth_bam_bound(len(sam), len(refs))
+        if kw.get("block_payload"):
+            cap += (2 * len(sam) // kw["block_payload"] + 16) * 40         # 26 bytes of framing per block
+        out = np.empty(cap, dtype=np.uint8)
+        n = cls.bam_into(a.ctypes.data, a.size, refs, out.ctypes.data, cap, **kw)
+        return out[:n].tobytes()
 
     @classmethod
     def sam_bound(cls, cfg, begin, end) -> int:
@@ -603,3 +633,156 @@ class Emul:
         counts = np.zeros(1 << (2 * k), dtype=np.uint64)
         self.lib().emul_spectrum(self.g, k, counts.ctypes.data)
         return counts
+
+
+# --------------------------------------------------------------------------- BAM: independent reader + host build of the device logic
+def bgzf_blocks(bam: bytes):
+    """[(offset, total, payload offset, payload length, isize)] of every BGZF block (SAM spec 4.1)."""
+    out, at = [], 0
+    while at < len(bam):
+        assert bam[at:at + 4] == b"\x1f\x8b\x08\x04", at
+        xlen = int.from_bytes(bam[at + 10:at + 12], "little")
+        sub, bsize = at + 12, None
+        while sub < at + 12 + xlen:
+            slen = int.from_bytes(bam[sub + 2:sub + 4], "little")
+            if bam[sub:sub + 2] == b"BC":
+                bsize = int.from_bytes(bam[sub + 4:sub + 6], "little")
+            sub += 4 + slen
+        total = bsize + 1
+        isize = int.from_bytes(bam[at + total - 4:at + total], "little")
+        out.append((at, total, at + 12 + xlen, total - 12 - xlen - 8, isize))
+        at += total
+    return out
+
+
+def bgzf_inflate(bam: bytes) -> bytes:
+    """The inflated stream, by zlib, CRCs checked."""
+    import zlib
+    parts = []
+    for at, total, po, pl, isize in bgzf_blocks(bam):
+        d = zlib.decompress(bam[po:po + pl], -15)
+        assert len(d) == isize and zlib.crc32(d) == int.from_bytes(bam[at + total - 8:at + total - 4], "little")
+        parts.append(d)
+    return b"".join(parts)
+
+
+def bam_to_sam(bam: bytes, read_group=None) -> bytes:
+    """What `samtools view [-r RG]` prints for this BAM: an independent reader (zlib + struct), all eleven fields and the
+    optional fields with their types.  Python loops: small inputs only."""
+    import struct
+    u = bgzf_inflate(bam)
+    assert u[:4] == b"BAM\x01"
+    l_text, = struct.unpack_from("<i", u, 4)
+    n_ref, = struct.unpack_from("<i", u, 8 + l_text)
+    p = 12 + l_text
+    names = []
+    for _ in range(n_ref):
+        l_name, = struct.unpack_from("<i", u, p)
+        names.append(u[p + 4:p + 4 + l_name - 1])
+        p += 8 + l_name
+    out = []
+    seqtab = b"=ACMGRSVTWYHKDBN"
+    while p < len(u):
+        bs, ref, pos, lrn, mapq, _bin, ncig, flag, lseq, nref, npos, tlen = struct.unpack_from("<iiiBBHHHiiii", u, p)
+        q = p + 36
+        qname = u[q:q + lrn - 1]; q += lrn
+        cig = b"".join(b"%d%c" % (v >> 4, b"MIDNSHP=XB??????"[v & 15]) for v in struct.unpack_from("<%dI" % ncig, u, q)) or b"*"
+        q += 4 * ncig
+        sb = u[q:q + (lseq + 1) // 2]; q += (lseq + 1) // 2
+        seq = bytes(seqtab[(sb[i >> 1] >> 4) if not i & 1 else (sb[i >> 1] & 15)] for i in range(lseq)) or b"*"
+        qb = u[q:q + lseq]; q += lseq
+        qual = b"*" if (lseq == 0 or qb[0] == 0xff) else bytes(c + 33 for c in qb)
+        tags, rg, end = [], None, p + 4 + bs
+        while q < end:
+            tag, ty = u[q:q + 2], u[q + 2:q + 3]; q += 3
+            if ty in b"ZH":
+                z = u.index(b"\0", q); val = u[q:z]; q = z + 1
+                tags.append(tag + b":" + ty + b":" + val)
+                if tag == b"RG" and ty == b"Z" and rg is None:
+                    rg = val
+            elif ty == b"A":
+                tags.append(tag + b":A:" + u[q:q + 1]); q += 1
+            elif ty == b"f":
+                tags.append(tag + b":f:" + (b"%g" % struct.unpack_from("<f", u, q)[0])); q += 4
+            elif ty == b"B":
+                st = u[q:q + 1]; n, = struct.unpack_from("<I", u, q + 1)
+                fmt = {b"c": "b", b"C": "B", b"s": "h", b"S": "H", b"i": "i", b"I": "I", b"f": "f"}[st]
+                vals = struct.unpack_from("<%d%s" % (n, fmt), u, q + 5)
+                tags.append(tag + b":B:" + st + b"".join(b",%d" % v for v in vals))
+                q += 5 + n * struct.calcsize(fmt)
+            else:
+                fmt = {b"c": "b", b"C": "B", b"s": "h", b"S": "H", b"i": "i", b"I": "I"}[ty]
+                tags.append(tag + b":i:%d" % struct.unpack_from("<" + fmt, u, q)[0]); q += struct.calcsize(fmt)
+        p = end
+        if read_group is not None and rg != (read_group.encode() if isinstance(read_group, str) else read_group):
+            continue
+        rname = names[ref] if ref >= 0 else b"*"
+        rnext = b"*" if nref < 0 else (b"=" if nref == ref else names[nref])
+        out.append(b"\t".join([qname, b"%d" % flag, rname, b"%d" % (pos + 1), b"%d" % mapq, cig, rnext, b"%d" % (npos + 1),
+                                b"%d" % tlen, seq, qual] + tags) + b"\n")
+    return b"".join(out)
+
+
+BAM_EMUL_SO = os.path.join(ROOT, "tests", "host_emul", "libpssbamemul.so")
+
+
+def build_bam_emul(force=False):
+    src = os.path.join(ROOT, "tests", "host_emul", "pss_bam_emul.cpp")
+    hdrs = [os.path.join(ROOT, "pss-bam_b200", "csrc", h) for h in ("pss_inflate.h", "pss_bamrec.h", "pss_record.h")]
+    newest = max(os.path.getmtime(f) for f in [src] + hdrs)
+    return _locked_build(BAM_EMUL_SO, newest, force,
+                         lambda out: ["g++", "-O2", "-g", "-std=c++17", "-Wno-unknown-pragmas", "-fPIC", "-shared", "-o", out, src])
+
+
+class BamEmul:
+    """pss_inflate.h / pss_bamrec.h compiled for the host (a TEST of the device logic, never a product path)."""
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            build_bam_emul()
+            lib = C.CDLL(BAM_EMUL_SO)
+            lib.emul_inflate.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+            lib.emul_bam_render.argtypes = [C.c_void_p, C.c_uint64, C.c_char_p, C.c_void_p, C.c_uint64,
+                                            C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+            lib.emul_bam_render.restype = C.c_long
+            lib.emul_bam_guess_stats.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)]
+            cls._lib = lib
+        return cls._lib
+
+    @classmethod
+    def inflate(cls, bam: bytes) -> bytes:
+        """Every BGZF payload through the device inflate logic."""
+        lib = cls.lib()
+        parts = []
+        for at, total, po, pl, isize in bgzf_blocks(bam):
+            src = np.frombuffer(bam, dtype=np.uint8, count=pl + 8 if po + pl + 8 <= len(bam) else pl, offset=po)
+            src = np.concatenate([src[:pl], np.zeros(8, dtype=np.uint8)])
+            out = np.zeros(isize + 16, dtype=np.uint8)
+            rc = lib.emul_inflate(src.ctypes.data, pl, out.ctypes.data, isize)
+            if rc != 0:
+                raise ValueError(f"inflate error {rc} in the block at {at}")
+            parts.append(out[:isize].tobytes())
+        return b"".join(parts)
+
+    @classmethod
+    def render(cls, inflated: bytes, read_group=None):
+        lib = cls.lib()
+        u = np.frombuffer(inflated + b"\0" * 16, dtype=np.uint8)
+        cap = 4 * len(inflated) + 4096
+        text = np.zeros(cap, dtype=np.uint8)
+        nr, nd = C.c_uint64(), C.c_uint64()
+        n = lib.emul_bam_render(u.ctypes.data, len(inflated), None if read_group is None else read_group.encode(), text.ctypes.data,
+                                cap, C.byref(nr), C.byref(nd))
+        if n < 0:
+            raise ValueError(f"render error {n}")
+        return text[:n].tobytes(), int(nr.value), int(nd.value)
+
+    @classmethod
+    def guess_stats(cls, inflated: bytes, block=65280):
+        lib = cls.lib()
+        u = np.frombuffer(inflated + b"\0" * 16, dtype=np.uint8)
+        out = (C.c_uint64 * 3)()
+        assert lib.emul_bam_guess_stats(u.ctypes.data, len(inflated), block, out) == 0
+        return [int(x) for x in out]

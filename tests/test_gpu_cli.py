@@ -134,3 +134,52 @@ def test_cli_with_packed_genome_cache(env):
     r = subprocess.run(cmd, cwd=d, env=e2, capture_output=True)
     assert r.returncode == 0 and b"ignoring genome cache" not in r.stderr
     check_outputs()
+
+
+@pytest.mark.parametrize("prog", ["pss-bam", "fragkon"])
+def test_cli_reads_real_bam_files(env, prog):
+    """-B with a real BAM (BGZF) file: decoded on the GPU, no samtools on PATH at all -- byte-identical outputs to the
+    golden files the reference wrote from the same alignments as SAM text; -R through the native filter."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from pss_testlib import Synth
+    d, e = env
+    e2 = dict(e, PATH="/usr/bin:/bin")                     # no samtools shim
+    refs = []
+    name = None
+    for ln in open(os.path.join(GOLD, MAN["fasta"]), "rb").read().split(b"\n"):
+        if ln.startswith(b">"):
+            name = ln[1:].split()[0].decode()
+            refs.append([name, 0])
+        elif name:
+            refs[-1][1] += len(ln.strip())
+    refs.append(["chrUn_synthetic_decoy", 1000])
+    cases = MAN["pss"][:4] if prog == "pss-bam" else MAN["fragkon"][:4]
+    done = 0
+    for case in cases:
+        sam = open(os.path.join(GOLD, case["sam"] + ".sam"), "rb").read()
+        try:
+            bam = Synth.bam(sam, refs, block_payload=3000)
+        except RuntimeError:
+            continue                                        # the edge corpus holds lines no BAM can represent
+        done += 1
+        # same file NAME as in the golden run (the headers of the outputs embed it), BAM content
+        bam_fn = os.path.join(d, "bamdir_" + prog, case["sam"] + ".sam")
+        os.makedirs(os.path.dirname(bam_fn), exist_ok=True)
+        with open(bam_fn, "wb") as f:
+            f.write(bam)
+        wd = os.path.dirname(bam_fn)
+        if not os.path.exists(os.path.join(wd, "genome.fa")):
+            os.symlink(os.path.join(GOLD, MAN["fasta"]), os.path.join(wd, "genome.fa"))
+        if prog == "pss-bam":
+            r = subprocess.run([os.path.join(BIN, "pss-bam"), "-F", "genome.fa", "-B", case["sam"] + ".sam", "-o", "out", *case["args"]],
+                               cwd=wd, env=e2, capture_output=True)
+            assert r.returncode == 0, r.stderr[-2000:]
+            assert open(os.path.join(wd, "out.pss.counts.txt"), "rb").read() == _gold(case["counts"])
+            assert open(os.path.join(wd, "out.pss.rates.txt"), "rb").read() == _gold(case["rates"])
+        else:
+            r = subprocess.run([os.path.join(BIN, "fragkon"), "-F", "genome.fa", "-B", case["sam"] + ".sam", *case["args"]],
+                               cwd=wd, env=e2, capture_output=True)
+            assert r.returncode == 0, r.stderr[-2000:]
+            assert not case["sparse"] and r.stdout == _gold(case["out"]), case
+    assert done >= 2
