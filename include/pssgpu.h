@@ -157,6 +157,13 @@ int pssgpu_pss_begin(pssgpu_ctx *ctx, const pssgpu_pss_params *p);
  * fgets() would hand to line2saml (pss-bam.c:761-764). */
 int pssgpu_feed(pssgpu_ctx *ctx, const char *sam_bytes, size_t len, int last);
 
+/* The same without waiting for the copies: `sam_bytes` (pinned memory from
+ * pssgpu_host_alloc) must stay untouched until pssgpu_feed_wait(ctx) returns.
+ * This is what lets one host thread keep the PCIe links of several GPUs busy at
+ * once (host/pss_host.c deals its input chunks to the members of a group). */
+int pssgpu_feed_async(pssgpu_ctx *ctx, const char *sam_bytes, size_t len, int last);
+int pssgpu_feed_wait(pssgpu_ctx *ctx);
+
 /* Same for SAM text already resident in device memory.  `d_sam` must be
  * 16-byte aligned and hold WHOLE lines (last byte '\n'); it must stay valid
  * until the next pssgpu_*_finish / pssgpu_sync.  No copy is made.  The bulk
@@ -248,6 +255,37 @@ int pssgpu_get_fragkon_stats(pssgpu_ctx *ctx, pssgpu_stats *out);
 int pssgpu_kmer_spectrum(pssgpu_ctx *ctx, int k, uint64_t *counts);
 int pssgpu_kmer_spectrum_shard(pssgpu_ctx *ctx, int k, int shard, int n_shards, uint64_t *counts);
 int pssgpu_kmer_spectrum_shard_device(pssgpu_ctx *ctx, int k, int shard, int n_shards, void *d_counts);
+
+/* ---- several GPUs of one box ---------------------------------------------------
+ * reads shard, the genome replicates, the tables are summed once at
+ * the end.  A group is one context per GPU in ONE process (the host programs
+ * use it when $PSSGPU_DEVICES names more than one GPU; bench.py instead runs
+ * one process per GPU under torchrun and sums with torch.distributed).  The sum
+ * is an ncclAllReduce(ncclSum, ncclUint64) over NVLink -- NCCL is loaded at run
+ * time -- or, without NCCL / with PSSGPU_GROUP_REDUCE=peer, peer copies to the
+ * first GPU and an add kernel there.  devices == NULL or n <= 0: all visible
+ * GPUs.  Group calls report through pssgpu_group_last_error. */
+typedef struct pssgpu_group pssgpu_group;
+int         pssgpu_group_init(const int *devices, int n, pssgpu_group **out);
+void        pssgpu_group_destroy(pssgpu_group *g);
+int         pssgpu_group_size(const pssgpu_group *g);
+pssgpu_ctx *pssgpu_group_ctx(pssgpu_group *g, int i);          /* member i, e.g. for pssgpu_feed_async / pssgpu_feed_bam */
+const char *pssgpu_group_last_error(const pssgpu_group *g);
+const char *pssgpu_group_reduce_backend(const pssgpu_group *g);
+double      pssgpu_group_last_reduce_ms(const pssgpu_group *g); /* device time of the last table sum */
+int pssgpu_group_genome_upload(pssgpu_group *g, const pssgpu_contig *contigs, uint64_t n_contigs);
+int pssgpu_group_genome_load_tagged(pssgpu_group *g, const char *path, const pssgpu_genome_tag *expect);
+int pssgpu_group_pss_begin(pssgpu_group *g, const pssgpu_pss_params *p);
+int pssgpu_group_fragkon_begin(pssgpu_group *g, const pssgpu_fragkon_params *p);
+int pssgpu_group_both_begin(pssgpu_group *g, const pssgpu_pss_params *pss, const pssgpu_fragkon_params *fragkon);
+/* Whole lines (a piece ends with '\n' unless `last`); pieces go to the members in turn. */
+int pssgpu_group_feed(pssgpu_group *g, const char *sam_bytes, size_t len, int last);
+int pssgpu_group_sync(pssgpu_group *g);
+int pssgpu_group_pss_finish(pssgpu_group *g, uint64_t *fwd, uint64_t *rev);
+int pssgpu_group_fragkon_finish(pssgpu_group *g, uint64_t *fp, uint64_t *tp);
+int pssgpu_group_get_stats(pssgpu_group *g, pssgpu_stats *out, int fragkon);
+/* genome-kmer-count.c:56-58 genome-sharded: member i counts slice i, then the 4^k counters are summed. */
+int pssgpu_group_kmer_spectrum(pssgpu_group *g, int k, uint64_t *counts);
 
 /* ---- measurement hooks ------------------------------------------------------------
  * CUDA-event timing of the kernels this library launches, on the stream it

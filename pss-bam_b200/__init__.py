@@ -38,7 +38,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     Safe under torchrun: one process builds (file lock), into a temporary file that is renamed into place, so no other
     rank ever dlopens a half-written library."""
     import fcntl
-    srcs = [os.path.join(CSRC, f) for f in ("pssgpu.cu", "pssgpu_bam.cu", "pssgpu_internal.h", "pss_kernels.cuh", "pss_record.h",
+    srcs = [os.path.join(CSRC, f) for f in ("pssgpu.cu", "pssgpu_bam.cu", "pssgpu_group.cu", "pssgpu_internal.h", "pss_kernels.cuh", "pss_record.h",
                                             "pss_inflate.h", "pss_bamrec.h")]
     srcs.append(os.path.join(ROOT, "include", "pssgpu.h"))
     newest = max(os.path.getmtime(s) for s in srcs)
@@ -56,7 +56,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
                 return LIB_PATH
             nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
             tmp = LIB_PATH + f".tmp{os.getpid()}"
-            cmd = [nvcc, *NVCC_FLAGS, "--threads", "2", "-o", tmp, os.path.join(CSRC, "pssgpu.cu"), os.path.join(CSRC, "pssgpu_bam.cu")]
+            cmd = [nvcc, *NVCC_FLAGS, "--threads", "3", "-o", tmp, os.path.join(CSRC, "pssgpu.cu"), os.path.join(CSRC, "pssgpu_bam.cu"),
+                   os.path.join(CSRC, "pssgpu_group.cu"), "-ldl"]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             r = subprocess.run(cmd, capture_output=True, text=True)
@@ -112,7 +113,11 @@ ABI_SYMBOLS = (
     "pssgpu_genome_upload", "pssgpu_genome_upload_device", "pssgpu_genome_save", "pssgpu_genome_load", "pssgpu_genome_save_tagged", "pssgpu_genome_load_tagged",
     "pssgpu_genome_info",
     "pssgpu_pss_default_params", "pssgpu_pss_begin", "pssgpu_feed", "pssgpu_feed_device", "pssgpu_sync",
-    "pssgpu_feed_bam", "pssgpu_bam_read_group", "pssgpu_bam_info",
+    "pssgpu_feed_bam", "pssgpu_bam_read_group", "pssgpu_bam_info", "pssgpu_feed_async", "pssgpu_feed_wait",
+    "pssgpu_group_init", "pssgpu_group_destroy", "pssgpu_group_size", "pssgpu_group_ctx", "pssgpu_group_last_error",
+    "pssgpu_group_reduce_backend", "pssgpu_group_last_reduce_ms", "pssgpu_group_genome_upload", "pssgpu_group_genome_load_tagged",
+    "pssgpu_group_pss_begin", "pssgpu_group_fragkon_begin", "pssgpu_group_both_begin", "pssgpu_group_feed", "pssgpu_group_sync",
+    "pssgpu_group_pss_finish", "pssgpu_group_fragkon_finish", "pssgpu_group_get_stats", "pssgpu_group_kmer_spectrum",
     "pssgpu_pss_finish", "pssgpu_pss_finish_device", "pssgpu_get_stats", "pssgpu_both_begin", "pssgpu_get_fragkon_stats",
     "pssgpu_fragkon_default_params", "pssgpu_fragkon_begin", "pssgpu_fragkon_finish", "pssgpu_fragkon_finish_device",
     "pssgpu_kmer_spectrum", "pssgpu_kmer_spectrum_shard", "pssgpu_kmer_spectrum_shard_device",
@@ -158,6 +163,31 @@ def load_library():
     lib.pssgpu_feed.argtypes = [P, P, C.c_size_t, C.c_int]
     lib.pssgpu_feed_device.argtypes = [P, P, C.c_size_t]
     lib.pssgpu_sync.argtypes = [P]
+    lib.pssgpu_feed_async.argtypes = [P, P, C.c_size_t, C.c_int]
+    lib.pssgpu_feed_wait.argtypes = [P]
+    lib.pssgpu_group_init.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(P)]
+    lib.pssgpu_group_destroy.argtypes = [P]
+    lib.pssgpu_group_destroy.restype = None
+    lib.pssgpu_group_size.argtypes = [P]
+    lib.pssgpu_group_ctx.argtypes = [P, C.c_int]
+    lib.pssgpu_group_ctx.restype = P
+    lib.pssgpu_group_last_error.argtypes = [P]
+    lib.pssgpu_group_last_error.restype = C.c_char_p
+    lib.pssgpu_group_reduce_backend.argtypes = [P]
+    lib.pssgpu_group_reduce_backend.restype = C.c_char_p
+    lib.pssgpu_group_last_reduce_ms.argtypes = [P]
+    lib.pssgpu_group_last_reduce_ms.restype = C.c_double
+    lib.pssgpu_group_genome_upload.argtypes = [P, C.POINTER(_Contig), C.c_uint64]
+    lib.pssgpu_group_genome_load_tagged.argtypes = [P, C.c_char_p, C.POINTER(_GenomeTag)]
+    lib.pssgpu_group_pss_begin.argtypes = [P, C.POINTER(_PssParams)]
+    lib.pssgpu_group_fragkon_begin.argtypes = [P, C.POINTER(_FkParams)]
+    lib.pssgpu_group_both_begin.argtypes = [P, C.POINTER(_PssParams), C.POINTER(_FkParams)]
+    lib.pssgpu_group_feed.argtypes = [P, P, C.c_size_t, C.c_int]
+    lib.pssgpu_group_sync.argtypes = [P]
+    lib.pssgpu_group_pss_finish.argtypes = [P, P, P]
+    lib.pssgpu_group_fragkon_finish.argtypes = [P, P, P]
+    lib.pssgpu_group_get_stats.argtypes = [P, C.POINTER(_Stats), C.c_int]
+    lib.pssgpu_group_kmer_spectrum.argtypes = [P, C.c_int, P]
     lib.pssgpu_feed_bam.argtypes = [P, P, C.c_size_t, C.c_int]
     lib.pssgpu_bam_read_group.argtypes = [P, C.c_char_p]
     lib.pssgpu_bam_info.argtypes = [P, C.POINTER(_BamStats)]
@@ -413,3 +443,99 @@ class Context:
         k = int(n.value)
         order = np.argsort(off[:k], kind="stable")
         return off[:k][order], code[:k][order]
+
+
+class Group:
+    """Several GPUs of one box in one process (pssgpu_group_*): reads dealt line-wise to the members, genome replicated,
+    tables summed with NCCL (or peer copies) when they are read."""
+
+    def __init__(self, devices=None):
+        self.lib = load_library()
+        h = C.c_void_p()
+        if devices is None:
+            rc = self.lib.pssgpu_group_init(None, 0, C.byref(h))
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = self.lib.pssgpu_group_init(arr, len(devices), C.byref(h))
+        if rc != 0:
+            raise PssGpuError(rc, self.lib.pssgpu_last_error(None).decode())
+        self.h = h
+        self._R = self._K = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pssgpu_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise PssGpuError(rc, self.lib.pssgpu_group_last_error(self.h).decode())
+
+    @property
+    def size(self):
+        return int(self.lib.pssgpu_group_size(self.h))
+
+    @property
+    def reduce_backend(self):
+        return self.lib.pssgpu_group_reduce_backend(self.h).decode()
+
+    @property
+    def last_reduce_ms(self):
+        return float(self.lib.pssgpu_group_last_reduce_ms(self.h))
+
+    def upload_genome(self, contigs):
+        contigs = list(contigs)
+        arr = (_Contig * max(1, len(contigs)))()
+        keep = []
+        for i, (cid, seq) in enumerate(contigs):
+            cid = cid.encode("latin1") if isinstance(cid, str) else bytes(cid)
+            addr, n, ka = _host_view(seq)
+            keep.append((cid, ka))
+            arr[i] = _Contig(cid, addr, n)
+        self._ck(self.lib.pssgpu_group_genome_upload(self.h, arr, len(contigs)))
+
+    def pss_begin(self, o: PssOptions = PssOptions()):
+        self._up, self._down = bytes(o.up_ctx), bytes(o.down_ctx)
+        p = _PssParams(o.region_len, o.min_len, o.max_len, o.min_mq, self._up, self._down, o.merged_only)
+        self._ck(self.lib.pssgpu_group_pss_begin(self.h, C.byref(p)))
+        self._R = o.region_len
+
+    def fragkon_begin(self, o: FragkonOptions = FragkonOptions()):
+        p = _FkParams(o.klen, o.min_len, o.max_len, o.min_mq, o.merged_only)
+        self._ck(self.lib.pssgpu_group_fragkon_begin(self.h, C.byref(p)))
+        self._K = o.klen
+
+    def feed(self, sam, last=False):
+        addr, n, keep = _host_view(sam)
+        self._ck(self.lib.pssgpu_group_feed(self.h, addr, n, 1 if last else 0))
+        del keep
+
+    def pss_finish(self):
+        R = self._R
+        fwd = np.zeros((R + 2, 16), dtype=np.uint64)
+        rev = np.zeros((R + 2, 16), dtype=np.uint64)
+        self._ck(self.lib.pssgpu_group_pss_finish(self.h, fwd.ctypes.data, rev.ctypes.data))
+        return fwd, rev
+
+    def fragkon_finish(self):
+        nb = 1 << (2 * self._K)
+        fp = np.zeros(nb, dtype=np.uint64)
+        tp = np.zeros(nb, dtype=np.uint64)
+        self._ck(self.lib.pssgpu_group_fragkon_finish(self.h, fp.ctypes.data, tp.ctypes.data))
+        return fp, tp
+
+    def stats(self, fragkon=False):
+        s = _Stats()
+        self._ck(self.lib.pssgpu_group_get_stats(self.h, C.byref(s), 1 if fragkon else 0))
+        return {k: int(getattr(s, k)) for k, _ in _Stats._fields_}
+
+    def kmer_spectrum(self, k: int):
+        counts = np.zeros(1 << (2 * k), dtype=np.uint64)
+        self._ck(self.lib.pssgpu_group_kmer_spectrum(self.h, k, counts.ctypes.data))
+        return counts

@@ -814,6 +814,24 @@ int pssgpu_feed(pssgpu_ctx *ctx, const char *sam, size_t len, int last)
     return PSSGPU_OK;
 }
 
+int pssgpu_feed_async(pssgpu_ctx *ctx, const char *sam, size_t len, int last)
+{
+    if (!ctx || (!sam && len)) return fail(ctx, PSSGPU_EINVAL, "feed_async: null argument");
+    if (ctx->mode < 0) return fail(ctx, PSSGPU_EINVAL, "feed_async: no tally open (call *_begin first)");
+    Bind bind(ctx);
+    const int rc = feed_impl(ctx, sam, len, last);
+    if (rc != PSSGPU_OK) cudaStreamSynchronize(ctx->copy_stream);      // after an error nothing reads `sam` any more
+    return rc;
+}
+
+int pssgpu_feed_wait(pssgpu_ctx *ctx)
+{
+    if (!ctx) return PSSGPU_EINVAL;
+    Bind bind(ctx);
+    CU(cudaStreamSynchronize(ctx->copy_stream));
+    return PSSGPU_OK;
+}
+
 int pssgpu_feed_device(pssgpu_ctx *ctx, const void *d_sam, size_t len)
 {
     if (!ctx || (!d_sam && len)) return fail(ctx, PSSGPU_EINVAL, "feed_device: null argument");

@@ -29,9 +29,9 @@
 namespace pssgpu {
 
 constexpr size_t   kBamCarryCap  = 16ull << 20;   // front of the inflated buffer: header / record carried between batches
-constexpr size_t   kBamBatchComp = 32ull << 20;   // compressed bytes per batch
-constexpr size_t   kBamBatchU    = 160ull << 20;  // inflated bytes per batch
-constexpr uint32_t kBamMaxBlocks = 16384;
+constexpr size_t   kBamBatchCompDefault = 128ull << 20;   // compressed bytes per batch ($PSSGPU_BAM_BATCH_MB): one warp inflates one
+                                                          // ~20 KB block, so a batch must hold several thousand blocks to fill 148 SMs
+constexpr uint32_t kBamMaxBlocks = 32768;
 constexpr uint32_t kBamLocCap    = 2048;          // record starts per block: 65536 / 38 bytes < 1725, + the carried one
 constexpr uint32_t kBamMaxRefs   = 1u << 21;
 constexpr uint32_t kBamNone      = 0xffffffffu;
@@ -67,6 +67,8 @@ struct BamIngest {
     uint8_t  *d_ubuf = nullptr;       // [0, kBamCarryCap) carry, then the inflated batch
     uint8_t  *d_text = nullptr;
     size_t    text_cap = 0;
+    size_t    batch_comp = 0, batch_u = 0;                       // limits of one batch: compressed / inflated bytes
+    uint8_t  *d_comp[2] = { nullptr, nullptr };                  // compressed staging, double buffered
     uint32_t *d_loc = nullptr;        // kBamMaxBlocks x kBamLocCap record starts (offsets in ubuf)
     uint32_t *d_s = nullptr, *d_e = nullptr, *d_n = nullptr;     // per block: guessed start, chain exit, records
     BamDesc  *d_desc[2] = { nullptr, nullptr };
@@ -347,7 +349,7 @@ void bam_destroy(pssgpu_ctx *ctx)
 {
     BamIngest *B = ctx->bam;
     if (!B) return;
-    cudaFree(B->d_state); cudaFree(B->d_ubuf); cudaFree(B->d_text); cudaFree(B->d_loc);
+    cudaFree(B->d_state); cudaFree(B->d_ubuf); cudaFree(B->d_text); cudaFree(B->d_loc); cudaFree(B->d_comp[0]); cudaFree(B->d_comp[1]);
     cudaFree(B->d_s); cudaFree(B->d_e); cudaFree(B->d_n);
     for (int i = 0; i < 2; i++) { cudaFree(B->d_desc[i]); if (B->h_desc[i]) cudaFreeHost(B->h_desc[i]); }
     cudaFree(B->d_hdr); cudaFree(B->d_ref_off); cudaFree(B->d_ref_len); cudaFree(B->d_rg);
@@ -389,9 +391,14 @@ int bam_ensure(pssgpu_ctx *ctx)
     if (!ctx->bam) ctx->bam = new BamIngest();
     BamIngest *B = ctx->bam;
     if (B->d_state) return PSSGPU_OK;
-    B->text_cap = 4 * kBamBatchU + (64ull << 20);
+    size_t mb = kBamBatchCompDefault >> 20;
+    if (const char *e = getenv("PSSGPU_BAM_BATCH_MB")) mb = std::min<size_t>(std::max<size_t>(1, strtoull(e, nullptr, 10)), 512);
+    B->batch_comp = mb << 20;
+    B->batch_u = 6 * B->batch_comp;                        // a batch also closes when its inflated size reaches this
+    B->text_cap = 3 * B->batch_u + (64ull << 20);          // lines are ~1.3 x the record bytes; beyond the cap: error, never silence
     CU(cudaMalloc(&B->d_state, sizeof(BamState)));
-    CU(cudaMalloc(&B->d_ubuf, kBamCarryCap + kBamBatchU + (1u << 20)));
+    CU(cudaMalloc(&B->d_ubuf, kBamCarryCap + B->batch_u + (1u << 20)));
+    for (int i = 0; i < 2; i++) CU(cudaMalloc(&B->d_comp[i], B->batch_comp + (128u << 10)));
     CU(cudaMalloc(&B->d_text, B->text_cap + 4096));
     CU(cudaMalloc(&B->d_loc, (size_t)kBamMaxBlocks * kBamLocCap * sizeof(uint32_t)));
     CU(cudaMalloc(&B->d_s, kBamMaxBlocks * sizeof(uint32_t)));
@@ -419,8 +426,6 @@ int bam_ensure(pssgpu_ctx *ctx)
     z.entry = kBamCarryCap;
     CU(cudaMemcpy(B->d_state, &z, sizeof z, cudaMemcpyHostToDevice));
     CU(cudaMemset(B->d_ubuf, 0, kBamCarryCap));
-    for (int s = 0; s < 2; s++)
-        if (!ctx->d_stage[s]) CU(cudaMalloc(&ctx->d_stage[s], kStageCap + 64));
     return PSSGPU_OK;
 }
 
@@ -460,7 +465,7 @@ int bam_submit(pssgpu_ctx *ctx, const uint8_t *src, size_t comp_len, uint32_t n_
     BamIngest *B = ctx->bam;
     const int  cur = ctx->cur;
     if (n_blocks) {
-        CU(cudaMemcpyAsync(ctx->d_stage[cur], src, comp_len, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CU(cudaMemcpyAsync(B->d_comp[cur], src, comp_len, cudaMemcpyHostToDevice, ctx->copy_stream));
         CU(cudaMemcpyAsync(B->d_desc[cur], B->h_desc[cur], n_blocks * sizeof(BamDesc), cudaMemcpyHostToDevice, ctx->copy_stream));
         ctx->h2d_bytes += comp_len;
     }
@@ -474,9 +479,9 @@ int bam_submit(pssgpu_ctx *ctx, const uint8_t *src, size_t comp_len, uint32_t n_
         const unsigned grid = (unsigned)std::min<uint64_t>((n_blocks + kInfWarps - 1) / kInfWarps, (uint64_t)B->inflate_grid);
         time_begin(ctx, comp_len);
         if (B->inflate_minb == 2)
-            bgzf_inflate_kernel<2><<<grid, kInfWarps * 32, smem, st>>>(B->d_desc[cur], n_blocks, ctx->d_stage[cur], B->d_ubuf + kBamCarryCap, S);
+            bgzf_inflate_kernel<2><<<grid, kInfWarps * 32, smem, st>>>(B->d_desc[cur], n_blocks, B->d_comp[cur], B->d_ubuf + kBamCarryCap, S);
         else
-            bgzf_inflate_kernel<3><<<grid, kInfWarps * 32, smem, st>>>(B->d_desc[cur], n_blocks, ctx->d_stage[cur], B->d_ubuf + kBamCarryCap, S);
+            bgzf_inflate_kernel<3><<<grid, kInfWarps * 32, smem, st>>>(B->d_desc[cur], n_blocks, B->d_comp[cur], B->d_ubuf + kBamCarryCap, S);
         time_end(ctx);
     }
     bam_prepare_kernel<<<1, 32, 0, st>>>(S, B->d_ubuf, total_u, B->d_hdr, B->d_ref_off, B->d_ref_len);
@@ -496,7 +501,7 @@ int bam_submit(pssgpu_ctx *ctx, const uint8_t *src, size_t comp_len, uint32_t n_
     CU(cudaGetLastError());
     if (n_blocks) {
         // the text of this batch: at most text_cap bytes, the real length is in the device state
-        const size_t bound = std::min<size_t>(B->text_cap, (size_t)(total_u + kBamCarryCap) * 2 + (1u << 20));
+        const size_t bound = std::min<size_t>(B->text_cap, (size_t)(total_u + (1u << 20)) * 3 / 2);
         int rc = launch_tally_mode(ctx, B->d_text, bound, ctx->fed_bytes, &S->text_len);
         if (rc != PSSGPU_OK) return rc;
     }
@@ -561,7 +566,7 @@ int feed_bam_impl(pssgpu_ctx *ctx, const uint8_t *data, size_t len, int last)
             int fr = bgzf_frame(data + off, len - off, &total, &po, &pl, &isz);
             if (fr < 0) return fail(ctx, PSSGPU_EINVAL, "feed_bam: not a BGZF block (at byte %llu)", (unsigned long long)(ctx->fed_bytes + off));
             if (fr == 0) { more = false; break; }
-            if ((off - start) + total > kBamBatchComp || total_u + isz > kBamBatchU) break;
+            if ((off - start) + total > B->batch_comp || total_u + isz > B->batch_u) break;
             desc[n_blocks++] = BamDesc{ (uint32_t)(off - start) + po, pl, (uint32_t)total_u, isz };
             total_u += isz;
             off += total;

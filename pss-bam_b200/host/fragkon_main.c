@@ -64,21 +64,21 @@ int main(int argc, char *argv[])
     if (par.klen & 1)
         fprintf(stderr, "    *** k is odd - counting %d bases outside %d bases inside of alignment.\n", par.klen / 2, par.klen / 2 + 1);
 
-    pssgpu_ctx *gpu = pss_open_device();
+    pssgpu_group *gpu = pss_open_devices();
     fprintf(stderr, "Reading genome sequence from: %s\n", fasta_fn);
-    pss_resident_genome(gpu, fasta_fn, NULL);
+    pss_resident_genome_group(gpu, fasta_fn, NULL);
     fprintf(stderr, "Finished loading genome.\nCounting kmer contexts for: %s\n", bam_fn);
 
-    if (pssgpu_fragkon_begin(gpu, &par) != PSSGPU_OK) pss_die(gpu, "fragkon_begin");
-    if (pss_stream_input(gpu, bam_fn, NULL) != PSSGPU_OK) pss_die(gpu, "tally");
+    if (pssgpu_group_fragkon_begin(gpu, &par) != PSSGPU_OK) pss_die_group(gpu, "fragkon_begin");
+    if (pss_stream_input_group(gpu, bam_fn, NULL) != PSSGPU_OK) pss_die_group(gpu, "tally");
 
     const size_t bins = (size_t)1 << (2 * par.klen);
     uint64_t *fp = (uint64_t *)calloc(bins, sizeof *fp), *tp = (uint64_t *)calloc(bins, sizeof *tp);
-    if (pssgpu_fragkon_finish(gpu, fp, tp) != PSSGPU_OK) pss_die(gpu, "fragkon_finish");
+    if (pssgpu_group_fragkon_finish(gpu, fp, tp) != PSSGPU_OK) pss_die_group(gpu, "fragkon_finish");
     pss_write_fragkon(stdout, fasta_fn, bam_fn, par.klen, fp, tp);
 
     free(fp); free(tp);
-    pssgpu_destroy(gpu);
+    pssgpu_group_destroy(gpu);
     fprintf(stderr, "Done.\n");
     return 0;
 }

@@ -36,16 +36,20 @@ int main(int argc, char *argv[])
     }
     if (!fa_in || !*fa_in) help();
 
-    pssgpu_ctx *gpu = pss_open_device();
+    pssgpu_group *gpu = pss_open_devices();
     unsigned long n_seqs = 0;
-    pss_resident_genome(gpu, fa_in, &n_seqs);
+    pss_resident_genome_group(gpu, fa_in, &n_seqs);
     if (k < 1 || k > 14) { fprintf(stderr, "ERROR: k must be in [1,14] on this build\n"); return 1; }
 
     const size_t bins = (size_t)1 << (2 * k);
     uint64_t *counts = (uint64_t *)calloc(bins, sizeof *counts);
-    if (pssgpu_kmer_spectrum(gpu, k, counts) != PSSGPU_OK) pss_die(gpu, "kmer_spectrum");
+    /* one GPU: the whole genome; several: GPU i counts slice i, the 4^k counters are summed over NVLink */
+    if (pssgpu_group_kmer_spectrum(gpu, k, counts) != PSSGPU_OK) pss_die_group(gpu, "kmer_spectrum");
+    if (getenv("PSSGPU_VERBOSE") && pssgpu_group_size(gpu) > 1)
+        fprintf(stderr, "spectrum summed over %d GPUs (%s) in %.3f ms\n", pssgpu_group_size(gpu), pssgpu_group_reduce_backend(gpu),
+                pssgpu_group_last_reduce_ms(gpu));
     pss_write_spectrum(stdout, n_seqs, k, counts);
     free(counts);
-    pssgpu_destroy(gpu);
+    pssgpu_group_destroy(gpu);
     exit(0);
 }

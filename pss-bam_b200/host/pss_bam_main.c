@@ -75,21 +75,21 @@ int main(int argc, char *argv[])
     if (read_group) fprintf(stderr, " -R %s", read_group);
     fprintf(stderr, " -U %s -D %s%s\n", par.up_ctx, par.down_ctx, par.merged_only ? " -m" : "");
 
-    pssgpu_ctx *gpu = pss_open_device();
+    pssgpu_group *gpu = pss_open_devices();
 
     fprintf(stderr, "Reading genome sequence from:\n%s\n", fasta_fn);
-    pss_resident_genome(gpu, fasta_fn, NULL);
+    pss_resident_genome_group(gpu, fasta_fn, NULL);
     fprintf(stderr, "Finished loading genome.\nCounting matches/mismatches from:\n%s\n", bam_fn);
 
-    if (pssgpu_pss_begin(gpu, &par) != PSSGPU_OK) pss_die(gpu, "pss_begin");
-    if (pss_stream_input(gpu, bam_fn, read_group) != PSSGPU_OK) pss_die(gpu, "tally");
+    if (pssgpu_group_pss_begin(gpu, &par) != PSSGPU_OK) pss_die_group(gpu, "pss_begin");
+    if (pss_stream_input_group(gpu, bam_fn, read_group) != PSSGPU_OK) pss_die_group(gpu, "tally");
 
     const int    R = par.region_len;
     const size_t cells = (size_t)(R + 2) * 16;
     uint64_t *fwd = (uint64_t *)calloc(cells, sizeof *fwd), *rev = (uint64_t *)calloc(cells, sizeof *rev);
     double   *fwd_rates = (double *)calloc((size_t)(R > 0 ? R : 1) * 12, sizeof(double));
     double   *rev_rates = (double *)calloc((size_t)(R > 0 ? R : 1) * 12, sizeof(double));
-    if (pssgpu_pss_finish(gpu, fwd, rev) != PSSGPU_OK) pss_die(gpu, "pss_finish");
+    if (pssgpu_group_pss_finish(gpu, fwd, rev) != PSSGPU_OK) pss_die_group(gpu, "pss_finish");
     pss_sub_rates(fwd, R, fwd_rates);
     pss_sub_rates(rev, R, rev_rates);
     int rc = pss_write_counts(fasta_fn, bam_fn, out_prefix, fwd, rev, R);
@@ -97,13 +97,13 @@ int main(int argc, char *argv[])
 
     if (getenv("PSSGPU_VERBOSE")) {
         pssgpu_stats st;
-        if (pssgpu_get_stats(gpu, &st) == PSSGPU_OK)
+        if (pssgpu_group_get_stats(gpu, &st, 0) == PSSGPU_OK)
             fprintf(stderr, "lines %llu counted %llu no_contig %llu filtered %llu unparsable %llu undefined %llu\n",
                     (unsigned long long)st.lines, (unsigned long long)st.counted, (unsigned long long)st.no_contig,
                     (unsigned long long)st.filtered, (unsigned long long)st.parse_fail, (unsigned long long)st.undefined);
     }
     free(fwd); free(rev); free(fwd_rates); free(rev_rates);
-    pssgpu_destroy(gpu);
+    pssgpu_group_destroy(gpu);
     fprintf(stderr, "Done.\n");
     return rc;
 }

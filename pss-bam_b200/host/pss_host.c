@@ -17,6 +17,40 @@ void pss_die(pssgpu_ctx *ctx, const char *what)
     exit(1);
 }
 
+void pss_die_group(pssgpu_group *g, const char *what)
+{
+    fprintf(stderr, "ERROR: %s: %s\n", what, pssgpu_group_last_error(g));
+    exit(1);
+}
+
+pssgpu_group *pss_open_devices(void)
+{
+    /* $PSSGPU_DEVICES: "all", or a comma separated list of CUDA device numbers; unset: $PSSGPU_DEVICE or device 0 */
+    const char *list = getenv("PSSGPU_DEVICES"), *one = getenv("PSSGPU_DEVICE");
+    int dev[64], n = 0;
+    pssgpu_group *g = NULL;
+    if (list && *list && strcmp(list, "all") != 0) {
+        const char *p = list;
+        while (*p && n < 64) {
+            char *end;
+            long v = strtol(p, &end, 10);
+            if (end == p) { fprintf(stderr, "ERROR: cannot read PSSGPU_DEVICES=%s\n", list); exit(1); }
+            dev[n++] = (int)v;
+            p = *end == ',' ? end + 1 : end;
+            if (*end && *end != ',') { fprintf(stderr, "ERROR: cannot read PSSGPU_DEVICES=%s\n", list); exit(1); }
+        }
+    } else if (!(list && *list)) {
+        dev[n++] = one ? atoi(one) : 0;
+    }
+    if (pssgpu_group_init(n ? dev : NULL, n, &g) != PSSGPU_OK) {
+        fprintf(stderr, "ERROR: no usable B200: %s\n(this build has no CPU path)\n", pssgpu_last_error(NULL));
+        exit(1);
+    }
+    if (pssgpu_group_size(g) > 1)
+        fprintf(stderr, "Using %d GPUs; tables are summed with: %s\n", pssgpu_group_size(g), pssgpu_group_reduce_backend(g));
+    return g;
+}
+
 pssgpu_ctx *pss_open_device(void)
 {
     const char *env = getenv("PSSGPU_DEVICE");
@@ -94,6 +128,49 @@ void pss_resident_genome(pssgpu_ctx *ctx, const char *fasta_fn, unsigned long *n
     destroy_genome(genome);
     if (cache[0] && pssgpu_genome_save_tagged(ctx, cache, &tag) != PSSGPU_OK)
         fprintf(stderr, "WARNING: could not write genome cache %s: %s\n", cache, pssgpu_last_error(ctx));
+}
+
+void pss_resident_genome_group(pssgpu_group *g, const char *fasta_fn, unsigned long *n_seqs)
+{
+    const int n = pssgpu_group_size(g);
+    const char *env = getenv("PSSGPU_GENOME_CACHE");
+    char        cache[2 * MAX_FN_LEN + 64];
+    pssgpu_genome_tag tag;
+    if (n == 1) { pss_resident_genome(pssgpu_group_ctx(g, 0), fasta_fn, n_seqs); return; }
+    cache[0] = 0;
+    if (env && *env && fasta_tag(fasta_fn, &tag) == 0) {
+        if (strcmp(env, "1") == 0) snprintf(cache, sizeof cache, "%s.pssgpu", fasta_fn);
+        else {
+            const char *base = strrchr(fasta_fn, '/');
+            snprintf(cache, sizeof cache, "%s/%s.%016llx.pssgpu", env, base ? base + 1 : fasta_fn,
+                     (unsigned long long)tag.source_path_hash);
+        }
+        if (access(cache, R_OK) == 0) {
+            uint64_t nc = 0;
+            if (pssgpu_group_genome_load_tagged(g, cache, &tag) == PSSGPU_OK &&
+                pssgpu_genome_info(pssgpu_group_ctx(g, 0), &nc, NULL, NULL) == PSSGPU_OK) {
+                if (n_seqs) *n_seqs = (unsigned long)nc;
+                return;
+            }
+            fprintf(stderr, "WARNING: ignoring genome cache %s: %s\n", cache, pssgpu_group_last_error(g));
+        }
+    }
+    Genome *genome = init_genome(fasta_fn);
+    if (!genome) { fprintf(stderr, "ERROR: cannot read %s\n", fasta_fn); exit(1); }
+    {
+        pssgpu_contig *c = (pssgpu_contig *)malloc((genome->n_seqs ? genome->n_seqs : 1) * sizeof *c);
+        for (size_t i = 0; i < genome->n_seqs; i++) {
+            c[i].id = genome->seqs[i]->id;
+            c[i].seq = genome->seqs[i]->seq;
+            c[i].len = genome->seqs[i]->len;
+        }
+        if (pssgpu_group_genome_upload(g, c, genome->n_seqs) != PSSGPU_OK) pss_die_group(g, "genome upload");
+        free(c);
+    }
+    if (n_seqs) *n_seqs = (unsigned long)genome->n_seqs;
+    destroy_genome(genome);
+    if (cache[0] && pssgpu_genome_save_tagged(pssgpu_group_ctx(g, 0), cache, &tag) != PSSGPU_OK)
+        fprintf(stderr, "WARNING: could not write genome cache %s: %s\n", cache, pssgpu_last_error(pssgpu_group_ctx(g, 0)));
 }
 
 FILE *pss_bam_to_sam(const char *bam_fn, const char *read_group)
@@ -215,5 +292,86 @@ static int pump_run(pssgpu_ctx *ctx, FILE *sam, int as_bam)
     pthread_cond_destroy(&p.cv);
     pssgpu_host_free(p.buf[0]);
     pssgpu_host_free(p.buf[1]);
+    return rc;
+}
+
+/* SAM text to the members of a group: whole lines, chunk by chunk in turn.  Every GPU has two pinned buffers; a chunk
+ * is read straight into one of them (behind the unfinished line left over from the previous chunk), cut after its
+ * last newline and handed to pssgpu_feed_async, which does not wait for the copy -- so the PCIe links of all GPUs work
+ * at once while this thread reads on.  A buffer is reused two rounds later, after pssgpu_feed_wait on its GPU. */
+static int deal_sam(pssgpu_group *g, FILE *in)
+{
+    const int n = pssgpu_group_size(g);
+    char    **buf = (char **)calloc((size_t)2 * n, sizeof *buf);
+    char     *carry = (char *)malloc(PSS_PIPE_CHUNK);
+    size_t    carry_len = 0, k = 0;
+    int       rc = PSSGPU_OK, single = -1;          /* single >= 0: a line longer than a chunk -- the rest goes to that GPU */
+    for (int i = 0; i < 2 * n; i++) {
+        buf[i] = (char *)pssgpu_host_alloc(PSS_PIPE_CHUNK);
+        if (!buf[i]) rc = PSSGPU_ENOMEM;
+    }
+    while (rc == PSSGPU_OK) {
+        const int   gpu = single >= 0 ? single : (int)(k % (size_t)n), slot = (int)((k / (size_t)n) & 1u);
+        pssgpu_ctx *c = pssgpu_group_ctx(g, gpu);
+        char       *b = buf[2 * gpu + slot];
+        if (k >= (size_t)2 * n || single >= 0) rc = pssgpu_feed_wait(c);
+        if (rc != PSSGPU_OK) break;
+        memcpy(b, carry, carry_len);
+        const size_t got = fread(b + carry_len, 1, PSS_PIPE_CHUNK - carry_len, in);
+        const size_t total = carry_len + got;
+        if (got == 0) {
+            if (total) rc = pssgpu_feed_async(c, b, total, 1);          /* a last line without a newline */
+            break;
+        }
+        if (single >= 0) {                          /* the member's own carry logic takes partial lines */
+            rc = pssgpu_feed_async(c, b, total, 0);
+            carry_len = 0;
+            k++;
+            continue;
+        }
+        char *nl = (char *)memrchr(b, '\n', total);
+        if (!nl) {
+            if (total < PSS_PIPE_CHUNK) { memcpy(carry, b, total); carry_len = total; continue; }   /* short read: keep reading */
+            single = gpu;
+            rc = pssgpu_feed_async(c, b, total, 0);
+            carry_len = 0;
+            k++;
+            continue;
+        }
+        const size_t cut = (size_t)(nl - b) + 1;
+        carry_len = total - cut;
+        memcpy(carry, b + cut, carry_len);
+        rc = pssgpu_feed_async(c, b, cut, 0);
+        k++;
+    }
+    for (int i = 0; i < n; i++) {
+        pssgpu_ctx *c = pssgpu_group_ctx(g, i);
+        int r2 = pssgpu_feed_wait(c);
+        if (r2 == PSSGPU_OK && single == i) r2 = pssgpu_feed(c, buf[0], 0, 1);       /* flush that member's carried line */
+        if (r2 == PSSGPU_OK) r2 = pssgpu_sync(c);
+        if (rc == PSSGPU_OK && r2 != PSSGPU_OK) { rc = r2; fprintf(stderr, "ERROR: GPU member %d: %s\n", i, pssgpu_last_error(c)); }
+    }
+    for (int i = 0; i < 2 * n; i++) pssgpu_host_free(buf[i]);
+    free(buf);
+    free(carry);
+    return rc;
+}
+
+int pss_stream_input_group(pssgpu_group *g, const char *bam_fn, const char *read_group)
+{
+    const int n = pssgpu_group_size(g);
+    int rc;
+    if (n == 1) return pss_stream_input(pssgpu_group_ctx(g, 0), bam_fn, read_group);
+    if (pss_is_bgzf(bam_fn) && !getenv("PSSGPU_USE_SAMTOOLS")) {
+        /* BAM records run across BGZF blocks and carry no sync marks: the byte stream of one file cannot be dealt to
+         * several GPUs without decoding it.  It is decoded -- and tallied -- on the first member; the others add zeros. */
+        fprintf(stderr, "Note: a BAM file is decoded on one GPU (device member 0 of %d).\n", n);
+        return pss_stream_input(pssgpu_group_ctx(g, 0), bam_fn, read_group);
+    }
+    {
+        FILE *sam = pss_bam_to_sam(bam_fn, read_group);
+        rc = deal_sam(g, sam);
+        pclose(sam);
+    }
     return rc;
 }

@@ -29,4 +29,11 @@ int pss_stream_input(pssgpu_ctx *ctx, const char *bam_fn, const char *read_group
 int pss_is_bgzf(const char *fn);
 void pss_die(pssgpu_ctx *ctx, const char *what);
 
+/* ---- several GPUs ($PSSGPU_DEVICES = "all" | "0,1,..."; unset: one GPU, $PSSGPU_DEVICE or 0) ---- */
+pssgpu_group *pss_open_devices(void);
+void pss_resident_genome_group(pssgpu_group *g, const char *fasta_fn, unsigned long *n_seqs);
+/* SAM text is dealt to the members line-wise, chunk by chunk (reads shard); a BAM file goes to member 0. */
+int  pss_stream_input_group(pssgpu_group *g, const char *bam_fn, const char *read_group);
+void pss_die_group(pssgpu_group *g, const char *what);
+
 #endif

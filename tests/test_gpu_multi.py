@@ -28,3 +28,83 @@ def test_nccl_sharded_equals_single_gpu_and_oracle(world):
     sys.stdout.write(r.stdout[-3000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "MISMATCH" not in r.stdout and "spectrum k=12 == oracle: ok" in r.stdout
+
+
+def _group_case(devices, env_extra):
+    """Python Group + the three CLIs over `devices`, against the oracle / the golden files."""
+    import importlib
+    import json
+    import numpy as np
+    from pss_testlib import FkParams, Oracle, PssParams, Synth, reads_cfg_config2, tmpdir
+    os.environ.update(env_extra)
+    try:
+        pkg = importlib.import_module("pss-bam_b200")
+        g = Synth.genome(93, [900_000, 400_000, 77_777], n_frac=0.01, lower_frac=0.03)
+        ora = Oracle(fasta=g.fasta_bytes())
+        sam = Synth.sam(reads_cfg_config2(seed=94), g, 0, 120_000)
+        grp = pkg.Group(devices)
+        assert grp.size == len(devices)
+        grp.upload_genome(ora.contigs())
+        lines = sam.split(b"\n")[:-1]
+        f, r, st = ora.pss(sam, PssParams())
+        grp.pss_begin(pkg.PssOptions())
+        for i in range(0, len(lines), 7001):                   # pieces of whole lines, dealt in turn
+            grp.feed(b"\n".join(lines[i:i + 7001]) + b"\n")
+        gf, gr = grp.pss_finish()
+        assert grp.stats() == st and np.array_equal(gf, f) and np.array_equal(gr, r)
+        fp, tp, fst = ora.fragkon(sam, FkParams(klen=8))
+        grp.fragkon_begin(pkg.FragkonOptions(klen=8))
+        for i in range(0, len(lines), 9973):
+            grp.feed(b"\n".join(lines[i:i + 9973]) + b"\n")
+        gfp, gtp = grp.fragkon_finish()
+        assert grp.stats() == fst and np.array_equal(gfp, fp) and np.array_equal(gtp, tp)
+        for k in (4, 8, 12):                                  # genome-sharded spectrum + sum of the 4^k counters
+            assert np.array_equal(grp.kmer_spectrum(k), ora.kmer_spectrum(k)), k
+        backend = grp.reduce_backend
+        grp.close()
+    finally:
+        for k in env_extra:
+            os.environ.pop(k, None)
+    # the host programs with $PSSGPU_DEVICES: byte-identical golden outputs
+    gold = os.path.join(ROOT, "tests", "golden", "v1")
+    man = json.load(open(os.path.join(gold, "manifest.json")))
+    bindir = os.path.join(ROOT, "pss-bam_b200", "bin")
+    subprocess.run(["make", "-C", os.path.join(ROOT, "pss-bam_b200", "host")], check=True, capture_output=True)
+    d = tmpdir()
+    shim = os.path.join(d, "samtools")
+    with open(os.path.join(ROOT, "oracle", "samtools_shim.sh")) as fi, open(shim, "w") as fo:
+        fo.write(fi.read())
+    os.chmod(shim, 0o755)
+    e = dict(os.environ, PATH=d + os.pathsep + os.environ.get("PATH", ""), PSSGPU_DEVICES=",".join(str(x) for x in devices), **env_extra)
+    for fn in [man["fasta"], *man["sams"].values()]:
+        os.symlink(os.path.join(gold, fn), os.path.join(d, fn))
+    rd = lambda name: open(os.path.join(gold, name), "rb").read()
+    for case in man["pss"][:5]:
+        rr = subprocess.run([os.path.join(bindir, "pss-bam"), "-F", "genome.fa", "-B", case["sam"] + ".sam", "-o", "out", *case["args"]],
+                            cwd=d, env=e, capture_output=True)
+        assert rr.returncode == 0, rr.stderr[-2000:]
+        assert open(os.path.join(d, "out.pss.counts.txt"), "rb").read() == rd(case["counts"])
+        assert open(os.path.join(d, "out.pss.rates.txt"), "rb").read() == rd(case["rates"])
+    for case in [c for c in man["fragkon"] if not c["sparse"]][:3]:
+        rr = subprocess.run([os.path.join(bindir, "fragkon"), "-F", "genome.fa", "-B", case["sam"] + ".sam", *case["args"]],
+                            cwd=d, env=e, capture_output=True)
+        assert rr.returncode == 0 and rr.stdout == rd(case["out"]), rr.stderr[-2000:]
+    for case in man["gkc"]:
+        rr = subprocess.run([os.path.join(bindir, "genome-kmer-count"), "-f", "genome.fa", "-k", str(case["k"])], cwd=d, env=e, capture_output=True)
+        assert rr.returncode == 0 and rr.stdout == rd(case["out"]), rr.stderr[-2000:]
+    return backend
+
+
+def test_group_of_member_contexts_on_one_gpu():
+    """The group code path -- dealing, per-member tallies, the sum (peer copies + add kernel), genome-sharded spectrum,
+    the CLIs with $PSSGPU_DEVICES -- with three member contexts on GPU 0 (PSSGPU_GROUP_ALLOW_DUP), so that a one-GPU
+    box covers it too."""
+    assert "peer" in _group_case([0, 0, 0], {"PSSGPU_GROUP_ALLOW_DUP": "1"})
+
+
+@pytest.mark.parametrize("reduce", ["nccl", "peer"])
+def test_group_on_two_gpus(reduce):
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    backend = _group_case([0, 1], {"PSSGPU_GROUP_REDUCE": reduce} if reduce == "peer" else {})
+    assert (reduce in backend) or reduce == "nccl"          # (without libnccl.so.2 the peer path takes over)
