@@ -357,6 +357,7 @@ def main_b200(a):
     ctx.upload_genome(list(zip(g.names, g.seqs)))
     ginfo = ctx.genome_info()
     t_genome = time.perf_counter() - t0
+    bam_refs = list(zip(g.names, g.lens)) + [("chrUn_synthetic_decoy", 1000)]      # the @SQ dictionary of the BAM variant
     cfg = reads_cfg_config2(seed=READS_SEED)
     n_reads = reads_per_rank(a, world)
     lo, hi = rank * n_reads, (rank + 1) * n_reads
@@ -435,7 +436,11 @@ def main_b200(a):
     ctx.timing_reset(False)
     check_tables = tables_host.clone()
 
+    # ---- end to end through the C ABI with HOST buffers, copies inside the timed region.  Two inputs: the SAM text
+    #      `samtools view` would have piped (pssgpu_feed) and the BAM file itself (pssgpu_feed_bam: BGZF inflate + BAM
+    #      decoding on the device) -- the reference's real input is the BAM (pss-bam.c:148-162).
     e2e = None
+    e2e_variants = {}
     if not a.no_e2e and host_has_all:
         e2e_steps = max(1, min(a.steps, 5))
         step_e2e()
@@ -443,10 +448,45 @@ def main_b200(a):
         ms_e2e = timed(step_e2e, e2e_steps)
         assert torch.equal(tables_host, check_tables), "host-fed and device-resident tallies differ"
         tm2 = ctx.timing()
-        e2e = {"value": world * n_reads * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": int(n_bytes), "d2h_bytes_per_step": int(tables_host.numel() * 8),
-               "ms_per_step": ms_e2e / e2e_steps, "sam_gb_per_s": n_bytes * world * e2e_steps / (ms_e2e * 1e-3) / 1e9,
-               "launches_per_step": int(tm2["launches"] // e2e_steps) if tm2["launches"] else None}
+        e2e_variants["sam_text"] = {
+            "value": world * n_reads * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT, "input": "SAM text in pinned host memory (pssgpu_feed)",
+            "h2d_bytes_per_step": int(n_bytes), "d2h_bytes_per_step": int(tables_host.numel() * 8),
+            "ms_per_step": ms_e2e / e2e_steps, "host_gb_per_s": n_bytes * world * e2e_steps / (ms_e2e * 1e-3) / 1e9,
+            "launches_per_step": int(tm2["launches"] // e2e_steps) if tm2["launches"] else None}
+        try:
+            refs = bam_refs
+            bcap = Synth.lib().synth_bam_bound(n_bytes, len(refs))
+            hbam = torch.empty(bcap, dtype=torch.uint8, pin_memory=True)
+            tb = time.perf_counter()
+            n_bam = Synth.bam_into(host.data_ptr(), n_bytes, refs, hbam.data_ptr(), bcap, level=6, qual_mode=1)
+            t_bam = time.perf_counter() - tb
+
+            def step_e2e_bam():
+                ctx.pss_begin(opts)
+                ctx.feed_bam_ptr(hbam.data_ptr(), n_bam, last=True)     # H2D of the compressed file + inflate + decode + tally
+                ctx.pss_finish_device(tables.data_ptr())
+                if world > 1:
+                    dist.all_reduce(tables)
+                tables_host.copy_(tables)
+                torch.cuda.synchronize()
+            step_e2e_bam()
+            ctx.timing_reset(False)
+            ms_bam = timed(step_e2e_bam, e2e_steps)
+            assert torch.equal(tables_host, check_tables), "BAM-fed and device-resident tallies differ"
+            tm3 = ctx.timing()
+            e2e_variants["bam"] = {
+                "value": world * n_reads * e2e_steps / (ms_bam * 1e-3), "unit": UNIT,
+                "input": "the same alignments as a BAM file (BGZF, zlib level 6, binned qualities) in pinned host memory (pssgpu_feed_bam)",
+                "h2d_bytes_per_step": int(n_bam), "d2h_bytes_per_step": int(tables_host.numel() * 8),
+                "ms_per_step": ms_bam / e2e_steps, "host_gb_per_s": n_bam * world * e2e_steps / (ms_bam * 1e-3) / 1e9,
+                "launches_per_step": int(tm3["launches"] // e2e_steps) if tm3["launches"] else None,
+                "bam_bytes_per_read": n_bam / n_reads, "bam_conversion_s": t_bam, "info": ctx.bam_info()}
+            del hbam
+        except Exception as ex:                                     # the text path stays the end-to-end number
+            e2e_variants["bam"] = {"error": f"{type(ex).__name__}: {ex}"}
+        best = max((v for v in e2e_variants.values() if "value" in v), key=lambda v: v["value"])
+        e2e = dict(best)
+        e2e["variants"] = e2e_variants
 
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):

@@ -161,13 +161,13 @@ PSS_HD void bam_put_i64(Sink &s, int64_t v)
     else bam_put_u32(s, (uint32_t)v);
 }
 
-// One record -> one line.  r points at block_size.  c must be bam_wellformed().
+// One record -> one line, in two parts (the render kernel writes the second one with all lanes of a warp).
+// r points at block_size.  c must be bam_wellformed().
+//   head: QNAME .. TLEN and the tab behind it        tail: SEQ, tab, QUAL, newline
 template <class Sink>
-PSS_HD void bam_render(const uint8_t *r, const BamCore &c, const BamRefs &R, Sink &s)
+PSS_HD void bam_render_head(const uint8_t *r, const BamCore &c, const BamRefs &R, Sink &s)
 {
     const uint8_t *cig = r + 4 + kBamFixed + c.l_read_name;
-    const uint8_t *seq = cig + 4ull * c.n_cigar;
-    const uint8_t *qual = seq + ((c.l_seq + 1u) >> 1);
     s.put('q'); s.put('\t');
     bam_put_u32(s, c.flag); s.put('\t');
     if (c.ref_id >= 0 && c.ref_id < R.n_ref) {
@@ -189,18 +189,31 @@ PSS_HD void bam_render(const uint8_t *r, const BamCore &c, const BamRefs &R, Sin
     }
     s.put('\t'); s.put('*'); s.put('\t'); s.put('0'); s.put('\t');
     bam_put_i64(s, (int64_t)c.tlen); s.put('\t');
-    if (c.l_seq == 0) {
-        s.put('*'); s.put('\t'); s.put('*');
-    } else {
-        for (uint32_t i = 0; i < c.l_seq; i++) {
-            const uint32_t b = seq[i >> 1];
-            s.put((uint8_t)"=ACMGRSVTWYHKDBN"[(i & 1u) ? (b & 15u) : (b >> 4)]);
-        }
-        s.put('\t');
-        if (qual[0] == 0xffu) s.put('*');
-        else s.fill('I', c.l_seq);
+}
+PSS_HD const uint8_t *bam_seq_ptr(const uint8_t *r, const BamCore &c) { return r + 4 + kBamFixed + c.l_read_name + 4ull * c.n_cigar; }
+// byte k of the tail (0 <= k < bam_tail_len): what the cooperative writer of the render kernel stores, lane by lane
+PSS_HD uint32_t bam_tail_len(const BamCore &c, bool qual_star) { return c.l_seq == 0 ? 4u : c.l_seq + 1u + (qual_star ? 1u : c.l_seq) + 1u; }
+PSS_HD bool bam_qual_is_star(const uint8_t *r, const BamCore &c) { return c.l_seq == 0 || bam_seq_ptr(r, c)[(c.l_seq + 1u) >> 1] == 0xffu; }
+PSS_HD uint8_t bam_tail_byte(const uint8_t *seq, const BamCore &c, bool qual_star, uint32_t k)
+{
+    if (c.l_seq == 0) return (uint8_t)"*\t*\n"[k];
+    if (k < c.l_seq) {
+        const uint32_t b = seq[k >> 1];
+        return (uint8_t)"=ACMGRSVTWYHKDBN"[(k & 1u) ? (b & 15u) : (b >> 4)];
     }
-    s.put('\n');
+    if (k == c.l_seq) return (uint8_t)'\t';
+    const uint32_t q = k - c.l_seq - 1u, ql = qual_star ? 1u : c.l_seq;
+    if (q < ql) return qual_star ? (uint8_t)'*' : (uint8_t)'I';
+    return (uint8_t)'\n';
+}
+template <class Sink>
+PSS_HD void bam_render(const uint8_t *r, const BamCore &c, const BamRefs &R, Sink &s)
+{
+    bam_render_head(r, c, R, s);
+    const uint8_t *seq = bam_seq_ptr(r, c);
+    const bool     qs = bam_qual_is_star(r, c);
+    const uint32_t n = bam_tail_len(c, qs);
+    for (uint32_t k = 0; k < n; k++) s.put(bam_tail_byte(seq, c, qs, k));
 }
 
 }  // namespace pssgpu

@@ -25,8 +25,10 @@
 
 #if defined(__CUDACC__)
 #define PSS_IHD __host__ __device__ __forceinline__
+#define PSS_IHD_COLD __host__ __device__ __noinline__      // set-up and rare paths: kept out of the symbol loop's register budget
 #else
 #define PSS_IHD inline
+#define PSS_IHD_COLD inline
 #endif
 
 namespace pssgpu {
@@ -138,7 +140,7 @@ struct InfBits {
 // Canonical Huffman code of `n` symbols with code lengths lens[0..n): fills count[], sorted[] and the first-level
 // table lut (2^bits entries).  Returns false for an over-subscribed or (non-trivially) incomplete code.  All lanes
 // call it together; the symbol loop is uniform, the table fill is spread over the lanes.
-PSS_IHD bool inf_build(const uint8_t *lens, int n, uint16_t *count, uint16_t *sorted, uint16_t *lut, int bits)
+PSS_IHD_COLD bool inf_build(const uint8_t *lens, int n, uint16_t *count, uint16_t *sorted, uint16_t *lut, int bits)
 {
     const int lane = InfLanes::lane(), W = InfLanes::width();
     for (int i = lane; i < 16; i += W) count[i] = 0;
@@ -190,10 +192,9 @@ PSS_IHD bool inf_build(const uint8_t *lens, int n, uint16_t *count, uint16_t *so
 }
 
 // one symbol of a canonical code that the first-level table did not resolve (or any symbol): bit by bit
-PSS_IHD int inf_slow(InfBits &B, const uint16_t *count, const uint16_t *sorted, int &len_out)
+PSS_IHD_COLD int inf_slow(uint32_t bits, const uint16_t *count, const uint16_t *sorted, int &len_out)
 {
     int      code = 0, first = 0, index = 0;
-    uint32_t bits = (uint32_t)B.buf;
     for (int l = 1; l <= 15; l++) {
         code |= (int)(bits & 1u);
         bits >>= 1;
@@ -216,7 +217,7 @@ PSS_IHD int inf_decode(InfBits &B, const uint16_t *lut, int bits, const uint16_t
         return (int)(e >> 4);
     }
     int       l;
-    const int s = inf_slow(B, count, sorted, l);
+    const int s = inf_slow((uint32_t)B.buf, count, sorted, l);
     B.drop(l);
     return s;
 }
@@ -234,6 +235,90 @@ PSS_IHD uint32_t inf_dist_code(int s)       // 0..29
     const uint32_t eb = s < 4 ? 0u : (uint32_t)((s - 2) >> 1);
     const uint32_t base = s < 4 ? (uint32_t)(1 + s) : (uint32_t)(1 + ((2 + (s & 1)) << eb));
     return base | (eb << 16);
+}
+
+// ---- the symbol loop ---------------------------------------------------------------------------------------------------
+// Literal/length + distance symbols of one DEFLATE block up to its end-of-block code, warp uniform.  This is where the
+// time goes: the loop is a chain of dependent steps (bit buffer -> table index -> shared-memory load -> code length ->
+// bit buffer), and with tens of warps per SM it is bound by instruction issue -- so the literal path is kept to a
+// handful of instructions: the first-level tables are read through their 32-bit shared-memory address (no generic
+// pointer arithmetic in the loop), the output position is one register, errors leave through one exit.
+#if defined(__CUDA_ARCH__)
+struct InfLut {
+    uint32_t a;                                              // shared-space address of a uint16_t table
+    __device__ __forceinline__ explicit InfLut(const uint16_t *p) : a((uint32_t)__cvta_generic_to_shared(p)) {}
+    __device__ __forceinline__ uint32_t operator[](uint32_t i) const
+    {
+        uint32_t v;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a + 2u * i) : "memory");
+        return v;
+    }
+};
+#else
+struct InfLut {
+    const uint16_t *p;
+    explicit InfLut(const uint16_t *q) : p(q) {}
+    uint32_t operator[](uint32_t i) const { return p[i]; }
+};
+#endif
+
+PSS_IHD int inf_symbols(InfBits &B, InflateTables &T, uint8_t *out, uint32_t &op_io, uint32_t out_len)
+{
+    const int    lane = InfLanes::lane(), W = InfLanes::width();
+    const InfLut lit(T.lit_lut), dst(T.dist_lut);
+    const bool   writer = lane == 0;
+    uint32_t     op = op_io;
+    int          rc = kInfOk;
+    for (;;) {
+        B.refill();                                          // >= 33 bits: a literal/length code and its extra bits
+        uint32_t e = lit[B.peek(kInfLitBits)];
+        uint32_t l = e & 15u;
+        int      s = (int)(e >> 4);
+        if (l == 0u) {                                       // a code longer than the first-level table (rare)
+            int ll;
+            s = inf_slow((uint32_t)B.buf, T.lit_count, T.lit_sorted, ll);
+            l = (uint32_t)ll;
+            if (s < 0) { rc = kInfBadSymbol; break; }
+        }
+        B.drop((int)l);
+        if (s < 256) {
+            if (op >= out_len) { rc = kInfOutputOverrun; break; }
+            if (writer) out[op] = (uint8_t)s;
+            op++;
+            continue;
+        }
+        if (s == 256) break;
+        if (s > 285) { rc = kInfBadSymbol; break; }
+        const uint32_t lc = inf_len_code(s - 257);
+        const uint32_t len = (lc & 0xffffu) + B.get((int)(lc >> 16));
+        B.refill();
+        e = dst[B.peek(kInfDistBits)];
+        l = e & 15u;
+        int ds = (int)(e >> 4);
+        if (l == 0u) {
+            int ll;
+            ds = inf_slow((uint32_t)B.buf, T.dist_count, T.dist_sorted, ll);
+            l = (uint32_t)ll;
+        }
+        B.drop((int)l);
+        if (ds < 0 || ds > 29) { rc = kInfBadDistance; break; }
+        const uint32_t dc = inf_dist_code(ds);
+        const uint32_t dist = (dc & 0xffffu) + B.get((int)(dc >> 16));
+        if (dist > op) { rc = kInfBadDistance; break; }
+        if (op + len > out_len) { rc = kInfOutputOverrun; break; }
+        InfLanes::sync();                                    // the bytes written so far are visible to every lane
+        uint8_t       *d = out + op;
+        const uint8_t *src = d - dist;
+        if (dist >= len) {
+            for (uint32_t i = (uint32_t)lane; i < len; i += (uint32_t)W) d[i] = src[i];
+        } else {
+            // overlapping copy = the last `dist` bytes repeated
+            for (uint32_t i = (uint32_t)lane; i < len; i += (uint32_t)W) d[i] = src[i % dist];
+        }
+        op += len;
+    }
+    op_io = op;
+    return rc;
 }
 
 // ---- one BGZF payload -------------------------------------------------------------------------------------------------
@@ -331,38 +416,9 @@ PSS_IHD int inflate_block(const uint8_t *in, uint32_t in_len, uint8_t *out, uint
             if (!inf_build(T.lens + 288, 32, T.dist_count, T.dist_sorted, T.dist_lut, kInfDistBits)) return kInfBadCodeLengths;
         }
         // ---- the symbol loop (warp uniform)
-        for (;;) {
-            B.refill();
-            const int s = inf_decode(B, T.lit_lut, kInfLitBits, T.lit_count, T.lit_sorted);
-            if (s < 256) {
-                if (s < 0) return kInfBadSymbol;
-                if (op >= out_len) return kInfOutputOverrun;
-                if (lane == 0) out[op] = (uint8_t)s;
-                op++;
-                continue;
-            }
-            if (s == 256) break;
-            if (s > 285) return kInfBadSymbol;
-            const uint32_t lc = inf_len_code(s - 257);
-            const uint32_t len = (lc & 0xffffu) + B.get((int)(lc >> 16));
-            B.refill();
-            const int ds = inf_decode(B, T.dist_lut, kInfDistBits, T.dist_count, T.dist_sorted);
-            if (ds < 0 || ds > 29) return kInfBadDistance;
-            const uint32_t dc = inf_dist_code(ds);
-            const uint32_t dist = (dc & 0xffffu) + B.get((int)(dc >> 16));
-            if (dist > op) return kInfBadDistance;
-            if (op + len > out_len) return kInfOutputOverrun;
-            InfLanes::sync();                                           // earlier bytes of this block are visible to every lane
-            uint8_t       *dst = out + op;
-            const uint8_t *src = dst - dist;
-            if (dist >= len) {
-                for (uint32_t i = (uint32_t)lane; i < len; i += (uint32_t)W) dst[i] = src[i];
-            } else {
-                // overlapping copy = the last `dist` bytes repeated
-                for (uint32_t i = (uint32_t)lane; i < len; i += (uint32_t)W) dst[i] = src[i % dist];
-            }
-            op += len;
-            InfLanes::sync();
+        {
+            const int rc = inf_symbols(B, T, out, op, out_len);
+            if (rc != kInfOk) return rc;
         }
     } while (!last);
     if (B.bytes_used(mis) > in_len) return kInfInputOverrun;       // bits beyond the payload were consumed (they read as 0)

@@ -199,6 +199,121 @@ __global__ void __launch_bounds__(kSpecSmemThreads, 1) spectrum_smem_kernel(cons
         if (v) atomicAdd(counts + ((size_t)pass << kSpecSmemLog) + i, (CT)v);
     }
 }
+// k = 7 .. 9, second generation: 65 536 bins per pass in the same 128 KB, as 16-bit counters packed two to a word
+// -- bin b lives in half (b >> 15) & 1 of word b & 0x7fff -- so 4^8 bins take ONE pass over the packed genome instead of
+// two (4^9: four instead of eight), and the per-k-mer code has no pass test.  A 16-bit counter cannot hold a hot bin
+// (poly-A: 10^8 hits), so it is drained on the fly, exactly: an increment is a 32-bit shared-memory atomic add of 1 or
+// 0x10000 that returns the old word; the old words of a group's 16 increments are OR-ed and looked at once -- if some
+// half had reached 0x8000, the thread clears that bit with an atomicAnd and, if it was the one that cleared it, adds
+// 32 768 to the global bin.  Between a half reaching 0x8000 and the first drain at most 16 increments per thread of the
+// CTA arrive (16 384 < 0x8000): a half never wraps and never carries into its neighbour.  k-mer validity (all K bases
+// ACGT) comes from one smeared mask per group, and a group without a bad base (99 % of them) runs 16 unpredicated
+// increments.
+constexpr int kSpec16Log   = 16;                   // bins per pass
+constexpr int kSpec16Words = 1 << 15;              // 32-bit words of shared memory
+template <int K, int NPASS, bool ALL, typename CT>
+__device__ __forceinline__ void spec16_group(uint32_t *s_words, uint64_t msb, uint32_t vmask, uint32_t pass, CT *__restrict__ counts)
+{
+    constexpr uint32_t n_bins = 1u << (2 * K);
+    constexpr uint32_t kmask = n_bins - 1u;
+    uint32_t acc = 0;
+#pragma unroll
+    for (int o = 0; o < 16; o++) {
+        if (!ALL && !((vmask >> (2 * o)) & 1u)) continue;
+        const uint32_t idx = (uint32_t)(msb >> (2 * (32 - o - K))) & kmask;
+        if (NPASS > 1 && (idx >> kSpec16Log) != pass) continue;
+        const uint32_t inc = (2 * K > 15) ? ((idx >> 15) & 1u) * 0xffffu + 1u : 1u;
+        acc |= atomicAdd(&s_words[idx & 0x7fffu], inc);
+    }
+    if (acc & 0x80008000u) {                       // rare: some half is past 0x8000 -- drain what this thread touched
+#pragma unroll 1
+        for (int o = 0; o < 16; o++) {
+            if (!ALL && !((vmask >> (2 * o)) & 1u)) continue;
+            const uint32_t idx = (uint32_t)(msb >> (2 * (32 - o - K))) & kmask;
+            if (NPASS > 1 && (idx >> kSpec16Log) != pass) continue;
+            const uint32_t bit = ((idx >> 15) & 1u) ? 0x80000000u : 0x8000u;
+            if (atomicAnd(&s_words[idx & 0x7fffu], ~bit) & bit) atomicAdd(counts + idx, (CT)32768);
+        }
+    }
+}
+// the same for a group of low-complexity sequence: per k-mer, the lanes of the warp that are here and want the same bin
+// elect one that adds for all (an increment of at most 32 per atomic: the drain bound of 16 increments per thread holds)
+template <int K, int NPASS, typename CT>
+__device__ __noinline__ void spec16_group_aggregated(uint32_t *s_words, uint64_t msb, uint32_t vmask, uint32_t pass, CT *__restrict__ counts)
+{
+    constexpr uint32_t n_bins = 1u << (2 * K);
+    constexpr uint32_t kmask = n_bins - 1u;
+    const uint32_t here = __activemask(), lane = threadIdx.x & 31u;
+    uint32_t acc = 0;
+#pragma unroll 1
+    for (int o = 0; o < 16; o++) {
+        const uint32_t idx = (uint32_t)(msb >> (2 * (32 - o - K))) & kmask;
+        const bool     want = ((vmask >> (2 * o)) & 1u) && (NPASS == 1 || (idx >> kSpec16Log) == pass);
+        // lanes that do not count this k-mer get a key of their own (bit 31 + lane) and add nothing
+        const uint32_t peers = __match_any_sync(here, want ? idx : (0x80000000u | lane));
+        if (want && lane == (uint32_t)__ffs((int)peers) - 1u) {
+            const uint32_t inc = (2 * K > 15) ? ((idx >> 15) & 1u) * 0xffffu + 1u : 1u;
+            acc |= atomicAdd(&s_words[idx & 0x7fffu], inc * (uint32_t)__popc(peers));
+        }
+    }
+    if (acc & 0x80008000u) {
+#pragma unroll 1
+        for (int o = 0; o < 16; o++) {
+            if (!((vmask >> (2 * o)) & 1u)) continue;
+            const uint32_t idx = (uint32_t)(msb >> (2 * (32 - o - K))) & kmask;
+            if (NPASS > 1 && (idx >> kSpec16Log) != pass) continue;
+            const uint32_t bit = ((idx >> 15) & 1u) ? 0x80000000u : 0x8000u;
+            if (atomicAnd(&s_words[idx & 0x7fffu], ~bit) & bit) atomicAdd(counts + idx, (CT)32768);
+        }
+    }
+}
+template <int K, typename CT>
+__global__ void __launch_bounds__(kSpecSmemThreads, 1) spectrum_smem16_kernel(const uint64_t *__restrict__ groups, uint64_t g_begin,
+                                                                               uint64_t g_end, uint32_t n_slices, CT *__restrict__ counts)
+{
+    extern __shared__ uint32_t s_words[];
+    constexpr uint32_t n_bins = 1u << (2 * K);
+    constexpr int      NPASS = n_bins > (1u << kSpec16Log) ? (int)(n_bins >> kSpec16Log) : 1;
+    constexpr uint32_t words = n_bins >= (1u << kSpec16Log) ? (uint32_t)kSpec16Words : (n_bins > 32768u ? 32768u : n_bins);
+    const uint32_t slice = blockIdx.x % n_slices, pass = blockIdx.x / n_slices;
+    for (uint32_t i = threadIdx.x; i < words; i += kSpecSmemThreads) s_words[i] = 0;
+    __syncthreads();
+    const uint64_t n = g_end - g_begin;
+    const uint64_t lo = g_begin + n * slice / n_slices, hi = g_begin + n * (slice + 1) / n_slices;
+    for (uint64_t gi = lo + threadIdx.x; gi < hi; gi += kSpecSmemThreads) {
+        const uint64_t g0 = __ldg(groups + gi), g1 = __ldg(groups + gi + 1);
+        const uint64_t cls = (g0 >> 32) | (g1 & 0xffffffff00000000ull);
+        uint64_t       bad = (cls | (cls >> 1)) & kEvenBits;                 // bit 2j: base j of the 32-base window is not ACGT
+        if ((uint32_t)bad == 0x55555555u) continue;                          // whole group invalid (padding / N run)
+        const uint64_t codes = (uint64_t)(uint32_t)g0 | ((uint64_t)(uint32_t)g1 << 32);
+        const uint64_t msb = rev_fields64(codes, 32);                        // base j of the window at field 31 - j
+        // smear: bit 2o set <=> some base of [o, o + K) is bad
+        {
+            int span = 1;
+#pragma unroll
+            for (int it = 0; it < 4; it++) {
+                const int step = span < K - span ? span : K - span;
+                if (step > 0) { bad |= bad >> (2 * step); span += step; }
+            }
+        }
+        const uint32_t inval = (uint32_t)bad & 0x55555555u;
+        // Low-complexity sequence (poly-A, (CA)n, (CAG)n ...): the window repeats with period 2 or 3 (a homopolymer with
+        // both), every lane of the warp then asks for the same few bins and the shared-memory atomics would serialise
+        // 32 ways.  Such groups take a path in which the lanes that want the same bin are found with match.any and one
+        // of them adds the popcount.
+        const bool periodic = ((msb ^ (msb >> 4)) << 4) == 0ull || ((msb ^ (msb >> 6)) << 6) == 0ull;
+        if (periodic) spec16_group_aggregated<K, NPASS, CT>(s_words, msb, ~inval, pass, counts);
+        else if (inval == 0u) spec16_group<K, NPASS, true, CT>(s_words, msb, 0u, pass, counts);
+        else spec16_group<K, NPASS, false, CT>(s_words, msb, ~inval, pass, counts);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < words; i += kSpecSmemThreads) {
+        const uint32_t v = s_words[i], lo16 = v & 0xffffu, hi16 = v >> 16;
+        const size_t   base = (size_t)pass << kSpec16Log;
+        if (lo16) atomicAdd(counts + base + i, (CT)lo16);
+        if (hi16) atomicAdd(counts + base + 0x8000u + i, (CT)hi16);
+    }
+}
 // k = 10 .. 12: one global atomic per k-mer is bound by the rate at which the SMs can send requests to L2 (16 ms for the
 // 3.1 Gb genome, 4^12 bins resident in L2).  Instead: (1) count the k-mers per bucket = high 2k-15 bits of the index
 // (<= 512 buckets), (2) scatter the low 15 bits of every k-mer, as u16, into its bucket's stretch of a scratch buffer

@@ -1026,7 +1026,25 @@ int pssgpu_kmer_spectrum_shard_device(pssgpu_ctx *ctx, int k, int shard, int n_s
             cudaFuncSetAttribute(radix_hist_kernel<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem);
             radix_hist_kernel<unsigned long long><<<rad_nb * parts, kSpecSmemThreads, hsmem, ctx->stream>>>(d_payload, off, parts, (unsigned long long *)d_counts);
         }
-    } else if (g1 > g0 && k >= 7 && k <= 9) {    // shared-memory bins, one CTA per SM and (slice, pass)
+    } else if (g1 > g0 && k >= 7 && k <= 9 && !getenv("PSSGPU_SPECTRUM_SMEM32")) {
+        // shared-memory bins, 16-bit counters packed two to a word: 65 536 bins per CTA -- one pass for 4^8 bins, four for 4^9
+        const uint32_t n_slices = (uint32_t)std::min<uint64_t>((uint64_t)ctx->sm_count, (g1 - g0 + kSpecSmemThreads - 1) / kSpecSmemThreads);
+        const uint32_t passes = (uint32_t)std::max<size_t>(1, bins >> kSpec16Log);
+        const size_t   smem = std::min<size_t>(std::max<size_t>(bins / 2, std::min<size_t>(bins, 32768)), kSpec16Words) * sizeof(uint32_t);
+        const dim3     sg(n_slices * passes);
+#define PSS_SPEC16(K_, CT_, PTR_)                                                                                      \
+        do {                                                                                                           \
+            cudaFuncSetAttribute(spectrum_smem16_kernel<K_, CT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            spectrum_smem16_kernel<K_, CT_><<<sg, kSpecSmemThreads, smem, ctx->stream>>>(ctx->d_groups, g0, g1, n_slices, PTR_); \
+        } while (0)
+        if (narrow) {
+            if (k == 7) PSS_SPEC16(7, unsigned int, d_narrow); else if (k == 8) PSS_SPEC16(8, unsigned int, d_narrow); else PSS_SPEC16(9, unsigned int, d_narrow);
+        } else {
+            unsigned long long *w = (unsigned long long *)d_counts;
+            if (k == 7) PSS_SPEC16(7, unsigned long long, w); else if (k == 8) PSS_SPEC16(8, unsigned long long, w); else PSS_SPEC16(9, unsigned long long, w);
+        }
+#undef PSS_SPEC16
+    } else if (g1 > g0 && k >= 7 && k <= 9) {    // the first generation (32-bit bins, two passes for 4^8): kept behind PSSGPU_SPECTRUM_SMEM32 for comparison
         const uint32_t n_slices = (uint32_t)std::min<uint64_t>((uint64_t)ctx->sm_count, (g1 - g0 + kSpecSmemThreads - 1) / kSpecSmemThreads);
         const uint32_t passes = (uint32_t)std::max<size_t>(1, bins >> kSpecSmemLog);
         const size_t   smem = std::min<size_t>(bins, kSpecSmemBins) * sizeof(uint32_t);

@@ -234,53 +234,86 @@ bam_fix_kernel(const BamDesc *__restrict__ desc, uint32_t n_blocks, const uint8_
     }
 }
 
-// One CTA per BGZF block: records -> SAM lines.
-__global__ void __launch_bounds__(128)
+// One CTA per BGZF block: records -> SAM lines.  Pass 1, one thread per record: well-formedness, the RG filter, the
+// length of the line; a CTA scan gives every line its place and ONE atomic allocates the block's stretch of the text.
+// Pass 2, one warp per record: lane 0 renders the short head (FLAG .. TLEN) into shared memory, then all lanes store
+// head, SEQ (4-bit codes -> letters) and QUAL byte by consecutive byte -- coalesced stores instead of one thread
+// dribbling 240 single bytes.
+constexpr int kRenderThreads = 128;
+constexpr int kRenderHeadCap = 240;                         // longer heads (long CIGARs / names) are written by lane 0 directly
+__global__ void __launch_bounds__(kRenderThreads)
 bam_render_kernel(const uint8_t *__restrict__ ubuf, BamState *st, const uint32_t *__restrict__ loc, const uint32_t *__restrict__ N,
                   BamRefs refs, const char *__restrict__ rg, int rg_len, uint8_t *__restrict__ text, uint64_t text_cap)
 {
-    __shared__ uint32_t s_warp[4];
+    __shared__ uint32_t s_off[kBamLocCap + 1];              // line lengths, then their exclusive prefix sums
+    __shared__ uint32_t s_warp[kRenderThreads / 32];
     __shared__ unsigned long long s_base;
+    __shared__ uint8_t  s_head[kRenderThreads / 32][kRenderHeadCap + 16];
     const uint32_t b = blockIdx.x, tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     if (!st->hdr_done || st->error) return;
     const uint32_t n = N[b];
+    if (n == 0) return;
     if (n > kBamLocCap) { if (tid == 0) bam_fail(st, kBamErrLocOverflow, b); return; }
     refs.n_ref = st->n_ref;
     const uint32_t *mine = loc + (size_t)b * kBamLocCap;
+    // ---- pass 1
     uint32_t dropped = 0;
-    for (uint32_t i0 = 0; i0 < n; i0 += 128) {
-        const uint32_t i = i0 + tid;
-        const uint8_t *r = nullptr;
-        BamCore        c{};
+    for (uint32_t i = tid; i < n; i += kRenderThreads) {
+        const uint8_t *r = ubuf + mine[i];
+        const BamCore  c = bam_core(r);
         uint32_t       len = 0;
-        if (i < n) {
-            r = ubuf + mine[i];
-            c = bam_core(r);
-            if (!bam_wellformed(c)) { bam_fail(st, kBamErrRecord, b); r = nullptr; }
-            else if (rg_len >= 0 && !bam_has_read_group(r, c, rg, rg_len)) { dropped++; r = nullptr; }
-            else { BamCountSink cs; bam_render(r, c, refs, cs); len = cs.n; }
+        if (!bam_wellformed(c)) bam_fail(st, kBamErrRecord, b);
+        else if (rg_len >= 0 && !bam_has_read_group(r, c, rg, rg_len)) dropped++;
+        else {
+            BamCountSink cs;
+            bam_render_head(r, c, refs, cs);
+            len = cs.n + bam_tail_len(c, bam_qual_is_star(r, c));
         }
-        // exclusive scan of len over the CTA, one allocation per round
-        uint32_t inc = len;
+        s_off[i] = len;
+    }
+    __syncthreads();
+    // exclusive scan of s_off[0 .. n): every thread owns a run of consecutive entries
+    const uint32_t per = (n + kRenderThreads - 1) / kRenderThreads, lo = tid * per, hi = lo + per < n ? lo + per : n;
+    uint32_t sum = 0;
+    for (uint32_t i = lo; i < hi; i++) sum += s_off[i];
+    uint32_t inc = sum;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
-            if ((int)lane >= d) inc += t;
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if ((int)lane >= d) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+    for (uint32_t w = 0; w < kRenderThreads / 32; w++) { const uint32_t v = s_warp[w]; if (w < warp) before += v; total += v; }
+    uint32_t run = before + inc - sum;
+    for (uint32_t i = lo; i < hi; i++) { const uint32_t v = s_off[i]; s_off[i] = run; run += v; }
+    if (tid == 0) { s_off[n] = total; s_base = total ? atomicAdd(&st->text_len, (unsigned long long)total) : 0ull; }
+    __syncthreads();
+    if (s_base + total > text_cap) { if (tid == 0) bam_fail(st, kBamErrTextOverflow, b); return; }
+    // ---- pass 2
+    for (uint32_t i = warp; i < n; i += kRenderThreads / 32) {
+        const uint32_t at = s_off[i], len = s_off[i + 1] - at;
+        if (len == 0) continue;                                     // dropped (RG filter / malformed)
+        const uint8_t *r = ubuf + mine[i];
+        const BamCore  c = bam_core(r);                             // warp uniform
+        const bool     qs = bam_qual_is_star(r, c);
+        const uint32_t tail = bam_tail_len(c, qs), head = len - tail;
+        uint8_t       *dst = text + s_base + at;
+        if (head <= (uint32_t)kRenderHeadCap) {
+            if (lane == 0) { BamWriteSink ws{ s_head[warp] }; bam_render_head(r, c, refs, ws); }
+            __syncwarp();
+            for (uint32_t k = lane; k < head; k += 32) dst[k] = s_head[warp][k];
+            __syncwarp();
+        } else if (lane == 0) {
+            BamWriteSink ws{ dst };
+            bam_render_head(r, c, refs, ws);
         }
-        if (lane == 31) s_warp[warp] = inc;
-        __syncthreads();
-        uint32_t before = 0, total = 0;
-        for (uint32_t w = 0; w < 4; w++) { const uint32_t v = s_warp[w]; if (w < warp) before += v; total += v; }
-        if (tid == 0) s_base = total ? atomicAdd(&st->text_len, (unsigned long long)total) : 0ull;
-        __syncthreads();
-        const unsigned long long at = s_base + before + inc - len;
-        if (s_base + total > text_cap) { if (tid == 0) bam_fail(st, kBamErrTextOverflow, b); return; }
-        if (r) { BamWriteSink ws{ text + at }; bam_render(r, c, refs, ws); }
-        __syncthreads();
+        const uint8_t *seq = bam_seq_ptr(r, c);
+        dst += head;
+        for (uint32_t k = lane; k < tail; k += 32) dst[k] = bam_tail_byte(seq, c, qs, k);
     }
     // counters: one atomic per warp
-    const uint32_t kept = 0;
-    (void)kept;
 #pragma unroll
     for (int d = 16; d; d >>= 1) dropped += __shfl_xor_sync(0xffffffffu, dropped, d);
     if (lane == 0 && dropped) atomicAdd(&st->n_dropped, (unsigned long long)dropped);

@@ -323,3 +323,29 @@ def test_line_longer_than_the_staging_buffer(small):
         gf, gr = ctx.pss_finish()
         assert ctx.stats() == st
         assert np.array_equal(gf, f) and np.array_equal(gr, r)
+
+
+def test_spectrum_hot_bins():
+    """Low-complexity genome: poly-A, (CA)n and (CAG)n stretches put 10^6 .. 10^7 k-mers into single bins -- far beyond
+    the 16-bit shared-memory counters of the k = 7..9 kernel, whose on-the-fly drain must stay exact -- next to N runs
+    and contig ends; the 32-bit-bin first generation (PSSGPU_SPECTRUM_SMEM32) and 64-bit global bins give the same."""
+    import os
+    g = Synth.genome(71, [9_000_000, 6_000_000, 1_000_003], n_frac=0.01, lower_frac=0.02)
+    for s, (at, n, motif) in zip(g.seqs, [(1_000_000, 5_000_000, b"A"), (500_000, 4_000_000, b"CA"), (1000, 700_000, b"CAG")]):
+        s[at:at + n] = np.frombuffer((motif * (n // len(motif) + 1))[:n], dtype=np.uint8)
+    g.seqs[0][3_000_000:3_000_040] = np.frombuffer(b"N" * 40, dtype=np.uint8)          # an N run inside the poly-A stretch
+    ora = Oracle(contigs=list(zip(g.names, g.seqs)))
+    ctx = pkg.Context(0)
+    ctx.upload_genome(list(zip(g.names, g.seqs)))
+    for k in (6, 7, 8, 9, 10):
+        want = ora.kmer_spectrum(k)
+        assert int(want.max()) > 3_000_000
+        assert np.array_equal(ctx.kmer_spectrum(k), want), k
+        assert np.array_equal(sum(ctx.kmer_spectrum(k, s, 5) for s in range(5)), want), k
+        for switch in ("PSSGPU_SPECTRUM_SMEM32", "PSSGPU_SPECTRUM_WIDE"):
+            os.environ[switch] = "1"
+            try:
+                assert np.array_equal(ctx.kmer_spectrum(k), want), (k, switch)
+            finally:
+                del os.environ[switch]
+    ctx.close()
