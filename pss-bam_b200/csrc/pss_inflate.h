@@ -140,7 +140,7 @@ struct InfBits {
 // Canonical Huffman code of `n` symbols with code lengths lens[0..n): fills count[], sorted[] and the first-level
 // table lut (2^bits entries).  Returns false for an over-subscribed or (non-trivially) incomplete code.  All lanes
 // call it together; the symbol loop is uniform, the table fill is spread over the lanes.
-PSS_IHD_COLD bool inf_build(const uint8_t *lens, int n, uint16_t *count, uint16_t *sorted, uint16_t *lut, int bits)
+PSS_IHD_COLD bool inf_build(const uint8_t *lens, int n, uint16_t *count, uint16_t *sorted, uint16_t *lut, int bits, bool flag_literals = false)
 {
     const int lane = InfLanes::lane(), W = InfLanes::width();
     for (int i = lane; i < 16; i += W) count[i] = 0;
@@ -183,7 +183,8 @@ PSS_IHD_COLD bool inf_build(const uint8_t *lens, int n, uint16_t *count, uint16_
             uint32_t r = 0;
             for (int b = 0; b < l; b++) r |= ((c >> b) & 1u) << (l - 1 - b);
 #endif
-            const uint16_t e = (uint16_t)((s << 4) | l);
+            // literal/length table: bit 15 marks a literal, so that the symbol loop decides "literal, resolved" with one test
+            const uint16_t e = (uint16_t)((s << 4) | l | ((flag_literals && s < 256) ? 0x8000 : 0));
             for (int k = lane; k < (1 << (bits - l)); k += W) lut[r + ((uint32_t)k << l)] = e;
         }
     }
@@ -262,18 +263,52 @@ struct InfLut {
 };
 #endif
 
+// one literal to the output (the pointer has been made opaque to the compiler, which would otherwise fall back to a
+// generic store: say "global" explicitly)
+PSS_IHD void inf_store(uint8_t *p, uint8_t v, bool writer)
+{
+#if defined(__CUDA_ARCH__)
+    if (writer) asm volatile("st.global.u8 [%0], %1;" ::"l"(p), "r"((uint32_t)v) : "memory");
+#else
+    if (writer) *p = v;
+#endif
+}
+
 PSS_IHD int inf_symbols(InfBits &B, InflateTables &T, uint8_t *out, uint32_t &op_io, uint32_t out_len)
 {
-    const int    lane = InfLanes::lane(), W = InfLanes::width();
-    const InfLut lit(T.lit_lut), dst(T.dist_lut);
-    const bool   writer = lane == 0;
-    uint32_t     op = op_io;
-    int          rc = kInfOk;
+    const int lane = InfLanes::lane(), W = InfLanes::width();
+    InfLut    lit(T.lit_lut), dst(T.dist_lut);
+    uint8_t  *wp = out + op_io;                              // next output byte
+    uint32_t  room = out_len - op_io;                        // bytes that may still be written
+#if defined(__CUDA_ARCH__)
+    // opaque to the compiler: otherwise it re-derives the shared-memory addresses (six instructions) in every iteration
+    asm volatile("" : "+r"(lit.a), "+r"(dst.a));
+    asm volatile("" : "+l"(wp));
+#endif
+    const bool writer = lane == 0;
+    int        rc = kInfOk;
     for (;;) {
-        B.refill();                                          // >= 33 bits: a literal/length code and its extra bits
-        uint32_t e = lit[B.peek(kInfLitBits)];
+        // ---- literals: bit buffer -> table -> literal flag, nothing else
+        uint32_t e;
+        for (;;) {
+            B.refill();                                      // >= 33 bits: two literal codes (<= 15 bits each) fit
+            e = lit[B.peek(kInfLitBits)];
+            if (!(e & 0x8000u) || room == 0u) break;
+            B.drop((int)(e & 15u));
+            inf_store(wp, (uint8_t)(e >> 4), writer);
+            wp++;
+            room--;
+            e = lit[B.peek(kInfLitBits)];                    // the second one on the same fill
+            if (!(e & 0x8000u) || room == 0u) break;
+            B.drop((int)(e & 15u));
+            inf_store(wp, (uint8_t)(e >> 4), writer);
+            wp++;
+            room--;
+        }
+        // ---- everything else: longer codes, lengths, end of block, errors
+        B.refill();                                          // (the entry `e` came from the low bits, which a fill leaves alone)
         uint32_t l = e & 15u;
-        int      s = (int)(e >> 4);
+        int      s = (int)((e & 0x7fffu) >> 4);
         if (l == 0u) {                                       // a code longer than the first-level table (rare)
             int ll;
             s = inf_slow((uint32_t)B.buf, T.lit_count, T.lit_sorted, ll);
@@ -282,9 +317,10 @@ PSS_IHD int inf_symbols(InfBits &B, InflateTables &T, uint8_t *out, uint32_t &op
         }
         B.drop((int)l);
         if (s < 256) {
-            if (op >= out_len) { rc = kInfOutputOverrun; break; }
-            if (writer) out[op] = (uint8_t)s;
-            op++;
+            if (room == 0u) { rc = kInfOutputOverrun; break; }
+            inf_store(wp, (uint8_t)s, writer);
+            wp++;
+            room--;
             continue;
         }
         if (s == 256) break;
@@ -304,20 +340,20 @@ PSS_IHD int inf_symbols(InfBits &B, InflateTables &T, uint8_t *out, uint32_t &op
         if (ds < 0 || ds > 29) { rc = kInfBadDistance; break; }
         const uint32_t dc = inf_dist_code(ds);
         const uint32_t dist = (dc & 0xffffu) + B.get((int)(dc >> 16));
-        if (dist > op) { rc = kInfBadDistance; break; }
-        if (op + len > out_len) { rc = kInfOutputOverrun; break; }
+        if (dist > out_len - room) { rc = kInfBadDistance; break; }
+        if (len > room) { rc = kInfOutputOverrun; break; }
         InfLanes::sync();                                    // the bytes written so far are visible to every lane
-        uint8_t       *d = out + op;
-        const uint8_t *src = d - dist;
+        const uint8_t *src = wp - dist;
         if (dist >= len) {
-            for (uint32_t i = (uint32_t)lane; i < len; i += (uint32_t)W) d[i] = src[i];
+            for (uint32_t i = (uint32_t)lane; i < len; i += (uint32_t)W) wp[i] = src[i];
         } else {
             // overlapping copy = the last `dist` bytes repeated
-            for (uint32_t i = (uint32_t)lane; i < len; i += (uint32_t)W) d[i] = src[i % dist];
+            for (uint32_t i = (uint32_t)lane; i < len; i += (uint32_t)W) wp[i] = src[i % dist];
         }
-        op += len;
+        wp += len;
+        room -= len;
     }
-    op_io = op;
+    op_io = out_len - room;
     return rc;
 }
 
@@ -363,7 +399,7 @@ PSS_IHD int inflate_block(const uint8_t *in, uint32_t in_len, uint8_t *out, uint
             for (int s = lane; s < 288; s += W) T.lens[s] = (uint8_t)(s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : 8);
             for (int s = lane; s < 32; s += W) T.lens[288 + s] = 5;
             InfLanes::sync();
-            if (!inf_build(T.lens, 288, T.lit_count, T.lit_sorted, T.lit_lut, kInfLitBits)) return kInfBadCodeLengths;
+            if (!inf_build(T.lens, 288, T.lit_count, T.lit_sorted, T.lit_lut, kInfLitBits, true)) return kInfBadCodeLengths;
             if (!inf_build(T.lens + 288, 32, T.dist_count, T.dist_sorted, T.dist_lut, kInfDistBits)) return kInfBadCodeLengths;
         } else {
             B.refill();
@@ -412,7 +448,7 @@ PSS_IHD int inflate_block(const uint8_t *in, uint32_t in_len, uint8_t *out, uint
             }
             InfLanes::sync();
             if (T.lens[256] == 0) return kInfBadCodeLengths;             // no end-of-block code
-            if (!inf_build(T.lens, 288, T.lit_count, T.lit_sorted, T.lit_lut, kInfLitBits)) return kInfBadCodeLengths;
+            if (!inf_build(T.lens, 288, T.lit_count, T.lit_sorted, T.lit_lut, kInfLitBits, true)) return kInfBadCodeLengths;
             if (!inf_build(T.lens + 288, 32, T.dist_count, T.dist_sorted, T.dist_lut, kInfDistBits)) return kInfBadCodeLengths;
         }
         // ---- the symbol loop (warp uniform)
