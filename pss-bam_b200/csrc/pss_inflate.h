@@ -44,6 +44,8 @@ struct InflateTables {                       // one per warp
     uint16_t lit_sorted[kInfMaxLit];         // symbols in canonical order (by code length, then symbol)
     uint16_t dist_sorted[kInfMaxDist];
     uint16_t lit_count[16], dist_count[16];  // codes per length
+    uint32_t lit_first, lit_index;           // state of the canonical walk after kInfLitBits levels (longer codes resume there)
+    uint32_t dist_first, dist_index;         // ... after kInfDistBits levels
     uint8_t  lens[kInfMaxLit + kInfMaxDist]; // code lengths of the block being set up
 };
 
@@ -140,7 +142,8 @@ struct InfBits {
 // Canonical Huffman code of `n` symbols with code lengths lens[0..n): fills count[], sorted[] and the first-level
 // table lut (2^bits entries).  Returns false for an over-subscribed or (non-trivially) incomplete code.  All lanes
 // call it together; the symbol loop is uniform, the table fill is spread over the lanes.
-PSS_IHD_COLD bool inf_build(const uint8_t *lens, int n, uint16_t *count, uint16_t *sorted, uint16_t *lut, int bits, bool flag_literals = false)
+PSS_IHD_COLD bool inf_build(const uint8_t *lens, int n, uint16_t *count, uint16_t *sorted, uint16_t *lut, int bits, bool flag_literals = false,
+                            uint32_t *resume_first = nullptr, uint32_t *resume_index = nullptr)
 {
     const int lane = InfLanes::lane(), W = InfLanes::width();
     for (int i = lane; i < 16; i += W) count[i] = 0;
@@ -164,6 +167,12 @@ PSS_IHD_COLD bool inf_build(const uint8_t *lens, int n, uint16_t *count, uint16_
             o += count[l];
             c = (c + count[l]) << 1;
         }
+    }
+    if (resume_first && lane == 0) {           // canonical walk (inf_long) after `bits` levels without a hit
+        uint32_t f = 0, ix = 0;
+        for (int l = 1; l <= bits; l++) { ix += count[l]; f = (f + count[l]) << 1; }
+        *resume_first = f;
+        *resume_index = ix;
     }
     const int used = n - (int)count[0];
     // incomplete codes are legal only in the one-code case (a single distance code, RFC 1951 3.2.7) -- and zlib also
@@ -223,6 +232,58 @@ PSS_IHD int inf_decode(InfBits &B, const uint16_t *lut, int bits, const uint16_t
     return s;
 }
 
+// A code longer than the first-level table: the canonical walk resumed behind the `bits` levels the table covers
+// (their state was computed when the table was built), at most 15 - bits steps.  `word` = the next 32 bits of the stream.
+PSS_IHD int inf_long(uint32_t word, const uint16_t *count, const uint16_t *sorted, uint32_t first0, uint32_t index0, int bits, int &len_out)
+{
+#if defined(__CUDA_ARCH__)
+    int code = (int)((__brev(word) >> (32 - bits)) << 1);
+#else
+    uint32_t rv = 0;
+    for (int b = 0; b < bits; b++) rv |= ((word >> b) & 1u) << (bits - 1 - b);
+    int code = (int)(rv << 1);
+#endif
+    int      first = (int)first0, index = (int)index0;
+    uint32_t rest = word >> bits;
+#pragma unroll
+    for (int l = bits + 1; l <= 15; l++) {
+        code |= (int)(rest & 1u);
+        rest >>= 1;
+        const int c = count[l];
+        if (code - c < first) { len_out = l; return sorted[index + (code - first)]; }
+        index += c;
+        first += c;
+        first <<= 1;
+        code <<= 1;
+    }
+    len_out = 15;
+    return -1;
+}
+
+// base | extra bits << 16 of the length symbols 257..285 and the distance symbols 0..29 (RFC 1951 3.2.5)
+#if defined(__CUDACC__)
+#define PSS_INF_CONST static __device__ __constant__
+#else
+#define PSS_INF_CONST static const
+#endif
+PSS_INF_CONST uint32_t kInfLenTab[32] = {
+    3, 4, 5, 6, 7, 8, 9, 10, 11 | (1 << 16), 13 | (1 << 16), 15 | (1 << 16), 17 | (1 << 16), 19 | (2 << 16), 23 | (2 << 16), 27 | (2 << 16),
+    31 | (2 << 16), 35 | (3 << 16), 43 | (3 << 16), 51 | (3 << 16), 59 | (3 << 16), 67 | (4 << 16), 83 | (4 << 16), 99 | (4 << 16),
+    115 | (4 << 16), 131 | (5 << 16), 163 | (5 << 16), 195 | (5 << 16), 227 | (5 << 16), 258, 0, 0, 0 };
+PSS_INF_CONST uint32_t kInfDistTab[32] = {
+    1, 2, 3, 4, 5 | (1 << 16), 7 | (1 << 16), 9 | (2 << 16), 13 | (2 << 16), 17 | (3 << 16), 25 | (3 << 16), 33 | (4 << 16), 49 | (4 << 16),
+    65 | (5 << 16), 97 | (5 << 16), 129 | (6 << 16), 193 | (6 << 16), 257 | (7 << 16), 385 | (7 << 16), 513 | (8 << 16), 769 | (8 << 16),
+    1025 | (9 << 16), 1537 | (9 << 16), 2049 | (10 << 16), 3073 | (10 << 16), 4097 | (11 << 16), 6145 | (11 << 16), 8193 | (12 << 16),
+    12289 | (12 << 16), 16385 | (13 << 16), 24577 | (13 << 16), 0, 0 };
+#if defined(__CUDACC__) && !defined(__CUDA_ARCH__)
+// host pass of nvcc: the device tables above cannot be read here; the host never decodes in the product library
+PSS_IHD uint32_t inf_len_tab(int) { return 0; }
+PSS_IHD uint32_t inf_dist_tab(int) { return 0; }
+#else
+PSS_IHD uint32_t inf_len_tab(int s) { return kInfLenTab[s]; }
+PSS_IHD uint32_t inf_dist_tab(int s) { return kInfDistTab[s]; }
+#endif
+
 // length / distance bases and extra bits (RFC 1951 3.2.5), packed: base | extra << 16
 PSS_IHD uint32_t inf_len_code(int s)        // s = symbol - 257, 0..28
 {
@@ -274,6 +335,24 @@ PSS_IHD void inf_store(uint8_t *p, uint8_t v, bool writer)
 #endif
 }
 
+// LZ77 match: wp[0 .. len) = wp[-dist ..], by all lanes (byte i by lane i mod 32).  An overlapping match (dist < len)
+// repeats its last `dist` bytes.  Matches of a BAM average nine bytes: one predicated load/store pair.
+PSS_IHD void inf_copy(uint8_t *wp, uint32_t dist, uint32_t len, int lane, int W)
+{
+    const uint8_t *src = wp - dist;
+#if defined(__CUDA_ARCH__)
+    (void)W;
+    for (uint32_t i = (uint32_t)lane; i < len; i += 32u) {
+        const uint32_t k = dist >= len ? i : i % dist;
+        uint32_t v;
+        asm volatile("ld.global.u8 %0, [%1];" : "=r"(v) : "l"(src + k) : "memory");
+        asm volatile("st.global.u8 [%0], %1;" ::"l"(wp + i), "r"(v) : "memory");
+    }
+#else
+    for (uint32_t i = (uint32_t)lane; i < len; i += (uint32_t)W) wp[i] = src[dist >= len ? i : i % dist];
+#endif
+}
+
 PSS_IHD int inf_symbols(InfBits &B, InflateTables &T, uint8_t *out, uint32_t &op_io, uint32_t out_len)
 {
     const int lane = InfLanes::lane(), W = InfLanes::width();
@@ -309,9 +388,9 @@ PSS_IHD int inf_symbols(InfBits &B, InflateTables &T, uint8_t *out, uint32_t &op
         B.refill();                                          // (the entry `e` came from the low bits, which a fill leaves alone)
         uint32_t l = e & 15u;
         int      s = (int)((e & 0x7fffu) >> 4);
-        if (l == 0u) {                                       // a code longer than the first-level table (rare)
+        if (l == 0u) {                                       // a code longer than the first-level table (7 % of the symbols of a BAM)
             int ll;
-            s = inf_slow((uint32_t)B.buf, T.lit_count, T.lit_sorted, ll);
+            s = inf_long((uint32_t)B.buf, T.lit_count, T.lit_sorted, T.lit_first, T.lit_index, kInfLitBits, ll);
             l = (uint32_t)ll;
             if (s < 0) { rc = kInfBadSymbol; break; }
         }
@@ -325,7 +404,7 @@ PSS_IHD int inf_symbols(InfBits &B, InflateTables &T, uint8_t *out, uint32_t &op
         }
         if (s == 256) break;
         if (s > 285) { rc = kInfBadSymbol; break; }
-        const uint32_t lc = inf_len_code(s - 257);
+        const uint32_t lc = inf_len_tab(s - 257);
         const uint32_t len = (lc & 0xffffu) + B.get((int)(lc >> 16));
         B.refill();
         e = dst[B.peek(kInfDistBits)];
@@ -333,23 +412,17 @@ PSS_IHD int inf_symbols(InfBits &B, InflateTables &T, uint8_t *out, uint32_t &op
         int ds = (int)(e >> 4);
         if (l == 0u) {
             int ll;
-            ds = inf_slow((uint32_t)B.buf, T.dist_count, T.dist_sorted, ll);
+            ds = inf_long((uint32_t)B.buf, T.dist_count, T.dist_sorted, T.dist_first, T.dist_index, kInfDistBits, ll);
             l = (uint32_t)ll;
         }
         B.drop((int)l);
         if (ds < 0 || ds > 29) { rc = kInfBadDistance; break; }
-        const uint32_t dc = inf_dist_code(ds);
+        const uint32_t dc = inf_dist_tab(ds);
         const uint32_t dist = (dc & 0xffffu) + B.get((int)(dc >> 16));
         if (dist > out_len - room) { rc = kInfBadDistance; break; }
         if (len > room) { rc = kInfOutputOverrun; break; }
         InfLanes::sync();                                    // the bytes written so far are visible to every lane
-        const uint8_t *src = wp - dist;
-        if (dist >= len) {
-            for (uint32_t i = (uint32_t)lane; i < len; i += (uint32_t)W) wp[i] = src[i];
-        } else {
-            // overlapping copy = the last `dist` bytes repeated
-            for (uint32_t i = (uint32_t)lane; i < len; i += (uint32_t)W) wp[i] = src[i % dist];
-        }
+        inf_copy(wp, dist, len, lane, W);
         wp += len;
         room -= len;
     }
@@ -399,8 +472,8 @@ PSS_IHD int inflate_block(const uint8_t *in, uint32_t in_len, uint8_t *out, uint
             for (int s = lane; s < 288; s += W) T.lens[s] = (uint8_t)(s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : 8);
             for (int s = lane; s < 32; s += W) T.lens[288 + s] = 5;
             InfLanes::sync();
-            if (!inf_build(T.lens, 288, T.lit_count, T.lit_sorted, T.lit_lut, kInfLitBits, true)) return kInfBadCodeLengths;
-            if (!inf_build(T.lens + 288, 32, T.dist_count, T.dist_sorted, T.dist_lut, kInfDistBits)) return kInfBadCodeLengths;
+            if (!inf_build(T.lens, 288, T.lit_count, T.lit_sorted, T.lit_lut, kInfLitBits, true, &T.lit_first, &T.lit_index)) return kInfBadCodeLengths;
+            if (!inf_build(T.lens + 288, 32, T.dist_count, T.dist_sorted, T.dist_lut, kInfDistBits, false, &T.dist_first, &T.dist_index)) return kInfBadCodeLengths;
         } else {
             B.refill();
             const int hlit = (int)B.get(5) + 257, hdist = (int)B.get(5) + 1, hclen = (int)B.get(4) + 4;
@@ -448,8 +521,8 @@ PSS_IHD int inflate_block(const uint8_t *in, uint32_t in_len, uint8_t *out, uint
             }
             InfLanes::sync();
             if (T.lens[256] == 0) return kInfBadCodeLengths;             // no end-of-block code
-            if (!inf_build(T.lens, 288, T.lit_count, T.lit_sorted, T.lit_lut, kInfLitBits, true)) return kInfBadCodeLengths;
-            if (!inf_build(T.lens + 288, 32, T.dist_count, T.dist_sorted, T.dist_lut, kInfDistBits)) return kInfBadCodeLengths;
+            if (!inf_build(T.lens, 288, T.lit_count, T.lit_sorted, T.lit_lut, kInfLitBits, true, &T.lit_first, &T.lit_index)) return kInfBadCodeLengths;
+            if (!inf_build(T.lens + 288, 32, T.dist_count, T.dist_sorted, T.dist_lut, kInfDistBits, false, &T.dist_first, &T.dist_index)) return kInfBadCodeLengths;
         }
         // ---- the symbol loop (warp uniform)
         {
