@@ -10,6 +10,7 @@
 #include "pssgpu_internal.h"
 
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <cstdlib>
 #include <cstring>
@@ -217,7 +218,15 @@ int pssgpu_group_init(const int *devices, int n, pssgpu_group **out)
     const char *mode = getenv("PSSGPU_GROUP_REDUCE");
     if (dev.size() > 1 && !has_dup && !(mode && strcmp(mode, "peer") == 0) && g->nccl.load()) {
         g->comm.assign(dev.size(), nullptr);
-        if (g->nccl.CommInitAll(g->comm.data(), (int)dev.size(), dev.data()) == 0) g->use_nccl = true;
+        // NCCL announces its version on stdout when NCCL_DEBUG asks for it -- stdout is where fragkon and
+        // genome-kmer-count print their tables: it goes to stderr for the duration of the initialisation
+        fflush(stdout);
+        const int saved = dup(1);
+        if (saved >= 0) dup2(2, 1);
+        const int rc = g->nccl.CommInitAll(g->comm.data(), (int)dev.size(), dev.data());
+        fflush(stdout);
+        if (saved >= 0) { dup2(saved, 1); close(saved); }
+        if (rc == 0) g->use_nccl = true;
         else g->comm.clear();
     }
     if (dev.size() > 1 && !g->use_nccl) {
