@@ -326,6 +326,18 @@ __global__ void __launch_bounds__(kSpecSmemThreads, 1) spectrum_smem16_kernel(co
 // per tile and the stores leave in runs -- (3) per bucket, a 32 768-bin histogram in shared memory.  32 bytes of
 // scratch per packed group; the k-mers cross HBM twice (2 bytes each) instead of crossing the L2 atomics once.
 constexpr int kRadixThreads = 512;                            // = groups per tile = most buckets
+// bit 2o of the result set <=> the k-mer that starts at base o of the window touches a base that is not ACGT
+template <int K>
+__device__ __forceinline__ uint32_t smear_bad(uint64_t bad)
+{
+    int span = 1;
+#pragma unroll
+    for (int it = 0; it < 4; it++) {
+        const int step = span < K - span ? span : K - span;
+        if (step > 0) { bad |= bad >> (2 * step); span += step; }
+    }
+    return (uint32_t)bad & 0x55555555u;
+}
 template <int K>
 __device__ __forceinline__ bool radix_kmers(const uint64_t *__restrict__ groups, uint64_t gi, uint64_t &msb, uint64_t &bad)
 {
@@ -348,9 +360,10 @@ __global__ void __launch_bounds__(kRadixThreads) radix_count_kernel(const uint64
     for (uint64_t gi = g_begin + (uint64_t)blockIdx.x * kRadixThreads + threadIdx.x; gi < g_end; gi += (uint64_t)gridDim.x * kRadixThreads) {
         uint64_t msb, bad;
         if (!radix_kmers<K>(groups, gi, msb, bad)) continue;
+        const uint32_t inval = smear_bad<K>(bad);
 #pragma unroll
         for (int o = 0; o < 16; o++) {
-            if (((bad >> (2 * o)) & kmask) != 0) continue;
+            if ((inval >> (2 * o)) & 1u) continue;
             const uint32_t idx = (uint32_t)(msb >> (2 * (32 - o - K))) & (uint32_t)kmask;
             atomicAdd(&s_cnt[idx >> kSpecSmemLog], 1u);
         }
@@ -397,10 +410,11 @@ __global__ void __launch_bounds__(kRadixThreads) radix_scatter_kernel(const uint
         uint32_t br[16];
         uint32_t vm = 0;
         if (any) {
+            const uint32_t inval = smear_bad<K>(bad);
 #pragma unroll
             for (int o = 0; o < 16; o++) {
                 br[o] = 0;
-                if (((bad >> (2 * o)) & kmask) != 0) continue;
+                if ((inval >> (2 * o)) & 1u) continue;
                 const uint32_t idx = (uint32_t)(msb >> (2 * (32 - o - K))) & (uint32_t)kmask;
                 const uint32_t b = idx >> kSpecSmemLog;
                 br[o] = b | (atomicAdd(&s_cnt[b], 1u) << 9);
@@ -472,189 +486,11 @@ __global__ void __launch_bounds__(kSpecSmemThreads, 1) radix_hist_kernel(const u
         if (v) atomicAdd(counts + ((size_t)b << kSpecSmemLog) + i, (CT)v);
     }
 }
-// k = 10 .. 12, second generation of the partition ("write combining"): buckets = the high 2k - 16 bits of the index
-// (<= 256), payload = its low 16 bits.  Every WARP keeps, in shared memory, a 16-payload (32-byte) buffer per bucket; a
-// k-mer is appended with one shared-memory atomic on the warp's own fill counter, and the lane that fills a buffer
-// flushes it -- one global atomic on the bucket's cursor, two 16-byte stores, a whole 32-byte sector.  The in-tile sort
-// of the first generation (rank every k-mer, scan the tile's bucket counts, place, copy out: ~59 instructions per
-// k-mer, 10 ms for the 3.1 Gb genome) becomes ~20 instructions per k-mer.  Bucket stretches start on 32-byte
-// boundaries (the scan pads them); buffers left partly full at the end are written from the BACK of the stretch, so that
-// the 32-byte flushes at its front stay aligned whatever order the warps finish in.
-constexpr int kWcThreads = 512;
-constexpr int kWcWarps   = kWcThreads / 32;
-constexpr int kWcCap     = 16;                                // payloads per buffer = one 32-byte sector
-template <int K>
-__global__ void __launch_bounds__(kWcThreads, 1) radix_wc_scatter_kernel(const uint64_t *__restrict__ groups, uint64_t g_begin, uint64_t g_end,
-                                                                          unsigned long long *__restrict__ front, unsigned long long *__restrict__ back,
-                                                                          uint16_t *__restrict__ payload)
-{
-    constexpr uint32_t NB = 1u << (2 * K - 16);
-    constexpr uint64_t kmask = (1ull << (2 * K)) - 1ull;
-    extern __shared__ __align__(16) unsigned char wc_raw[];
-    // per warp: NB buffers of 16 payloads, then NB fill counters
-    uint16_t *buf = reinterpret_cast<uint16_t *>(wc_raw) + (size_t)(threadIdx.x >> 5) * NB * kWcCap;
-    uint32_t *cnt = reinterpret_cast<uint32_t *>(wc_raw + (size_t)kWcWarps * NB * kWcCap * sizeof(uint16_t)) + (size_t)(threadIdx.x >> 5) * NB;
-    const uint32_t lane = threadIdx.x & 31u, full = 0xffffffffu;
-    for (uint32_t i = lane; i < NB; i += 32) cnt[i] = 0;
-    __syncwarp();
-    const uint64_t n_warps = (uint64_t)gridDim.x * kWcWarps, wid = (uint64_t)blockIdx.x * kWcWarps + (threadIdx.x >> 5);
-    for (uint64_t g0 = g_begin + wid * 32; g0 < g_end; g0 += n_warps * 32) {          // 32 consecutive groups per warp step
-        const uint64_t gi = g0 + lane;
-        uint64_t msb = 0, bad = ~0ull;
-        const bool any = gi < g_end && radix_kmers<K>(groups, gi, msb, bad);
-        // smear: bit 2o set <=> some base of [o, o + K) is bad
-        if (any) {
-            int span = 1;
-#pragma unroll
-            for (int it = 0; it < 4; it++) {
-                const int step = span < K - span ? span : K - span;
-                if (step > 0) { bad |= bad >> (2 * step); span += step; }
-            }
-        }
-        const uint32_t vmask = any ? ~(uint32_t)bad & 0x55555555u : 0u;
-        if (!__any_sync(full, vmask != 0u)) continue;
-#pragma unroll 4
-        for (int o = 0; o < 16; o++) {
-            const uint32_t idx = (uint32_t)(msb >> (2 * (32 - o - K))) & (uint32_t)kmask;
-            const uint32_t b = idx >> 16;
-            bool pending = (vmask >> (2 * o)) & 1u;
-            for (;;) {                                          // one round unless a buffer fills up under this warp's hands
-                uint32_t slot = 0xffffu;
-                if (pending) slot = atomicAdd(&cnt[b], 1u);
-                if (slot < (uint32_t)kWcCap) { buf[b * kWcCap + slot] = (uint16_t)idx; pending = false; }
-                __syncwarp();
-                if (slot == (uint32_t)kWcCap - 1u) {            // this lane completed the buffer: it flushes it
-                    const unsigned long long at = atomicAdd(front + b, (unsigned long long)kWcCap);
-                    const uint4 *src = reinterpret_cast<const uint4 *>(buf + b * kWcCap);
-                    uint4       *dst = reinterpret_cast<uint4 *>(payload + at);
-                    const uint4  v0 = src[0], v1 = src[1];
-                    dst[0] = v0; dst[1] = v1;
-                    cnt[b] = 0;
-                }
-                __syncwarp();
-                if (!__any_sync(full, pending)) break;
-            }
-        }
-    }
-    // what is left in this warp's buffers: to the back of the stretches
-    __syncwarp();
-    for (uint32_t b = lane; b < NB; b += 32) {
-        const uint32_t n = cnt[b];
-        if (n) {
-            const unsigned long long end = atomicAdd(back + b, 0ull - (unsigned long long)n);       // returns the old end
-            for (uint32_t i = 0; i < n; i++) payload[end - n + i] = buf[b * kWcCap + i];
-        }
-    }
-}
-// bucket counts -> stretches that start on 32-byte boundaries: off[b] (start), front[b] = off[b], back[b] = off[b] + cnt[b]
-__global__ void __launch_bounds__(kRadixThreads) radix_wc_scan_kernel(const unsigned long long *__restrict__ cnt, unsigned long long *__restrict__ off,
-                                                                       unsigned long long *__restrict__ front, unsigned long long *__restrict__ back, uint32_t nb)
-{
-    __shared__ unsigned long long s[kRadixThreads];
-    const uint32_t t = threadIdx.x;
-    const unsigned long long mine = t < nb ? ((cnt[t] + (unsigned long long)kWcCap - 1ull) & ~((unsigned long long)kWcCap - 1ull)) : 0ull;
-    s[t] = mine;
-    __syncthreads();
-    for (uint32_t d = 1; d < kRadixThreads; d <<= 1) {
-        const unsigned long long v = t >= d ? s[t - d] : 0ull;
-        __syncthreads();
-        s[t] += v;
-        __syncthreads();
-    }
-    if (t < nb) { const unsigned long long ex = s[t] - mine; off[t] = ex; front[t] = ex; back[t] = ex + cnt[t]; }
-}
-// bucket counts with 16-bit payloads (bucket = index >> 16)
-template <int K>
-__global__ void __launch_bounds__(kRadixThreads) radix_wc_count_kernel(const uint64_t *__restrict__ groups, uint64_t g_begin, uint64_t g_end,
-                                                                        unsigned long long *__restrict__ bucket_cnt)
-{
-    constexpr uint32_t nb = 1u << (2 * K - 16);
-    constexpr uint64_t kmask = (1ull << (2 * K)) - 1ull;
-    // one counter set per warp (the lanes of a warp that hit one bucket are combined by the hardware's POPC.INC)
-    __shared__ uint32_t s_cnt[(kRadixThreads / 32) * nb > 4096 ? 4096 : (kRadixThreads / 32) * nb];
-    constexpr uint32_t copies = ((kRadixThreads / 32) * nb > 4096 ? 4096 : (kRadixThreads / 32) * nb) / nb;
-    for (uint32_t i = threadIdx.x; i < copies * nb; i += kRadixThreads) s_cnt[i] = 0;
-    __syncthreads();
-    uint32_t *mine = s_cnt + ((threadIdx.x >> 5) % copies) * nb;
-    for (uint64_t gi = g_begin + (uint64_t)blockIdx.x * kRadixThreads + threadIdx.x; gi < g_end; gi += (uint64_t)gridDim.x * kRadixThreads) {
-        uint64_t msb, bad;
-        if (!radix_kmers<K>(groups, gi, msb, bad)) continue;
-        {
-            int span = 1;
-#pragma unroll
-            for (int it = 0; it < 4; it++) {
-                const int step = span < K - span ? span : K - span;
-                if (step > 0) { bad |= bad >> (2 * step); span += step; }
-            }
-        }
-        const uint32_t vmask = ~(uint32_t)bad & 0x55555555u;
-#pragma unroll
-        for (int o = 0; o < 16; o++) {
-            if (!((vmask >> (2 * o)) & 1u)) continue;
-            const uint32_t idx = (uint32_t)(msb >> (2 * (32 - o - K))) & (uint32_t)kmask;
-            atomicAdd(&mine[idx >> 16], 1u);
-        }
-    }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < nb; i += kRadixThreads) {
-        unsigned long long v = 0;
-        for (uint32_t c = 0; c < copies; c++) v += s_cnt[c * nb + i];
-        if (v) atomicAdd(bucket_cnt + i, v);
-    }
-}
-// bucket (blockIdx.x / parts), part (blockIdx.x % parts): 65 536-bin histogram of a stretch of 16-bit payloads in the
-// packed 16-bit shared-memory counters of spec16 (exact drain; eight increments between checks)
-template <typename CT>
-__global__ void __launch_bounds__(kSpecSmemThreads, 1) radix_hist16_kernel(const uint16_t *__restrict__ payload, const unsigned long long *__restrict__ off,
-                                                                            const unsigned long long *__restrict__ cnt, uint32_t parts, CT *__restrict__ counts)
-{
-    extern __shared__ uint32_t s_words[];
-    const uint32_t b = blockIdx.x / parts, part = blockIdx.x % parts;
-    for (uint32_t i = threadIdx.x; i < (uint32_t)kSpec16Words; i += kSpecSmemThreads) s_words[i] = 0;
-    __syncthreads();
-    CT *mine = counts + ((size_t)b << 16);
-    const unsigned long long lo0 = off[b], n = cnt[b];
-    // parts are cut at multiples of 8 payloads (16 bytes); lo0 is 32-byte aligned
-    const unsigned long long n8 = (n + 7) / 8;
-    const unsigned long long a8 = n8 * part / parts, e8 = n8 * (part + 1) / parts;
-    const uint4 *p4 = reinterpret_cast<const uint4 *>(payload + lo0);
-    auto add = [&](uint32_t p) { return atomicAdd(&s_words[p & 0x7fffu], (p >> 15) * 0xffffu + 1u); };
-    auto drain = [&](uint32_t p) {
-        const uint32_t bit = (p >> 15) ? 0x80000000u : 0x8000u;
-        if (atomicAnd(&s_words[p & 0x7fffu], ~bit) & bit) atomicAdd(mine + p, (CT)32768);
-    };
-    for (unsigned long long i = a8 + threadIdx.x; i < e8; i += kSpecSmemThreads) {
-        const uint4 v = __ldg(p4 + i);
-        const uint32_t w[4] = { v.x, v.y, v.z, v.w };
-        const unsigned long long left = n - i * 8;               // payloads of this vector that exist (the last one may be partial)
-        uint32_t acc = 0;
-        if (left >= 8) {
-            const bool same = v.x == v.y && v.y == v.z && v.z == v.w && (v.x >> 16) == (v.x & 0xffffu);
-            if (same) {
-                // a run of one k-mer (low-complexity sequence): the lanes holding the same value elect one that adds for all
-                const uint32_t p = v.x & 0xffffu;
-                const uint32_t peers = __match_any_sync(__activemask(), p);
-                if ((threadIdx.x & 31u) == (uint32_t)__ffs((int)peers) - 1u)
-                    acc |= atomicAdd(&s_words[p & 0x7fffu], ((p >> 15) * 0xffffu + 1u) * 8u * (uint32_t)__popc(peers));
-            } else {
-#pragma unroll
-                for (int k = 0; k < 4; k++) { acc |= add(w[k] & 0xffffu); acc |= add(w[k] >> 16); }
-            }
-        } else {
-            for (uint32_t k = 0; k < (uint32_t)left; k++) acc |= add((w[k >> 1] >> (16 * (k & 1))) & 0xffffu);
-        }
-        if (acc & 0x80008000u) {
-            const uint32_t m = left >= 8 ? 8u : (uint32_t)left;
-            for (uint32_t k = 0; k < m; k++) drain((w[k >> 1] >> (16 * (k & 1))) & 0xffffu);
-        }
-    }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < (uint32_t)kSpec16Words; i += kSpecSmemThreads) {
-        const uint32_t v = s_words[i], lo16 = v & 0xffffu, hi16 = v >> 16;
-        if (lo16) atomicAdd(mine + i, (CT)lo16);
-        if (hi16) atomicAdd(mine + 0x8000u + i, (CT)hi16);
-    }
-}
+// (Measured and rejected, round 2: a "write combining" partition -- per-warp 32-byte buffers per bucket in shared
+// memory, appended with shared-memory atomics, flushed by the lane that fills one -- is exact but three times slower
+// than the in-tile sort above (38 ms against 12 ms at k = 12, 103 ms against 10 ms at k = 10 with its 16 buckets): every
+// flush needs a global atomic on the bucket's cursor and the whole warp waits for it at the next __syncwarp, about twice
+// per round of 32 k-mers.  profiles/r2_spectrum_radix_write_combining_experiment.json; git history has the kernels.)
 // u32 spectrum -> u64 output
 __global__ void __launch_bounds__(256) widen_kernel(const unsigned int *__restrict__ in, unsigned long long *__restrict__ out, uint64_t n)
 {

@@ -1015,45 +1015,18 @@ int pssgpu_kmer_spectrum_shard_device(pssgpu_ctx *ctx, int k, int shard, int n_s
     } else {
         CU(cudaMemsetAsync(d_counts, 0, bins * sizeof(uint64_t), ctx->stream));
     }
-    // k = 10 .. 12: radix partition through a scratch buffer (32 bytes per group); without the memory for it, L2 atomics.
-    // Second generation (default): 16-bit payloads, per-warp write-combining buffers, 65 536-bin bucket histograms;
-    // PSSGPU_SPECTRUM_RADIX1 selects the first one (in-tile sort, 15-bit payloads) for comparison.
+    // k = 10 .. 12: radix partition through a scratch buffer (32 bytes per group); without the memory for it, L2 atomics
     uint16_t *d_payload = nullptr;
-    unsigned long long *d_rad = nullptr;                   // bucket counts | offsets | cursors
-    const bool     wc = !getenv("PSSGPU_SPECTRUM_RADIX1");
-    const uint32_t rad_nb = (k >= 10 && k <= 12) ? (1u << (2 * k - (wc ? kSpec16Log : kSpecSmemLog))) : 0u;
+    unsigned long long *d_rad = nullptr;                   // bucket counts | offsets (nb + 1) | cursors
+    const uint32_t rad_nb = (k >= 10 && k <= 12) ? (1u << (2 * k - kSpecSmemLog)) : 0u;
     if (rad_nb && g1 > g0 && !getenv("PSSGPU_SPECTRUM_ATOMICS")) {
-        if (cudaMalloc(&d_payload, ((g1 - g0) * 16 + (size_t)rad_nb * kWcCap) * sizeof(uint16_t) + 64) != cudaSuccess) { cudaGetLastError(); d_payload = nullptr; }
-        else if (cudaMalloc(&d_rad, (4 * (size_t)rad_nb + 2) * sizeof(unsigned long long)) != cudaSuccess) {
+        if (cudaMalloc(&d_payload, (g1 - g0) * 16 * sizeof(uint16_t) + 64) != cudaSuccess) { cudaGetLastError(); d_payload = nullptr; }
+        else if (cudaMalloc(&d_rad, (3 * (size_t)rad_nb + 2) * sizeof(unsigned long long)) != cudaSuccess) {
             cudaGetLastError(); cudaFree(d_payload); d_payload = nullptr; d_rad = nullptr;
         }
     }
     time_begin(ctx, (g1 - g0) * sizeof(uint64_t));
-    if (d_payload && wc) {
-        unsigned long long *cnt = d_rad, *off = d_rad + rad_nb, *front = d_rad + 2 * (size_t)rad_nb, *back = d_rad + 3 * (size_t)rad_nb;
-        cudaMemsetAsync(d_rad, 0, (4 * (size_t)rad_nb + 2) * sizeof(unsigned long long), ctx->stream);
-        const unsigned cgrid = (unsigned)std::min<uint64_t>((g1 - g0 + kRadixThreads - 1) / kRadixThreads, (uint64_t)ctx->sm_count * 4);
-        const unsigned sgrid = (unsigned)std::min<uint64_t>((g1 - g0 + kWcThreads - 1) / kWcThreads, (uint64_t)ctx->sm_count);
-        const uint32_t parts = std::max<uint32_t>(1u, (2u * (uint32_t)ctx->sm_count + rad_nb - 1) / rad_nb);
-        const size_t   ssmem = (size_t)kWcWarps * rad_nb * (kWcCap * sizeof(uint16_t) + sizeof(uint32_t));
-        const size_t   hsmem = (size_t)kSpec16Words * sizeof(uint32_t);
-#define PSS_RADIX_WC(K_)                                                                                               \
-        do {                                                                                                           \
-            cudaFuncSetAttribute(radix_wc_scatter_kernel<K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem); \
-            radix_wc_count_kernel<K_><<<cgrid, kRadixThreads, 0, ctx->stream>>>(ctx->d_groups, g0, g1, cnt);          \
-            radix_wc_scan_kernel<<<1, kRadixThreads, 0, ctx->stream>>>(cnt, off, front, back, rad_nb);                \
-            radix_wc_scatter_kernel<K_><<<sgrid, kWcThreads, ssmem, ctx->stream>>>(ctx->d_groups, g0, g1, front, back, d_payload); \
-        } while (0)
-        if (k == 10) PSS_RADIX_WC(10); else if (k == 11) PSS_RADIX_WC(11); else PSS_RADIX_WC(12);
-#undef PSS_RADIX_WC
-        if (narrow) {
-            cudaFuncSetAttribute(radix_hist16_kernel<unsigned int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem);
-            radix_hist16_kernel<unsigned int><<<rad_nb * parts, kSpecSmemThreads, hsmem, ctx->stream>>>(d_payload, off, cnt, parts, d_narrow);
-        } else {
-            cudaFuncSetAttribute(radix_hist16_kernel<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem);
-            radix_hist16_kernel<unsigned long long><<<rad_nb * parts, kSpecSmemThreads, hsmem, ctx->stream>>>(d_payload, off, cnt, parts, (unsigned long long *)d_counts);
-        }
-    } else if (d_payload) {
+    if (d_payload) {
         unsigned long long *cnt = d_rad, *off = d_rad + rad_nb, *cur = d_rad + 2 * (size_t)rad_nb + 1;
         cudaMemsetAsync(d_rad, 0, (3 * (size_t)rad_nb + 2) * sizeof(unsigned long long), ctx->stream);
         const unsigned rgrid = (unsigned)std::min<uint64_t>((g1 - g0 + kRadixThreads - 1) / kRadixThreads, (uint64_t)ctx->sm_count * 4);
