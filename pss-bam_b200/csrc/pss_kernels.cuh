@@ -836,13 +836,93 @@ __device__ __forceinline__ uint32_t ballot_bits(uint32_t word, uint32_t mask)
     return r;
 }
 
-// The two count tables of one warp-load of records, without atomics: lane l
-// owns cell (l & 15) of table (l >> 4); five ballots per table and row turn
-// "which lanes hit my cell" into a popcount.  acc[] packs two rows per
-// register (16-bit partial sums).  All 32 lanes must be converged.
+// ---------------------------------------------------------------------------
+// The two count tables of one warp-load of records, without atomics.
+//
+// What a record adds is 5 bits per table and row (two bits of reference code, two of read code, "counts").  Round 1
+// fetched every one of the 2 x 17 x 5 bit planes with its own ballot (LOP3 + VOTE, then IMAD picks: 37 instructions
+// per row); now the warp TRANSPOSES them: five 32 x 32 bit-matrix transposes across the lanes (SHFL + PRMT for the
+// byte-granular steps, SHFL + SHF + LOP3 below that: 13 instructions each) hand lane 2r + t the five planes -- one bit
+// per record of the warp-load -- of row r of table t, and the lane counts its 16 cells with 20 LOP3 + 16 POPC into
+// eight registers of packed 16-bit sums.  About 140 instructions per 16 rows of both tables instead of 590.
+// Rows 16 and 17 (-r 15 has 17 rows) still go the ballot way: lane l owns cell (l & 15) of table (l >> 4).
+// All 32 lanes must be converged.
+// ---------------------------------------------------------------------------
+#ifndef PSS_TALLY_TRANSPOSE
+#define PSS_TALLY_TRANSPOSE 1
+#endif
+struct XposeConsts {
+    uint32_t sel16, sel8, s4, s2, s1, r4, r2, r1;
+};
+__device__ __forceinline__ XposeConsts xpose_consts(uint32_t lane)
+{
+    XposeConsts c;
+    c.sel16 = (lane & 16u) ? 0x3276u : 0x5410u;
+    c.sel8 = (lane & 8u) ? 0x3715u : 0x6240u;
+    c.s4 = (lane & 4u) ? 0xf0f0f0f0u : 0x0f0f0f0fu;  c.r4 = (lane & 4u) ? 28u : 4u;
+    c.s2 = (lane & 2u) ? 0xccccccccu : 0x33333333u;  c.r2 = (lane & 2u) ? 30u : 2u;
+    c.s1 = (lane & 1u) ? 0xaaaaaaaau : 0x55555555u;  c.r1 = (lane & 1u) ? 31u : 1u;
+    return c;
+}
+// bit j of lane i's word <-> bit i of lane j's word.  One step per bit of the index: the lower lane of a pair keeps
+// the positions whose index bit is clear and takes its partner's into the others, the upper lane the other way round.
+__device__ __forceinline__ uint32_t xpose32(uint32_t x, const XposeConsts &c)
+{
+    const uint32_t full = 0xffffffffu;
+    uint32_t       t;
+    t = __shfl_xor_sync(full, x, 16);  x = __byte_perm(x, t, c.sel16);
+    t = __shfl_xor_sync(full, x, 8);   x = __byte_perm(x, t, c.sel8);
+    t = __shfl_xor_sync(full, x, 4);   x = lop3<0xE4>(x, __funnelshift_l(t, t, c.r4), c.s4);      // (x & s) | (rot(t) & ~s)
+    t = __shfl_xor_sync(full, x, 2);   x = lop3<0xE4>(x, __funnelshift_l(t, t, c.r2), c.s2);
+    t = __shfl_xor_sync(full, x, 1);   x = lop3<0xE4>(x, __funnelshift_l(t, t, c.r1), c.s1);
+    return x;
+}
+// rows [16 set, 16 set + 16) of both tables: acc[0..7] = the 16 cells of (table lane & 1, row 16 set + lane / 2)
+__device__ __forceinline__ void tally_set16(uint32_t aref, uint32_t aread, uint32_t abad, uint32_t bref, uint32_t bread, uint32_t bbad,
+                                            uint32_t row_mask, const XposeConsts &xc, uint32_t *acc, uint32_t one)
+{
+    constexpr uint32_t E = 0x55555555u;
+    // bit 2r: table a, bit 2r + 1: table b -- one word per plane
+    const uint32_t X0 = xpose32(lop3<0xE4>(aref, bref << 1, E), xc), X1 = xpose32(lop3<0xE4>(aref >> 1, bref, E), xc);
+    const uint32_t Y0 = xpose32(lop3<0xE4>(aread, bread << 1, E), xc), Y1 = xpose32(lop3<0xE4>(aread >> 1, bread, E), xc);
+    const uint32_t ga = ~abad & row_mask, gb = ~bbad & row_mask;
+    const uint32_t G = xpose32(ga | (gb << 1), xc);
+    uint32_t q[4];
+    q[0] = lop3<0x10>(G, Y1, Y0); q[1] = lop3<0x20>(G, Y1, Y0); q[2] = lop3<0x40>(G, Y1, Y0); q[3] = lop3<0x80>(G, Y1, Y0);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {                            // cell = read * 4 + ref (pss-bam.c:24-35)
+        const uint32_t n0 = (uint32_t)__popc(lop3<0x10>(q[k], X1, X0)), n1 = (uint32_t)__popc(lop3<0x20>(q[k], X1, X0));
+        const uint32_t n2 = (uint32_t)__popc(lop3<0x40>(q[k], X1, X0)), n3 = (uint32_t)__popc(lop3<0x80>(q[k], X1, X0));
+        acc[2 * k] = imad(n1, 65536u, imad(n0, one, acc[2 * k]));
+        acc[2 * k + 1] = imad(n3, 65536u, imad(n2, one, acc[2 * k + 1]));
+    }
+}
 template <int NACC, int ROWS>
 __device__ __forceinline__ void tally_rows(const PssStreams &st, uint32_t (&acc)[NACC ? NACC : 1], int rows, uint32_t lane, uint32_t one)
 {
+    static_assert(NACC == 0 || NACC == 9 || NACC == 16, "9: rows 0..15 transposed + rows 16, 17 by ballots; 16: two transposed sets");
+#if PSS_TALLY_TRANSPOSE
+    constexpr uint32_t E = 0x55555555u;
+    const XposeConsts xc = xpose_consts(lane);
+    {
+        const int      n0 = ROWS ? (ROWS < 16 ? ROWS : 16) : (rows < 16 ? rows : 16);
+        const uint32_t m0 = n0 >= 16 ? E : (((1u << (2 * n0)) - 1u) & E);
+        tally_set16((uint32_t)st.a_ref, (uint32_t)st.a_read, (uint32_t)st.a_bad, (uint32_t)st.b_ref, (uint32_t)st.b_read, (uint32_t)st.b_bad,
+                    m0, xc, acc, one);
+    }
+    if (NACC == 16) {
+        if (rows > 16) {                                      // warp uniform
+            const int      n1 = rows - 16;
+            const uint32_t m1 = n1 >= 16 ? E : (((1u << (2 * n1)) - 1u) & E);
+            tally_set16((uint32_t)(st.a_ref >> 32), (uint32_t)(st.a_read >> 32), (uint32_t)(st.a_bad >> 32), (uint32_t)(st.b_ref >> 32),
+                        (uint32_t)(st.b_read >> 32), (uint32_t)(st.b_bad >> 32), m1, xc, acc + 8, one);
+        }
+        return;
+    }
+    constexpr int kFirstBallotRow = 16;
+#else
+    constexpr int kFirstBallotRow = 0;
+#endif
     const uint32_t tbi = lane >> 4;                           // which table this lane counts for
     const uint32_t neg1 = 0u - one;
     const uint32_t cell = lane & 15u;
@@ -857,7 +937,7 @@ __device__ __forceinline__ void tally_rows(const PssStreams &st, uint32_t (&acc)
     // on the idle FMA pipe instead of a SEL on the ALU pipe (the pipe this kernel is bound by)
     auto pick = [&](uint32_t a, uint32_t b) { return imad(tbi, imad(a, neg1, b), a); };
 #pragma unroll
-    for (int j = 0; j < 2 * NACC; j++) {
+    for (int j = kFirstBallotRow; j < 2 * NACC; j++) {
         if (ROWS ? j >= ROWS : j >= rows) break;              // ROWS: the row count as a compile-time constant (0: run time)
         const int      h = j >> 4;
         const uint32_t m0 = 1u << (2 * (j & 15)), m1 = 2u << (2 * (j & 15));
@@ -874,9 +954,26 @@ __device__ __forceinline__ void tally_rows(const PssStreams &st, uint32_t (&acc)
 template <int NACC>
 __device__ __forceinline__ void flush_acc(uint32_t (&acc)[NACC ? NACC : 1], int rows, uint32_t lane, uint32_t *table)
 {
+#if PSS_TALLY_TRANSPOSE
+    {
+        const uint32_t tb = lane & 1u, row = lane >> 1;
+#pragma unroll
+        for (int h = 0; h < (NACC == 16 ? 2 : 1); h++) {
+            if ((int)row + 16 * h >= rows) break;
+#pragma unroll
+            for (int c = 0; c < 16; c++) {
+                const uint32_t v = (acc[8 * h + (c >> 1)] >> (16 * (c & 1))) & 0xffffu;
+                if (v) atomicAdd(&table[tb * 512 + (row + 16 * h) * 16 + c], v);
+            }
+        }
+    }
+    constexpr int kFirstBallotRow = NACC == 16 ? 32 : 16;
+#else
+    constexpr int kFirstBallotRow = 0;
+#endif
     const uint32_t tb = lane >> 4, cell = lane & 15u;
 #pragma unroll
-    for (int j = 0; j < 2 * NACC; j++) {
+    for (int j = kFirstBallotRow; j < 2 * NACC; j++) {
         if (j >= rows) break;
         const uint32_t v = (acc[j >> 1] >> (16 * (j & 1))) & 0xffffu;
         if (v) atomicAdd(&table[tb * 512 + j * 16 + cell], v);
