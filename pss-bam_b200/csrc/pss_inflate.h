@@ -16,9 +16,12 @@
 //   * the decode tables of a dynamic block are filled by all lanes together.
 // Parallelism across the GPU comes from the ~10^5 independent BGZF blocks of a batch.
 //
-// Tables (per warp, in shared memory; 3.7 KB): a 10-bit first-level table for literal/length codes and an 8-bit one for
-// distance codes (entry = symbol << 4 | code length; 0 = longer code), and for the rare longer codes the canonical
-// count/sorted-symbol arrays walked bit by bit.
+// Tables (per warp, in shared memory): 32-bit entries that carry everything the symbol loop needs -- the literal byte
+// or the base of a length / distance together with the code length and "code length + extra bits" -- so that a symbol
+// costs one look-up and a match needs no second table (RFC 1951 3.2.5 is folded in when a block's tables are built).
+// Literal/length codes longer than the first level go through second-level tables behind it (zlib's scheme); the
+// canonical count/sorted-symbol arrays, walked bit by bit, remain as the fallback (second-level area full, long distance
+// codes).
 #pragma once
 
 #include <stdint.h>
@@ -33,14 +36,28 @@
 
 namespace pssgpu {
 
-constexpr int kInfLitBits  = 10;
+#ifndef PSS_INF_LIT_BITS
+#define PSS_INF_LIT_BITS 10
+#endif
+constexpr int kInfLitBits  = PSS_INF_LIT_BITS;               // first-level bits of the literal/length table
 constexpr int kInfDistBits = 8;
+#ifndef PSS_INF_LIT_SUB
+#define PSS_INF_LIT_SUB (PSS_INF_LIT_BITS >= 10 ? 320 : 352)
+#endif
+constexpr int kInfLitSub   = PSS_INF_LIT_SUB;                // second-level entries (zlib's worst case: 1332 / 852 in all;
+                                                             // a block that needs more takes the canonical walk)
 constexpr int kInfMaxLit   = 288;
 constexpr int kInfMaxDist  = 32;
 
+// table entry: bits 0..4 code length (second level: of the whole code), bit 5 literal, bit 6 second-level pointer,
+// bit 7 special, bits 8..12 code length + extra bits (pointer: bits of the second-level index), bits 16..31 value:
+// literal byte / base length / base distance / start of the second-level table / kind of special
+constexpr uint32_t kInfELit = 0x20u, kInfESub = 0x40u, kInfESpecial = 0x80u;
+constexpr uint32_t kInfSpEnd = 0u, kInfSpWalk = 1u, kInfSpInvalid = 2u;      // special: end of block / canonical walk / no such code
+
 struct InflateTables {                       // one per warp
-    uint16_t lit_lut[1 << kInfLitBits];      // symbol << 4 | length, 0: code longer than kInfLitBits
-    uint16_t dist_lut[1 << kInfDistBits];
+    uint32_t lit_lut[(1 << kInfLitBits) + kInfLitSub];
+    uint32_t dist_lut[1 << kInfDistBits];
     uint16_t lit_sorted[kInfMaxLit];         // symbols in canonical order (by code length, then symbol)
     uint16_t dist_sorted[kInfMaxDist];
     uint16_t lit_count[16], dist_count[16];  // codes per length
@@ -138,128 +155,6 @@ struct InfBits {
     PSS_IHD uint32_t bytes_used(uint32_t mis) const { return next * 4u - mis - (uint32_t)(cnt >> 3); }
 };
 
-// ---- table set-up ---------------------------------------------------------------------------------------------------
-// Canonical Huffman code of `n` symbols with code lengths lens[0..n): fills count[], sorted[] and the first-level
-// table lut (2^bits entries).  Returns false for an over-subscribed or (non-trivially) incomplete code.  All lanes
-// call it together; the symbol loop is uniform, the table fill is spread over the lanes.
-PSS_IHD_COLD bool inf_build(const uint8_t *lens, int n, uint16_t *count, uint16_t *sorted, uint16_t *lut, int bits, bool flag_literals = false,
-                            uint32_t *resume_first = nullptr, uint32_t *resume_index = nullptr)
-{
-    const int lane = InfLanes::lane(), W = InfLanes::width();
-    for (int i = lane; i < 16; i += W) count[i] = 0;
-    for (int i = lane; i < (1 << bits); i += W) lut[i] = 0;
-    InfLanes::sync();
-    if (lane == 0)
-        for (int s = 0; s < n; s++) count[lens[s]]++;
-    InfLanes::sync();
-    // offsets / first codes per length (uniform, in registers)
-    uint32_t offs[16], code[16];
-    int      left = 1;
-    bool     ok = true;
-    {
-        uint32_t o = 0, c = 0;
-        offs[0] = 0; code[0] = 0;
-        for (int l = 1; l < 16; l++) {
-            left <<= 1;
-            left -= (int)count[l];
-            if (left < 0) ok = false;
-            offs[l] = o; code[l] = c;
-            o += count[l];
-            c = (c + count[l]) << 1;
-        }
-    }
-    if (resume_first && lane == 0) {           // canonical walk (inf_long) after `bits` levels without a hit
-        uint32_t f = 0, ix = 0;
-        for (int l = 1; l <= bits; l++) { ix += count[l]; f = (f + count[l]) << 1; }
-        *resume_first = f;
-        *resume_index = ix;
-    }
-    const int used = n - (int)count[0];
-    // incomplete codes are legal only in the one-code case (a single distance code, RFC 1951 3.2.7) -- and zlib also
-    // lets a block with no distance code at all pass
-    if (left > 0 && used > 1) ok = false;
-    if (!ok) return false;
-    for (int s = 0; s < n; s++) {
-        const int l = lens[s];
-        if (l == 0) continue;                                           // uniform
-        const uint32_t c = code[l]++;
-        if (lane == 0) sorted[offs[l]] = (uint16_t)s;
-        offs[l]++;
-        if (l <= bits) {
-#if defined(__CUDA_ARCH__)
-            const uint32_t r = __brev(c) >> (32 - l);
-#else
-            uint32_t r = 0;
-            for (int b = 0; b < l; b++) r |= ((c >> b) & 1u) << (l - 1 - b);
-#endif
-            // literal/length table: bit 15 marks a literal, so that the symbol loop decides "literal, resolved" with one test
-            const uint16_t e = (uint16_t)((s << 4) | l | ((flag_literals && s < 256) ? 0x8000 : 0));
-            for (int k = lane; k < (1 << (bits - l)); k += W) lut[r + ((uint32_t)k << l)] = e;
-        }
-    }
-    InfLanes::sync();
-    return true;
-}
-
-// one symbol of a canonical code that the first-level table did not resolve (or any symbol): bit by bit
-PSS_IHD_COLD int inf_slow(uint32_t bits, const uint16_t *count, const uint16_t *sorted, int &len_out)
-{
-    int      code = 0, first = 0, index = 0;
-    for (int l = 1; l <= 15; l++) {
-        code |= (int)(bits & 1u);
-        bits >>= 1;
-        const int c = count[l];
-        if (code - c < first) { len_out = l; return sorted[index + (code - first)]; }
-        index += c;
-        first += c;
-        first <<= 1;
-        code <<= 1;
-    }
-    len_out = 15;
-    return -1;
-}
-
-PSS_IHD int inf_decode(InfBits &B, const uint16_t *lut, int bits, const uint16_t *count, const uint16_t *sorted)
-{
-    const uint32_t e = lut[B.peek(bits)];
-    if (e & 15u) {
-        B.drop((int)(e & 15u));
-        return (int)(e >> 4);
-    }
-    int       l;
-    const int s = inf_slow((uint32_t)B.buf, count, sorted, l);
-    B.drop(l);
-    return s;
-}
-
-// A code longer than the first-level table: the canonical walk resumed behind the `bits` levels the table covers
-// (their state was computed when the table was built), at most 15 - bits steps.  `word` = the next 32 bits of the stream.
-PSS_IHD int inf_long(uint32_t word, const uint16_t *count, const uint16_t *sorted, uint32_t first0, uint32_t index0, int bits, int &len_out)
-{
-#if defined(__CUDA_ARCH__)
-    int code = (int)((__brev(word) >> (32 - bits)) << 1);
-#else
-    uint32_t rv = 0;
-    for (int b = 0; b < bits; b++) rv |= ((word >> b) & 1u) << (bits - 1 - b);
-    int code = (int)(rv << 1);
-#endif
-    int      first = (int)first0, index = (int)index0;
-    uint32_t rest = word >> bits;
-#pragma unroll
-    for (int l = bits + 1; l <= 15; l++) {
-        code |= (int)(rest & 1u);
-        rest >>= 1;
-        const int c = count[l];
-        if (code - c < first) { len_out = l; return sorted[index + (code - first)]; }
-        index += c;
-        first += c;
-        first <<= 1;
-        code <<= 1;
-    }
-    len_out = 15;
-    return -1;
-}
-
 // base | extra bits << 16 of the length symbols 257..285 and the distance symbols 0..29 (RFC 1951 3.2.5)
 #if defined(__CUDACC__)
 #define PSS_INF_CONST static __device__ __constant__
@@ -284,150 +179,381 @@ PSS_IHD uint32_t inf_len_tab(int s) { return kInfLenTab[s]; }
 PSS_IHD uint32_t inf_dist_tab(int s) { return kInfDistTab[s]; }
 #endif
 
-// length / distance bases and extra bits (RFC 1951 3.2.5), packed: base | extra << 16
-PSS_IHD uint32_t inf_len_code(int s)        // s = symbol - 257, 0..28
+// ---- table entries ----------------------------------------------------------------------------------------------------
+enum : int { kInfKindPlain = 0, kInfKindLit = 1, kInfKindDist = 2 };      // what the symbols of a code are
+// the entry of symbol s with code length l
+PSS_IHD uint32_t inf_entry(int kind, int s, int l)
 {
-    // extra bits: 0 for s < 8, then (s - 4) / 4; code 28 is the literal 258
-    const uint32_t eb = s < 8 ? 0u : (uint32_t)((s - 4) >> 2);
-    const uint32_t base = s < 8 ? (uint32_t)(3 + s) : (uint32_t)(3 + ((4 + (s & 3)) << eb));
-    return s == 28 ? 258u : (base | (eb << 16));
+    const uint32_t ul = (uint32_t)l;
+    if (kind == kInfKindPlain) return ((uint32_t)s << 16) | ul;
+    if (kind == kInfKindLit) {
+        if (s < 256) return ((uint32_t)s << 16) | kInfELit | ul;
+        if (s == 256) return (kInfSpEnd << 16) | kInfESpecial | ul;
+        if (s > 285) return (kInfSpInvalid << 16) | kInfESpecial | ul;
+        const uint32_t lc = inf_len_tab(s - 257);
+        return ((lc & 0xffffu) << 16) | ((ul + (lc >> 16)) << 8) | ul;
+    }
+    if (s > 29) return (kInfSpInvalid << 16) | kInfESpecial | ul;
+    const uint32_t dc = inf_dist_tab(s);
+    return ((dc & 0xffffu) << 16) | ((ul + (dc >> 16)) << 8) | ul;
 }
-PSS_IHD uint32_t inf_dist_code(int s)       // 0..29
+PSS_IHD uint32_t inf_brev(uint32_t c, int l)      // the l-bit code c in the order its bits arrive
 {
-    const uint32_t eb = s < 4 ? 0u : (uint32_t)((s - 2) >> 1);
-    const uint32_t base = s < 4 ? (uint32_t)(1 + s) : (uint32_t)(1 + ((2 + (s & 1)) << eb));
-    return base | (eb << 16);
+#if defined(__CUDA_ARCH__)
+    return __brev(c) >> (32 - l);
+#else
+    uint32_t r = 0;
+    for (int b = 0; b < l; b++) r |= ((c >> b) & 1u) << (l - 1 - b);
+    return r;
+#endif
+}
+
+// ---- table set-up ---------------------------------------------------------------------------------------------------
+// Canonical Huffman code of `n` symbols with code lengths lens[0..n): fills count[], sorted[] and the table lut:
+// 2^bits first-level entries and, when sub_cap > 0, second-level tables for the longer codes in the sub_cap entries
+// behind them.  First-level slots that no short code claims are left as "walk" entries (canonical walk: it finds the
+// long codes no second-level table was built for, and rejects bit patterns that are no code at all).  Returns false
+// for an over-subscribed or (non-trivially) incomplete code.  All lanes call it together; the symbol loops are uniform,
+// the table fills are spread over the lanes.
+PSS_IHD_COLD bool inf_build(const uint8_t *lens, int n, uint16_t *count, uint16_t *sorted, uint32_t *lut, int bits, int kind, int sub_cap,
+                            uint32_t *resume_first = nullptr, uint32_t *resume_index = nullptr)
+{
+    const int lane = InfLanes::lane(), W = InfLanes::width();
+    for (int i = lane; i < 16; i += W) count[i] = 0;
+    for (int i = lane; i < (1 << bits) + sub_cap; i += W) lut[i] = (kInfSpWalk << 16) | kInfESpecial;
+    InfLanes::sync();
+    if (lane == 0)
+        for (int s = 0; s < n; s++) count[lens[s]]++;
+    InfLanes::sync();
+    // offsets / first codes per length (uniform)
+    uint32_t offs[16], code[16];
+    int      left = 1, max_len = 0;
+    bool     ok = true;
+    {
+        uint32_t o = 0, c = 0;
+        offs[0] = 0; code[0] = 0;
+        for (int l = 1; l < 16; l++) {
+            left <<= 1;
+            left -= (int)count[l];
+            if (left < 0) ok = false;
+            offs[l] = o; code[l] = c;
+            o += count[l];
+            c = (c + count[l]) << 1;
+            if (count[l]) max_len = l;
+        }
+    }
+    if (resume_first && lane == 0) {           // canonical walk (inf_long) after `bits` levels without a hit
+        uint32_t f = 0, ix = 0;
+        for (int l = 1; l <= bits; l++) { ix += count[l]; f = (f + count[l]) << 1; }
+        *resume_first = f;
+        *resume_index = ix;
+    }
+    const int used = n - (int)count[0];
+    // incomplete codes are legal only in the one-code case (a single distance code, RFC 1951 3.2.7) -- and zlib also
+    // lets a block with no distance code at all pass
+    if (left > 0 && used > 1) ok = false;
+    if (!ok) return false;
+    // second-level tables, first pass (uniform, no table reads): codes longer than `bits` in canonical order -- their
+    // left-aligned values grow, so the codes that share their first `bits` bits are neighbours and the last of them is
+    // the longest: one table of 2^(that length - bits) entries per distinct prefix
+    if (sub_cap > 0 && max_len > bits) {
+        int      cur_p = -1, cur_len = 0, next_free = 0;
+        bool     full = false;
+        for (int l = bits + 1; l <= max_len; l++) {
+            for (uint32_t k = 0; k < count[l]; k++) {
+                const int p = (int)(inf_brev(code[l] + k, l) & ((1u << bits) - 1u));
+                if (p != cur_p) {
+                    if (cur_p >= 0 && !full) {
+                        const int sb = cur_len - bits;
+                        if (next_free + (1 << sb) <= sub_cap) {
+                            if (lane == 0) lut[cur_p] = ((uint32_t)((1 << bits) + next_free) << 16) | ((uint32_t)sb << 8) | kInfESub | (uint32_t)bits;
+                            next_free += 1 << sb;
+                        } else full = true;                    // this and the remaining prefixes stay "walk"
+                    }
+                    cur_p = p;
+                }
+                cur_len = l;
+            }
+        }
+        if (cur_p >= 0 && !full) {
+            const int sb = cur_len - bits;
+            if (next_free + (1 << sb) <= sub_cap && lane == 0)
+                lut[cur_p] = ((uint32_t)((1 << bits) + next_free) << 16) | ((uint32_t)sb << 8) | kInfESub | (uint32_t)bits;
+        }
+        InfLanes::sync();
+    }
+    for (int s = 0; s < n; s++) {
+        const int l = lens[s];
+        if (l == 0) continue;                                           // uniform
+        const uint32_t c = code[l]++;
+        if (lane == 0) sorted[offs[l]] = (uint16_t)s;
+        offs[l]++;
+        const uint32_t r = inf_brev(c, l);
+        const uint32_t e = inf_entry(kind, s, l);
+        if (l <= bits) {
+            for (int k = lane; k < (1 << (bits - l)); k += W) lut[r + ((uint32_t)k << l)] = e;
+        } else if (sub_cap > 0) {
+            const uint32_t root = lut[r & ((1u << bits) - 1u)];          // written before the last sync
+            if (root & kInfESub) {
+                const int      sb = (int)((root >> 8) & 31u), rest = l - bits;
+                const uint32_t base = (root >> 16) + (r >> bits);
+                for (int k = lane; k < (1 << (sb - rest)); k += W) lut[base + ((uint32_t)k << rest)] = e;
+            }
+        }
+    }
+    InfLanes::sync();
+    return true;
+}
+
+// one symbol of a canonical code that the first-level table did not resolve (or any symbol): bit by bit
+PSS_IHD_COLD int inf_slow(uint32_t bits, const uint16_t *count, const uint16_t *sorted, int &len_out)
+{
+    int      code = 0, first = 0, index = 0;
+    for (int l = 1; l <= 15; l++) {
+        code |= (int)(bits & 1u);
+        bits >>= 1;
+        const int c = count[l];
+        if (code - c < first) { len_out = l; return sorted[index + (code - first)]; }
+        index += c;
+        first += c;
+        first <<= 1;
+        code <<= 1;
+    }
+    len_out = 15;
+    return -1;
+}
+
+// a symbol of a small "plain" code (the code-length code of a dynamic block)
+PSS_IHD int inf_decode(InfBits &B, const uint32_t *lut, int bits, const uint16_t *count, const uint16_t *sorted)
+{
+    const uint32_t e = lut[B.peek(bits)];
+    if (!(e & kInfESpecial)) {
+        B.drop((int)(e & 31u));
+        return (int)(e >> 16);
+    }
+    int       l;
+    const int s = inf_slow((uint32_t)B.buf, count, sorted, l);
+    B.drop(l);
+    return s;
+}
+
+// A code longer than the first-level table: the canonical walk resumed behind the `bits` levels the table covers
+// (their state was computed when the table was built), at most 15 - bits steps.  `word` = the next 32 bits of the stream
+// (at least 15 of them valid).
+PSS_IHD_COLD int inf_long(uint32_t word, const uint16_t *count, const uint16_t *sorted, uint32_t first0, uint32_t index0, int bits, int &len_out)
+{
+    int code = (int)(inf_brev(word & ((1u << bits) - 1u), bits) << 1);
+    int      first = (int)first0, index = (int)index0;
+    uint32_t rest = word >> bits;
+    for (int l = bits + 1; l <= 15; l++) {
+        code |= (int)(rest & 1u);
+        rest >>= 1;
+        const int c = count[l];
+        if (code - c < first) { len_out = l; return sorted[index + (code - first)]; }
+        index += c;
+        first += c;
+        first <<= 1;
+        code <<= 1;
+    }
+    len_out = 15;
+    return -1;
 }
 
 // ---- the symbol loop ---------------------------------------------------------------------------------------------------
 // Literal/length + distance symbols of one DEFLATE block up to its end-of-block code, warp uniform.  This is where the
 // time goes: the loop is a chain of dependent steps (bit buffer -> table index -> shared-memory load -> code length ->
-// bit buffer), and with tens of warps per SM it is bound by instruction issue -- so the literal path is kept to a
-// handful of instructions: the first-level tables are read through their 32-bit shared-memory address (no generic
-// pointer arithmetic in the loop), the output position is one register, errors leave through one exit.
+// bit buffer), and with tens of warps per SM it is bound by instruction issue -- so it is written for few instructions:
+//   * one refill guarantees 32 valid bits; two literals, or a literal and a length with its extra bits, or a distance
+//     with its extra bits are taken from those 32 bits with 32-bit shifts, and the 64-bit buffer is advanced once;
+//   * the table entry is the decoded symbol (byte / base / bit counts): no second look-up, no arithmetic on symbols;
+//   * while at least 260 bytes of output are left nothing checks the output bound (a step writes at most 1 + 258);
+//     the last bytes of a block go through the same code with the checks compiled in;
+//   * the first-level tables are read through their 32-bit shared-memory address, errors leave through one exit.
 #if defined(__CUDA_ARCH__)
 struct InfLut {
-    uint32_t a;                                              // shared-space address of a uint16_t table
-    __device__ __forceinline__ explicit InfLut(const uint16_t *p) : a((uint32_t)__cvta_generic_to_shared(p)) {}
+    uint32_t a;                                              // shared-space address of a uint32_t table
+    __device__ __forceinline__ explicit InfLut(const uint32_t *p) : a((uint32_t)__cvta_generic_to_shared(p)) {}
     __device__ __forceinline__ uint32_t operator[](uint32_t i) const
     {
         uint32_t v;
-        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a + 2u * i) : "memory");
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a + 4u * i) : "memory");
         return v;
     }
 };
 #else
 struct InfLut {
-    const uint16_t *p;
-    explicit InfLut(const uint16_t *q) : p(q) {}
+    const uint32_t *p;
+    explicit InfLut(const uint32_t *q) : p(q) {}
     uint32_t operator[](uint32_t i) const { return p[i]; }
 };
 #endif
 
 // one literal to the output (the pointer has been made opaque to the compiler, which would otherwise fall back to a
 // generic store: say "global" explicitly)
-PSS_IHD void inf_store(uint8_t *p, uint8_t v, bool writer)
+PSS_IHD void inf_store(uint8_t *p, uint32_t v, bool writer)
 {
 #if defined(__CUDA_ARCH__)
-    if (writer) asm volatile("st.global.u8 [%0], %1;" ::"l"(p), "r"((uint32_t)v) : "memory");
+    if (writer) asm volatile("st.global.u8 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 #else
-    if (writer) *p = v;
+    if (writer) *p = (uint8_t)v;
 #endif
 }
 
 // LZ77 match: wp[0 .. len) = wp[-dist ..], by all lanes (byte i by lane i mod 32).  An overlapping match (dist < len)
-// repeats its last `dist` bytes.  Matches of a BAM average nine bytes: one predicated load/store pair.
-PSS_IHD void inf_copy(uint8_t *wp, uint32_t dist, uint32_t len, int lane, int W)
+// repeats its last `dist` bytes.  The general form, kept out of line: matches longer than 32 bytes.
+PSS_IHD_COLD void inf_copy_long(uint8_t *wp, uint32_t dist, uint32_t len)
 {
+    const int lane = InfLanes::lane(), W = InfLanes::width();
     const uint8_t *src = wp - dist;
-#if defined(__CUDA_ARCH__)
-    (void)W;
-    for (uint32_t i = (uint32_t)lane; i < len; i += 32u) {
-        const uint32_t k = dist >= len ? i : i % dist;
-        uint32_t v;
-        asm volatile("ld.global.u8 %0, [%1];" : "=r"(v) : "l"(src + k) : "memory");
-        asm volatile("st.global.u8 [%0], %1;" ::"l"(wp + i), "r"(v) : "memory");
-    }
-#else
     for (uint32_t i = (uint32_t)lane; i < len; i += (uint32_t)W) wp[i] = src[dist >= len ? i : i % dist];
+}
+// Matches of a BAM average nine bytes: up to 32 bytes are one predicated load/store pair per lane.  wpl = wp + lane.
+// The pair is split: the load is issued when the match is decoded, the store when the NEXT match (or the end of the
+// loop) comes round -- the bytes come back from L2 (they were written moments ago; stores do not allocate in L1) while
+// the warp decodes the next symbols instead of waiting for them.  Nothing in between reads the bytes still owed:
+// literals go to other addresses, and the next match settles the debt before it loads.
+struct InfPending {
+    uint8_t *dst;
+    uint32_t v;
+    bool     owed;
+};
+PSS_IHD void inf_settle(InfPending &P)
+{
+#if defined(__CUDA_ARCH__)
+    if (P.owed) asm volatile("st.global.u8 [%0], %1;" ::"l"(P.dst), "r"(P.v) : "memory");
+    P.owed = false;
+#else
+    (void)P;
+#endif
+}
+PSS_IHD void inf_copy(uint8_t *wp, uint8_t *wpl, uint32_t dist, uint32_t len, int lane, InfPending &P)
+{
+#if defined(__CUDA_ARCH__)
+    inf_settle(P);
+    InfLanes::sync();                                        // the bytes written so far are visible to every lane
+    if (len > 32u) { inf_copy_long(wp, dist, len); return; }                  // warp uniform
+    uint32_t back = dist;
+    if (dist < len) {                                                           // warp uniform: a run (binned qualities)
+        // lane % dist without an integer division: (lane + 0.5) / dist is never within 1e-3 of an integer
+        const uint32_t q = (uint32_t)__fdividef((float)lane + 0.5f, (float)dist);
+        back = dist + q * dist;
+    }
+    P.owed = (uint32_t)lane < len;
+    P.dst = wpl;
+    if (P.owed) asm volatile("ld.global.u8 %0, [%1];" : "=r"(P.v) : "l"(wpl - back) : "memory");
+#else
+    (void)wpl; (void)lane; (void)P;
+    const uint8_t *src = wp - dist;
+    for (uint32_t i = 0; i < len; i++) wp[i] = src[dist >= len ? i : i % dist];
 #endif
 }
 
-PSS_IHD int inf_symbols(InfBits &B, InflateTables &T, uint8_t *out, uint32_t &op_io, uint32_t out_len)
+constexpr int      kInfMore = 101;                           // inf_loop<false>: fewer than kInfFastRoom bytes of output left
+constexpr uint32_t kInfFastRoom = 260;                       // bytes of output a step without bound checks may need (1 + 258)
+
+// The symbol loop proper.  A step takes two literals | [a literal and] one literal, end of block or match.
+// CAREFUL = false: runs while op <= limit (= out_len - kInfFastRoom) and checks no output bound; returns kInfMore when
+// it runs out of that guarantee.  CAREFUL = true: one symbol per step, every bound checked (the tail of a block).
+// Returns kInfOk at the end-of-block code, or an error.
+template <bool CAREFUL>
+PSS_IHD int inf_loop(InfBits &B, InfLut lit, InfLut dst, InflateTables &T, uint8_t *out, uint32_t &op_io, uint32_t out_len, uint32_t limit)
 {
-    const int lane = InfLanes::lane(), W = InfLanes::width();
-    InfLut    lit(T.lit_lut), dst(T.dist_lut);
-    uint8_t  *wp = out + op_io;                              // next output byte
-    uint32_t  room = out_len - op_io;                        // bytes that may still be written
-#if defined(__CUDA_ARCH__)
-    // opaque to the compiler: otherwise it re-derives the shared-memory addresses (six instructions) in every iteration
-    asm volatile("" : "+r"(lit.a), "+r"(dst.a));
-    asm volatile("" : "+l"(wp));
-#endif
+    constexpr uint32_t kLitMask = (1u << kInfLitBits) - 1u, kDistMask = (1u << kInfDistBits) - 1u;
+    const int  lane = InfLanes::lane();
     const bool writer = lane == 0;
-    int        rc = kInfOk;
+    uint32_t   op = op_io;
+#if defined(__CUDA_ARCH__)
+    // opaque to the compiler: otherwise it re-derives the shared-memory addresses in every iteration
+    asm volatile("" : "+r"(lit.a), "+r"(dst.a));
+    asm volatile("" : "+l"(out));
+#endif
+    uint8_t *const outl = out + lane;
+    InfPending     pend;
+    pend.owed = false; pend.dst = out; pend.v = 0;
+    int            rc;
     for (;;) {
-        // ---- literals: bit buffer -> table -> literal flag, nothing else
-        uint32_t e;
-        for (;;) {
-            B.refill();                                      // >= 33 bits: two literal codes (<= 15 bits each) fit
-            e = lit[B.peek(kInfLitBits)];
-            if (!(e & 0x8000u) || room == 0u) break;
-            B.drop((int)(e & 15u));
-            inf_store(wp, (uint8_t)(e >> 4), writer);
-            wp++;
-            room--;
-            e = lit[B.peek(kInfLitBits)];                    // the second one on the same fill
-            if (!(e & 0x8000u) || room == 0u) break;
-            B.drop((int)(e & 15u));
-            inf_store(wp, (uint8_t)(e >> 4), writer);
-            wp++;
-            room--;
-        }
-        // ---- everything else: longer codes, lengths, end of block, errors
-        B.refill();                                          // (the entry `e` came from the low bits, which a fill leaves alone)
-        uint32_t l = e & 15u;
-        int      s = (int)((e & 0x7fffu) >> 4);
-        if (l == 0u) {                                       // a code longer than the first-level table (7 % of the symbols of a BAM)
-            int ll;
-            s = inf_long((uint32_t)B.buf, T.lit_count, T.lit_sorted, T.lit_first, T.lit_index, kInfLitBits, ll);
-            l = (uint32_t)ll;
-            if (s < 0) { rc = kInfBadSymbol; break; }
-        }
-        B.drop((int)l);
-        if (s < 256) {
-            if (room == 0u) { rc = kInfOutputOverrun; break; }
-            inf_store(wp, (uint8_t)s, writer);
-            wp++;
-            room--;
-            continue;
-        }
-        if (s == 256) break;
-        if (s > 285) { rc = kInfBadSymbol; break; }
-        const uint32_t lc = inf_len_tab(s - 257);
-        const uint32_t len = (lc & 0xffffu) + B.get((int)(lc >> 16));
+        if (!CAREFUL && op > limit) { rc = kInfMore; break; }
         B.refill();
-        e = dst[B.peek(kInfDistBits)];
-        l = e & 15u;
-        int ds = (int)(e >> 4);
-        if (l == 0u) {
-            int ll;
-            ds = inf_long((uint32_t)B.buf, T.dist_count, T.dist_sorted, T.dist_first, T.dist_index, kInfDistBits, ll);
-            l = (uint32_t)ll;
+        uint32_t x = (uint32_t)B.buf;                        // 32 valid bits
+        uint32_t e = lit[x & kLitMask];
+        uint32_t used = 0;
+        uint8_t *wp = out + op;
+        if (!CAREFUL && (e & kInfELit)) {
+            inf_store(wp, e >> 16, writer);
+            wp++; op++;
+            used = e & 31u;                                  // a first-level hit: <= kInfLitBits bits
+            x >>= used;                                      // >= 22 valid bits: any code and the extra bits of a length
+            e = lit[x & kLitMask];
+            if (e & kInfELit) {
+                inf_store(wp, e >> 16, writer);
+                op++;
+                B.drop((int)(used + (e & 31u)));
+                continue;
+            }
         }
-        B.drop((int)l);
-        if (ds < 0 || ds > 29) { rc = kInfBadDistance; break; }
-        const uint32_t dc = inf_dist_tab(ds);
-        const uint32_t dist = (dc & 0xffffu) + B.get((int)(dc >> 16));
-        if (dist > out_len - room) { rc = kInfBadDistance; break; }
-        if (len > room) { rc = kInfOutputOverrun; break; }
-        InfLanes::sync();                                    // the bytes written so far are visible to every lane
-        inf_copy(wp, dist, len, lane, W);
-        wp += len;
-        room -= len;
+        if (e & (kInfESub | kInfESpecial | kInfELit)) {      // anything but a length with a first-level code
+            if (e & kInfESub) e = lit[(e >> 16) + ((x >> kInfLitBits) & ((1u << ((e >> 8) & 31u)) - 1u))];
+            if (e & kInfESpecial) {
+                if ((e >> 16) == kInfSpWalk) {               // no table entry: the canonical walk decides
+                    int       ll;
+                    const int s = inf_long(x, T.lit_count, T.lit_sorted, T.lit_first, T.lit_index, kInfLitBits, ll);
+                    if (s < 0) { rc = kInfBadSymbol; break; }
+                    e = inf_entry(kInfKindLit, s, ll);
+                }
+                if (e & kInfESpecial) {
+                    if ((e >> 16) != kInfSpEnd) { rc = kInfBadSymbol; break; }
+                    B.drop((int)(used + (e & 31u)));
+                    rc = kInfOk;
+                    break;
+                }
+            }
+            if (e & kInfELit) {
+                if (CAREFUL && op >= out_len) { rc = kInfOutputOverrun; break; }
+                inf_store(wp, e >> 16, writer);
+                op++;
+                B.drop((int)(used + (e & 31u)));
+                continue;
+            }
+        }
+        // a match: length base + extra bits (code and extra bits: <= 20 bits of x), then the distance the same way (<= 28)
+        const uint32_t tot = (e >> 8) & 31u;
+        const uint32_t len = (e >> 16) + ((x & ((1u << tot) - 1u)) >> (e & 31u));
+        B.drop((int)(used + tot));
+        B.refill();
+        x = (uint32_t)B.buf;
+        uint32_t d = dst[x & kDistMask];
+        if (d & kInfESpecial) {
+            if ((d >> 16) != kInfSpWalk) { rc = kInfBadDistance; break; }
+            int       ll;
+            const int ds = inf_long(x, T.dist_count, T.dist_sorted, T.dist_first, T.dist_index, kInfDistBits, ll);
+            if (ds < 0) { rc = kInfBadDistance; break; }
+            d = inf_entry(kInfKindDist, ds, ll);
+            if (d & kInfESpecial) { rc = kInfBadDistance; break; }
+        }
+        const uint32_t dtot = (d >> 8) & 31u;
+        const uint32_t dist = (d >> 16) + ((x & ((1u << dtot) - 1u)) >> (d & 31u));
+        B.drop((int)dtot);
+        if (dist > op) { rc = kInfBadDistance; break; }
+        if (CAREFUL && len > out_len - op) { rc = kInfOutputOverrun; break; }
+        inf_copy(wp, outl + op, dist, len, lane, pend);
+        op += len;
     }
-    op_io = out_len - room;
+    inf_settle(pend);
+    op_io = op;
     return rc;
+}
+PSS_IHD_COLD int inf_loop_careful(InfBits &B, InflateTables &T, uint8_t *out, uint32_t &op, uint32_t out_len)
+{
+    return inf_loop<true>(B, InfLut(T.lit_lut), InfLut(T.dist_lut), T, out, op, out_len, 0u);
+}
+
+PSS_IHD int inf_symbols(InfBits &B, InflateTables &T, uint8_t *out, uint32_t &op, uint32_t out_len)
+{
+    if (out_len >= kInfFastRoom) {
+        const int rc = inf_loop<false>(B, InfLut(T.lit_lut), InfLut(T.dist_lut), T, out, op, out_len, out_len - kInfFastRoom);
+        if (rc != kInfMore) return rc;
+    }
+    return inf_loop_careful(B, T, out, op, out_len);
 }
 
 // ---- one BGZF payload -------------------------------------------------------------------------------------------------
@@ -472,8 +598,8 @@ PSS_IHD int inflate_block(const uint8_t *in, uint32_t in_len, uint8_t *out, uint
             for (int s = lane; s < 288; s += W) T.lens[s] = (uint8_t)(s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : 8);
             for (int s = lane; s < 32; s += W) T.lens[288 + s] = 5;
             InfLanes::sync();
-            if (!inf_build(T.lens, 288, T.lit_count, T.lit_sorted, T.lit_lut, kInfLitBits, true, &T.lit_first, &T.lit_index)) return kInfBadCodeLengths;
-            if (!inf_build(T.lens + 288, 32, T.dist_count, T.dist_sorted, T.dist_lut, kInfDistBits, false, &T.dist_first, &T.dist_index)) return kInfBadCodeLengths;
+            if (!inf_build(T.lens, 288, T.lit_count, T.lit_sorted, T.lit_lut, kInfLitBits, kInfKindLit, kInfLitSub, &T.lit_first, &T.lit_index)) return kInfBadCodeLengths;
+            if (!inf_build(T.lens + 288, 32, T.dist_count, T.dist_sorted, T.dist_lut, kInfDistBits, kInfKindDist, 0, &T.dist_first, &T.dist_index)) return kInfBadCodeLengths;
         } else {
             B.refill();
             const int hlit = (int)B.get(5) + 257, hdist = (int)B.get(5) + 1, hclen = (int)B.get(4) + 4;
@@ -491,7 +617,7 @@ PSS_IHD int inflate_block(const uint8_t *in, uint32_t in_len, uint8_t *out, uint
                 if (lane == 0) cl[pos] = (uint8_t)v;
             }
             InfLanes::sync();
-            if (!inf_build(cl, 19, T.dist_count, T.dist_sorted, T.dist_lut, 7)) return kInfBadCodeLengths;
+            if (!inf_build(cl, 19, T.dist_count, T.dist_sorted, T.dist_lut, 7, kInfKindPlain, 0)) return kInfBadCodeLengths;
             // the hlit + hdist code lengths, run-length coded.  They are collected at lens[0 .. hlit + hdist) and the
             // distance part is moved to lens[288 ..) afterwards; the code-length table lives in dist_* meanwhile, and
             // cl[] may be overwritten once it is built.
@@ -521,8 +647,8 @@ PSS_IHD int inflate_block(const uint8_t *in, uint32_t in_len, uint8_t *out, uint
             }
             InfLanes::sync();
             if (T.lens[256] == 0) return kInfBadCodeLengths;             // no end-of-block code
-            if (!inf_build(T.lens, 288, T.lit_count, T.lit_sorted, T.lit_lut, kInfLitBits, true, &T.lit_first, &T.lit_index)) return kInfBadCodeLengths;
-            if (!inf_build(T.lens + 288, 32, T.dist_count, T.dist_sorted, T.dist_lut, kInfDistBits, false, &T.dist_first, &T.dist_index)) return kInfBadCodeLengths;
+            if (!inf_build(T.lens, 288, T.lit_count, T.lit_sorted, T.lit_lut, kInfLitBits, kInfKindLit, kInfLitSub, &T.lit_first, &T.lit_index)) return kInfBadCodeLengths;
+            if (!inf_build(T.lens + 288, 32, T.dist_count, T.dist_sorted, T.dist_lut, kInfDistBits, kInfKindDist, 0, &T.dist_first, &T.dist_index)) return kInfBadCodeLengths;
         }
         // ---- the symbol loop (warp uniform)
         {

@@ -29,13 +29,16 @@
 namespace pssgpu {
 
 constexpr size_t   kBamCarryCap  = 16ull << 20;   // front of the inflated buffer: header / record carried between batches
-constexpr size_t   kBamBatchCompDefault = 128ull << 20;   // compressed bytes per batch ($PSSGPU_BAM_BATCH_MB): one warp inflates one
+constexpr size_t   kBamBatchCompDefault = 256ull << 20;   // compressed bytes per batch ($PSSGPU_BAM_BATCH_MB): one warp inflates one
                                                           // ~20 KB block, so a batch must hold several thousand blocks to fill 148 SMs
 constexpr uint32_t kBamMaxBlocks = 32768;
 constexpr uint32_t kBamLocCap    = 2048;          // record starts per block: 65536 / 38 bytes < 1725, + the carried one
 constexpr uint32_t kBamMaxRefs   = 1u << 21;
 constexpr uint32_t kBamNone      = 0xffffffffu;
-constexpr int      kInfWarps     = 16;            // warps per CTA of the inflate kernel
+#ifndef PSS_INF_WARPS
+#define PSS_INF_WARPS 10
+#endif
+constexpr int      kInfWarps     = PSS_INF_WARPS; // warps per CTA of the inflate kernel: 7.3 KB of tables each, three CTAs per SM
 
 enum : unsigned {
     kBamOk = 0, kBamErrInflate = 100 /* + pss_inflate.h code */, kBamErrMagic = 200, kBamErrHeaderTooLarge, kBamErrTooManyRefs,

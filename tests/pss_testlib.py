@@ -726,17 +726,31 @@ def bam_to_sam(bam: bytes, read_group=None) -> bytes:
 BAM_EMUL_SO = os.path.join(ROOT, "tests", "host_emul", "libpssbamemul.so")
 
 
-def build_bam_emul(force=False):
+# other shapes of the inflate tables: a second-level area too small for real blocks (the canonical-walk fallback runs)
+# and a 9-bit first level (more second-level look-ups)
+BAM_EMUL_VARIANTS = {"": [], "walk": ["-DPSS_INF_LIT_SUB=8"], "lit9": ["-DPSS_INF_LIT_BITS=9"]}
+
+
+def build_bam_emul(force=False, variant=""):
     src = os.path.join(ROOT, "tests", "host_emul", "pss_bam_emul.cpp")
     hdrs = [os.path.join(ROOT, "pss-bam_b200", "csrc", h) for h in ("pss_inflate.h", "pss_bamrec.h", "pss_record.h")]
     newest = max(os.path.getmtime(f) for f in [src] + hdrs)
-    return _locked_build(BAM_EMUL_SO, newest, force,
-                         lambda out: ["g++", "-O2", "-g", "-std=c++17", "-Wno-unknown-pragmas", "-fPIC", "-shared", "-o", out, src])
+    target = BAM_EMUL_SO if not variant else BAM_EMUL_SO.replace(".so", f"_{variant}.so")
+    return _locked_build(target, newest, force,
+                         lambda out: ["g++", "-O2", "-g", "-std=c++17", "-Wno-unknown-pragmas", "-fPIC", "-shared",
+                                      *BAM_EMUL_VARIANTS[variant], "-o", out, src])
 
 
 class BamEmul:
     """pss_inflate.h / pss_bamrec.h compiled for the host (a TEST of the device logic, never a product path)."""
     _lib = None
+
+    @classmethod
+    def variant_lib(cls, variant):
+        """emul_inflate of a differently shaped build of the inflate tables (BAM_EMUL_VARIANTS)."""
+        lib = C.CDLL(build_bam_emul(variant=variant))
+        lib.emul_inflate.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+        return lib
 
     @classmethod
     def lib(cls):
