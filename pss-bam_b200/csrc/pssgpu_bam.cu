@@ -208,6 +208,13 @@ bam_fix_kernel(const BamDesc *__restrict__ desc, uint32_t n_blocks, const uint8_
             const uint32_t s = have ? S[b] : kBamNone, e = have ? E[b] : 0u;
             const uint32_t u1 = have ? (uint32_t)(kBamCarryCap + desc[b].dst_off + desc[b].isize) : 0u;
             const uint32_t cnt = n_blocks - base < 32u ? n_blocks - base : 32u;
+            {   // the usual case in one step: every guess of the group is the exit of the chain before it (lane 0: the
+                // known entry) and lies in its own block -- by induction all 32 are true
+                const uint32_t pe = __shfl_up_sync(0xffffffffu, e, 1);
+                const uint64_t want = lane == 0 ? expected : (uint64_t)pe;
+                const bool     good = have && s != kBamNone && e != kBamNone && (uint64_t)s == want && want < (uint64_t)u1;
+                if (cnt == 32u && __all_sync(0xffffffffu, good)) { expected = __shfl_sync(0xffffffffu, e, 31); continue; }
+            }
             for (uint32_t i = 0; i < cnt; i++) {
                 const uint32_t si = __shfl_sync(0xffffffffu, s, (int)i), ei = __shfl_sync(0xffffffffu, e, (int)i);
                 const uint32_t u1i = __shfl_sync(0xffffffffu, u1, (int)i);
@@ -239,11 +246,20 @@ bam_fix_kernel(const BamDesc *__restrict__ desc, uint32_t n_blocks, const uint8_
 
 // One CTA per BGZF block: records -> SAM lines.  Pass 1, one thread per record: well-formedness, the RG filter, the
 // length of the line; a CTA scan gives every line its place and ONE atomic allocates the block's stretch of the text.
-// Pass 2, one warp per record: lane 0 renders the short head (FLAG .. TLEN) into shared memory, then all lanes store
-// head, SEQ (4-bit codes -> letters) and QUAL byte by consecutive byte -- coalesced stores instead of one thread
-// dribbling 240 single bytes.
+// Pass 2, 32 records per warp and round: every lane renders the short head (FLAG .. TLEN) of ONE record into its own
+// slot of shared memory -- 32 heads at once instead of one lane at a time -- then the warp goes through the 32 records
+// together and stores head, SEQ (4-bit codes -> letters) and QUAL byte by consecutive byte: coalesced stores instead
+// of one thread dribbling 240 single bytes.
 constexpr int kRenderThreads = 128;
-constexpr int kRenderHeadCap = 240;                         // longer heads (long CIGARs / names) are written by lane 0 directly
+constexpr int kRenderHeadCap = 96;                          // longer heads (long CIGARs / names) are written by their lane directly
+constexpr int kRenderHeadStride = 100;                      // 25 words: the 32 slots of a warp start in 32 different banks
+// "=ACMGRSVTWYHKDBN"[n] without a (divergent) constant-memory access: the 16 letters sit in four registers
+__device__ __forceinline__ uint32_t bam_base_letter(uint32_t n)
+{
+    const uint32_t lo = __byte_perm(0x4d43413du, 0x56535247u, n & 7u);      // "=ACM" "GRSV"
+    const uint32_t hi = __byte_perm(0x48595754u, 0x4e42444bu, n & 7u);      // "TWYH" "KDBN"
+    return ((n & 8u) ? hi : lo) & 0xffu;
+}
 __global__ void __launch_bounds__(kRenderThreads)
 bam_render_kernel(const uint8_t *__restrict__ ubuf, BamState *st, const uint32_t *__restrict__ loc, const uint32_t *__restrict__ N,
                   BamRefs refs, const char *__restrict__ rg, int rg_len, uint8_t *__restrict__ text, uint64_t text_cap)
@@ -251,7 +267,7 @@ bam_render_kernel(const uint8_t *__restrict__ ubuf, BamState *st, const uint32_t
     __shared__ uint32_t s_off[kBamLocCap + 1];              // line lengths, then their exclusive prefix sums
     __shared__ uint32_t s_warp[kRenderThreads / 32];
     __shared__ unsigned long long s_base;
-    __shared__ uint8_t  s_head[kRenderThreads / 32][kRenderHeadCap + 16];
+    __shared__ uint8_t  s_head[kRenderThreads / 32][32 * kRenderHeadStride];
     const uint32_t b = blockIdx.x, tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     if (!st->hdr_done || st->error) return;
     const uint32_t n = N[b];
@@ -295,26 +311,63 @@ bam_render_kernel(const uint8_t *__restrict__ ubuf, BamState *st, const uint32_t
     __syncthreads();
     if (s_base + total > text_cap) { if (tid == 0) bam_fail(st, kBamErrTextOverflow, b); return; }
     // ---- pass 2
-    for (uint32_t i = warp; i < n; i += kRenderThreads / 32) {
-        const uint32_t at = s_off[i], len = s_off[i + 1] - at;
-        if (len == 0) continue;                                     // dropped (RG filter / malformed)
-        const uint8_t *r = ubuf + mine[i];
-        const BamCore  c = bam_core(r);                             // warp uniform
-        const bool     qs = bam_qual_is_star(r, c);
-        const uint32_t tail = bam_tail_len(c, qs), head = len - tail;
-        uint8_t       *dst = text + s_base + at;
-        if (head <= (uint32_t)kRenderHeadCap) {
-            if (lane == 0) { BamWriteSink ws{ s_head[warp] }; bam_render_head(r, c, refs, ws); }
-            __syncwarp();
-            for (uint32_t k = lane; k < head; k += 32) dst[k] = s_head[warp][k];
-            __syncwarp();
-        } else if (lane == 0) {
-            BamWriteSink ws{ dst };
-            bam_render_head(r, c, refs, ws);
+    uint8_t *const text_b = text + s_base;
+    for (uint32_t i0 = warp * 32u; i0 < n; i0 += kRenderThreads) {
+        // this lane's record: the head into the lane's slot, what the cooperative part needs into registers
+        const uint32_t i = i0 + lane;
+        uint32_t       m_at = 0, m_seq = 0, m_lseq = 0, m_meta = 0;          // meta: head length | QUAL is '*' << 16 | head already stored << 17
+        if (i < n) {
+            const uint32_t at = s_off[i], len = s_off[i + 1] - at;
+            if (len) {                                                  // 0: dropped (RG filter / malformed)
+                const uint8_t *r = ubuf + mine[i];
+                const BamCore  c = bam_core(r);
+                const bool     qs = bam_qual_is_star(r, c);
+                const uint32_t head = len - bam_tail_len(c, qs);
+                m_at = at; m_lseq = c.l_seq;
+                m_seq = (uint32_t)(bam_seq_ptr(r, c) - ubuf);
+                m_meta = head | (qs ? 0x10000u : 0u);
+                if (head <= (uint32_t)kRenderHeadCap) {
+                    BamWriteSink ws{ s_head[warp] + lane * kRenderHeadStride };
+                    bam_render_head(r, c, refs, ws);
+                } else {
+                    BamWriteSink ws{ text_b + at };
+                    bam_render_head(r, c, refs, ws);
+                    m_meta |= 0x20000u;
+                }
+                m_meta |= 0x40000u;                                     // a line to write
+            }
         }
-        const uint8_t *seq = bam_seq_ptr(r, c);
-        dst += head;
-        for (uint32_t k = lane; k < tail; k += 32) dst[k] = bam_tail_byte(seq, c, qs, k);
+        __syncwarp();
+        const uint32_t cnt = n - i0 < 32u ? n - i0 : 32u;
+        for (uint32_t j = 0; j < cnt; j++) {
+            const uint32_t meta = __shfl_sync(0xffffffffu, m_meta, (int)j);
+            if (!(meta & 0x40000u)) continue;                           // warp uniform
+            const uint32_t at = __shfl_sync(0xffffffffu, m_at, (int)j), l_seq = __shfl_sync(0xffffffffu, m_lseq, (int)j);
+            const uint8_t *seq = ubuf + __shfl_sync(0xffffffffu, m_seq, (int)j);
+            const uint32_t head = meta & 0xffffu;
+            const bool     qs = (meta & 0x10000u) != 0u;
+            uint8_t       *dst = text_b + at;
+            if (!(meta & 0x20000u)) {
+                const uint8_t *hs = s_head[warp] + j * kRenderHeadStride;
+                for (uint32_t k = lane; k < head; k += 32) dst[k] = hs[k];
+            }
+            dst += head;
+            if (l_seq == 0) {
+                if (lane < 4u) dst[lane] = (uint8_t)"*\t*\n"[lane];
+                continue;
+            }
+            // SEQ, tab, QUAL ('I' per base, or '*'), newline
+            const uint32_t ql = qs ? 1u : l_seq, tail = l_seq + 1u + ql + 1u;
+            for (uint32_t k = lane; k < tail; k += 32) {
+                uint32_t v;
+                if (k < l_seq) {
+                    const uint32_t bb = seq[k >> 1];
+                    v = bam_base_letter((k & 1u) ? (bb & 15u) : (bb >> 4));
+                } else v = k == l_seq ? (uint32_t)'\t' : k == tail - 1u ? (uint32_t)'\n' : qs ? (uint32_t)'*' : (uint32_t)'I';
+                dst[k] = (uint8_t)v;
+            }
+        }
+        __syncwarp();
     }
     // counters: one atomic per warp
 #pragma unroll
