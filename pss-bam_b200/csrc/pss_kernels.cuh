@@ -1639,7 +1639,9 @@ __global__ void __launch_bounds__(kThreads, PSS_TALLY_CTAS_PER_SM) tally_warp_ke
     __syncthreads();
     cta_epilogue<MODE>(S.sh, A, tid, kThreads, rows);
 }
+#if PSS_TALLY_THREADS == 256      // (tuning builds with other CTA sizes do not use the warp-tile variant)
 static_assert(sizeof(TallyWarpSmem) + 1024 <= 232448 / PSS_TALLY_CTAS_PER_SM, "the CTAs of the warp-tile kernel must fit one SM");
+#endif
 
 static_assert(sizeof(TallySmem) + 1024 <= 232448 / PSS_TALLY_CTAS_PER_SM, "the CTAs of the tally kernel must fit one SM");
 
