@@ -64,6 +64,7 @@ struct InflateTables {                       // one per warp
     uint32_t lit_first, lit_index;           // state of the canonical walk after kInfLitBits levels (longer codes resume there)
     uint32_t dist_first, dist_index;         // ... after kInfDistBits levels
     uint8_t  lens[kInfMaxLit + kInfMaxDist]; // code lengths of the block being set up
+    uint32_t stage[32];                      // per lane: the aligned word around the source byte of the match in flight (inf_copy)
 };
 
 enum : int {
@@ -407,29 +408,41 @@ PSS_IHD_COLD void inf_copy_long(uint8_t *wp, uint32_t dist, uint32_t len)
     const uint8_t *src = wp - dist;
     for (uint32_t i = (uint32_t)lane; i < len; i += (uint32_t)W) wp[i] = src[dist >= len ? i : i % dist];
 }
-// Matches of a BAM average nine bytes: up to 32 bytes are one predicated load/store pair per lane.  wpl = wp + lane.
-// The pair is split: the load is issued when the match is decoded, the store when the NEXT match (or the end of the
-// loop) comes round -- the bytes come back from L2 (they were written moments ago; stores do not allocate in L1) while
-// the warp decodes the next symbols instead of waiting for them.  Nothing in between reads the bytes still owed:
-// literals go to other addresses, and the next match settles the debt before it loads.
+// Matches of a BAM average nine bytes: up to 32 bytes are one load and one store per lane.  wpl = wp + lane.
+// The bytes were written moments ago and come back from L2 (stores do not allocate in L1): a few hundred cycles that a
+// load into a register would make the warp sit out at once (its consumer, or the next branch, waits on the
+// scoreboard).  So the source is fetched ASYNCHRONOUSLY -- every lane cp.asyncs the aligned word around its own source
+// byte into its own word of shared memory, tracked by the async-copy counter instead of a register scoreboard -- and the
+// store is issued when the NEXT match (or the end of the loop) comes round, after the warp has decoded the symbols in
+// between.  Nothing in between reads the bytes still owed: literals go to other addresses, and the next match settles
+// the debt before it fetches.
 struct InfPending {
-    uint8_t *dst;
-    uint32_t v;
-    bool     owed;
+    uint8_t *dst;                // where this lane's byte goes
+    uint32_t sidx;               // ... and where it sits in the stage
+    uint32_t owed;               // this lane has a byte to store
+    uint32_t any;                // warp uniform: a match is pending
 };
-PSS_IHD void inf_settle(InfPending &P)
+PSS_IHD void inf_settle(InfPending &P, uint32_t stage)
 {
 #if defined(__CUDA_ARCH__)
-    if (P.owed) asm volatile("st.global.u8 [%0], %1;" ::"l"(P.dst), "r"(P.v) : "memory");
-    P.owed = false;
+    if (P.any) {                                             // warp uniform
+        asm volatile("cp.async.wait_all;" ::: "memory");     // this lane's own word has landed: no other lane's is needed
+        if (P.owed) {
+            uint32_t v;
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(stage + P.sidx) : "memory");
+            asm volatile("st.global.u8 [%0], %1;" ::"l"(P.dst), "r"(v) : "memory");
+        }
+        P.any = 0u;
+    }
 #else
-    (void)P;
+    (void)P; (void)stage;
 #endif
 }
-PSS_IHD void inf_copy(uint8_t *wp, uint8_t *wpl, uint32_t dist, uint32_t len, int lane, InfPending &P)
+// `stage` = this LANE's word of the warp's stage
+PSS_IHD void inf_copy(uint8_t *wp, uint8_t *wpl, uint32_t dist, uint32_t len, int lane, InfPending &P, uint32_t stage)
 {
 #if defined(__CUDA_ARCH__)
-    inf_settle(P);
+    inf_settle(P, stage);
     InfLanes::sync();                                        // the bytes written so far are visible to every lane
     if (len > 32u) { inf_copy_long(wp, dist, len); return; }                  // warp uniform
     uint32_t back = dist;
@@ -438,11 +451,14 @@ PSS_IHD void inf_copy(uint8_t *wp, uint8_t *wpl, uint32_t dist, uint32_t len, in
         const uint32_t q = (uint32_t)__fdividef((float)lane + 0.5f, (float)dist);
         back = dist + q * dist;
     }
-    P.owed = (uint32_t)lane < len;
+    const uintptr_t src = (uintptr_t)(wpl - back);           // this lane's source byte; it fetches the aligned word around it
+    P.any = 1u;
+    P.owed = (uint32_t)lane < len ? 1u : 0u;
     P.dst = wpl;
-    if (P.owed) asm volatile("ld.global.u8 %0, [%1];" : "=r"(P.v) : "l"(wpl - back) : "memory");
+    P.sidx = (uint32_t)(src & 3u);
+    if (P.owed) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(stage), "l"(src & ~(uintptr_t)3) : "memory");
 #else
-    (void)wpl; (void)lane; (void)P;
+    (void)wpl; (void)lane; (void)P; (void)stage;
     const uint8_t *src = wp - dist;
     for (uint32_t i = 0; i < len; i++) wp[i] = src[dist >= len ? i : i % dist];
 #endif
@@ -469,7 +485,12 @@ PSS_IHD int inf_loop(InfBits &B, InfLut lit, InfLut dst, InflateTables &T, uint8
 #endif
     uint8_t *const outl = out + lane;
     InfPending     pend;
-    pend.owed = false; pend.dst = out; pend.v = 0;
+    pend.owed = 0u; pend.any = 0u; pend.dst = out; pend.sidx = 0;
+#if defined(__CUDA_ARCH__)
+    const uint32_t stage = (uint32_t)__cvta_generic_to_shared(T.stage + lane);       // this lane's word
+#else
+    const uint32_t stage = 0;
+#endif
     int            rc;
     for (;;) {
         if (!CAREFUL && op > limit) { rc = kInfMore; break; }
@@ -535,10 +556,10 @@ PSS_IHD int inf_loop(InfBits &B, InfLut lit, InfLut dst, InflateTables &T, uint8
         B.drop((int)dtot);
         if (dist > op) { rc = kInfBadDistance; break; }
         if (CAREFUL && len > out_len - op) { rc = kInfOutputOverrun; break; }
-        inf_copy(wp, outl + op, dist, len, lane, pend);
+        inf_copy(wp, outl + op, dist, len, lane, pend, stage);
         op += len;
     }
-    inf_settle(pend);
+    inf_settle(pend, stage);
     op_io = op;
     return rc;
 }
