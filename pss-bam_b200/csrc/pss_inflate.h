@@ -389,14 +389,16 @@ struct InfLut {
 };
 #endif
 
-// one literal to the output (the pointer has been made opaque to the compiler, which would otherwise fall back to a
-// generic store: say "global" explicitly)
-PSS_IHD void inf_store(uint8_t *p, uint32_t v, bool writer)
+// one literal to the output, at p[OFF] (the pointer has been made opaque to the compiler, which would otherwise fall
+// back to a generic store: say "global" explicitly).  Every lane stores the same byte to the same address -- the
+// memory system makes one write of it -- which costs less than keeping a "lane 0" predicate alive through the loop.
+template <int OFF = 0>
+PSS_IHD void inf_store(uint8_t *p, uint32_t v)
 {
 #if defined(__CUDA_ARCH__)
-    if (writer) asm volatile("st.global.u8 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    asm volatile("st.global.u8 [%0+%2], %1;" ::"l"(p), "r"(v), "n"(OFF) : "memory");
 #else
-    if (writer) *p = (uint8_t)v;
+    p[OFF] = (uint8_t)v;
 #endif
 }
 
@@ -420,20 +422,17 @@ struct InfPending {
     uint8_t *dst;                // where this lane's byte goes
     uint32_t sidx;               // ... and where it sits in the stage
     uint32_t owed;               // this lane has a byte to store
-    uint32_t any;                // warp uniform: a match is pending
 };
 PSS_IHD void inf_settle(InfPending &P, uint32_t stage)
 {
 #if defined(__CUDA_ARCH__)
-    if (P.any) {                                             // warp uniform
-        asm volatile("cp.async.wait_all;" ::: "memory");     // this lane's own word has landed: no other lane's is needed
-        if (P.owed) {
-            uint32_t v;
-            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(stage + P.sidx) : "memory");
-            asm volatile("st.global.u8 [%0], %1;" ::"l"(P.dst), "r"(v) : "memory");
-        }
-        P.any = 0u;
+    asm volatile("cp.async.wait_all;" ::: "memory");         // this lane's own word has landed: no other lane's is needed
+    if (P.owed) {
+        uint32_t v;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(stage + P.sidx) : "memory");
+        asm volatile("st.global.u8 [%0], %1;" ::"l"(P.dst), "r"(v) : "memory");
     }
+    P.owed = 0u;
 #else
     (void)P; (void)stage;
 #endif
@@ -452,7 +451,6 @@ PSS_IHD void inf_copy(uint8_t *wp, uint8_t *wpl, uint32_t dist, uint32_t len, in
         back = dist + q * dist;
     }
     const uintptr_t src = (uintptr_t)(wpl - back);           // this lane's source byte; it fetches the aligned word around it
-    P.any = 1u;
     P.owed = (uint32_t)lane < len ? 1u : 0u;
     P.dst = wpl;
     P.sidx = (uint32_t)(src & 3u);
@@ -476,7 +474,6 @@ PSS_IHD int inf_loop(InfBits &B, InfLut lit, InfLut dst, InflateTables &T, uint8
 {
     constexpr uint32_t kLitMask = (1u << kInfLitBits) - 1u, kDistMask = (1u << kInfDistBits) - 1u;
     const int  lane = InfLanes::lane();
-    const bool writer = lane == 0;
     uint32_t   op = op_io;
 #if defined(__CUDA_ARCH__)
     // opaque to the compiler: otherwise it re-derives the shared-memory addresses in every iteration
@@ -484,8 +481,9 @@ PSS_IHD int inf_loop(InfBits &B, InfLut lit, InfLut dst, InflateTables &T, uint8
     asm volatile("" : "+l"(out));
 #endif
     uint8_t *const outl = out + lane;
+    uint32_t       bad_dist = 0;
     InfPending     pend;
-    pend.owed = 0u; pend.any = 0u; pend.dst = out; pend.sidx = 0;
+    pend.owed = 0u; pend.dst = out; pend.sidx = 0;
 #if defined(__CUDA_ARCH__)
     const uint32_t stage = (uint32_t)__cvta_generic_to_shared(T.stage + lane);       // this lane's word
 #else
@@ -500,17 +498,18 @@ PSS_IHD int inf_loop(InfBits &B, InfLut lit, InfLut dst, InflateTables &T, uint8
         uint32_t used = 0;
         uint8_t *wp = out + op;
         if (!CAREFUL && (e & kInfELit)) {
-            inf_store(wp, e >> 16, writer);
-            wp++; op++;
+            inf_store(wp, e >> 16);
+            op++;
             used = e & 31u;                                  // a first-level hit: <= kInfLitBits bits
             x >>= used;                                      // >= 22 valid bits: any code and the extra bits of a length
             e = lit[x & kLitMask];
             if (e & kInfELit) {
-                inf_store(wp, e >> 16, writer);
+                inf_store<1>(wp, e >> 16);
                 op++;
                 B.drop((int)(used + (e & 31u)));
                 continue;
             }
+            wp++;
         }
         if (e & (kInfESub | kInfESpecial | kInfELit)) {      // anything but a length with a first-level code
             if (e & kInfESub) e = lit[(e >> 16) + ((x >> kInfLitBits) & ((1u << ((e >> 8) & 31u)) - 1u))];
@@ -530,7 +529,7 @@ PSS_IHD int inf_loop(InfBits &B, InfLut lit, InfLut dst, InflateTables &T, uint8
             }
             if (e & kInfELit) {
                 if (CAREFUL && op >= out_len) { rc = kInfOutputOverrun; break; }
-                inf_store(wp, e >> 16, writer);
+                inf_store(wp, e >> 16);
                 op++;
                 B.drop((int)(used + (e & 31u)));
                 continue;
@@ -554,13 +553,22 @@ PSS_IHD int inf_loop(InfBits &B, InfLut lit, InfLut dst, InflateTables &T, uint8
         const uint32_t dtot = (d >> 8) & 31u;
         const uint32_t dist = (d >> 16) + ((x & ((1u << dtot) - 1u)) >> (d & 31u));
         B.drop((int)dtot);
-        if (dist > op) { rc = kInfBadDistance; break; }
+        // a distance that reaches back before the block is an error; the fast loop only notes it and reports it when
+        // it ends (the bytes such a match copies come from inside the buffer -- up to 32 KiB before the block, the carry
+        // region lies there -- and the block is rejected anyway)
+#if defined(__CUDA_ARCH__)
+        if (CAREFUL) { if (dist > op) { rc = kInfBadDistance; break; } }
+        else bad_dist |= (dist > op) ? 1u : 0u;
+#else
+        if (dist > op) { rc = kInfBadDistance; break; }       // (the host build has no such slack before its buffers)
+#endif
         if (CAREFUL && len > out_len - op) { rc = kInfOutputOverrun; break; }
         inf_copy(wp, outl + op, dist, len, lane, pend, stage);
         op += len;
     }
     inf_settle(pend, stage);
     op_io = op;
+    if (bad_dist) return kInfBadDistance;
     return rc;
 }
 PSS_IHD_COLD int inf_loop_careful(InfBits &B, InflateTables &T, uint8_t *out, uint32_t &op, uint32_t out_len)
