@@ -463,9 +463,9 @@ PSS_IHD void inf_copy(uint8_t *wp, uint8_t *wpl, uint32_t dist, uint32_t len, in
 }
 
 constexpr int      kInfMore = 101;                           // inf_loop<false>: fewer than kInfFastRoom bytes of output left
-constexpr uint32_t kInfFastRoom = 260;                       // bytes of output a step without bound checks may need (1 + 258)
+constexpr uint32_t kInfFastRoom = 260;                       // bytes of output a step without bound checks may need (1 + 258; 3 literals)
 
-// The symbol loop proper.  A step takes two literals | [a literal and] one literal, end of block or match.
+// The symbol loop proper.  A step takes two or three literals | [a literal and] one literal, end of block or match.
 // CAREFUL = false: runs while op <= limit (= out_len - kInfFastRoom) and checks no output bound; returns kInfMore when
 // it runs out of that guarantee.  CAREFUL = true: one symbol per step, every bound checked (the tail of a block).
 // Returns kInfOk at the end-of-block code, or an error.
@@ -506,7 +506,15 @@ PSS_IHD int inf_loop(InfBits &B, InfLut lit, InfLut dst, InflateTables &T, uint8
             if (e & kInfELit) {
                 inf_store<1>(wp, e >> 16);
                 op++;
-                B.drop((int)(used + (e & 31u)));
+                used += e & 31u;
+                x >>= e & 31u;                               // >= 12 valid bits: enough for one more first-level literal
+                e = lit[x & kLitMask];
+                if (e & kInfELit) {                          // (anything else is looked up again after the next refill)
+                    inf_store<2>(wp, e >> 16);
+                    op++;
+                    used += e & 31u;
+                }
+                B.drop((int)used);
                 continue;
             }
             wp++;
