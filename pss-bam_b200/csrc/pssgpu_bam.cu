@@ -90,7 +90,7 @@ __device__ __forceinline__ void bam_fail(BamState *st, unsigned code, unsigned a
     if (atomicCAS(&st->error, 0u, code) == 0u) st->error_arg = arg;
 }
 
-// MINB = CTAs per SM the register allocation aims at: 3 (48 warps, <= 42 registers) or 2 (32 warps, <= 64 registers)
+// MINB = CTAs per SM the register allocation aims at: 3 (30 warps at the default 10 warps per CTA, 64 registers) or 2
 template <int MINB>
 __global__ void __launch_bounds__(kInfWarps * 32, MINB)
 bgzf_inflate_kernel(const BamDesc *__restrict__ desc, uint32_t n_blocks, const uint8_t *__restrict__ comp, uint8_t *udata, BamState *st)
