@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(kRadixThreads) radix_scatter_kernel(const uint
     constexpr uint64_t kmask = (1ull << (2 * K)) - 1ull;
     __shared__ uint32_t s_cnt[kRadixThreads], s_toff[kRadixThreads + 1], s_warp[kRadixThreads / 32];
     __shared__ unsigned long long s_goff[kRadixThreads];
-    __shared__ uint16_t s_pay[16 * kRadixThreads], s_bkt[16 * kRadixThreads];
+    __shared__ uint32_t s_rec[16 * kRadixThreads];            // payload | bucket << 16, in bucket order: one store per k-mer
     const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
     const uint64_t n_tiles = (g_end - g_begin + kRadixThreads - 1) / kRadixThreads;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -445,13 +445,12 @@ __global__ void __launch_bounds__(kRadixThreads) radix_scatter_kernel(const uint
                 const uint32_t idx = (uint32_t)(msb >> (2 * (32 - o - K))) & (uint32_t)kmask;
                 const uint32_t b = br[o] & 511u;
                 const uint32_t pos = s_toff[b] + (br[o] >> 9);
-                s_pay[pos] = (uint16_t)(idx & (uint32_t)(kSpecSmemBins - 1));
-                s_bkt[pos] = (uint16_t)b;
+                s_rec[pos] = (idx & (uint32_t)(kSpecSmemBins - 1)) | (b << 16);
             }
         }
         __syncthreads();
         const uint32_t n_tile = s_toff[kRadixThreads];
-        for (uint32_t i = t; i < n_tile; i += kRadixThreads) payload[s_goff[s_bkt[i]] + i] = s_pay[i];
+        for (uint32_t i = t; i < n_tile; i += kRadixThreads) { const uint32_t v = s_rec[i]; payload[s_goff[v >> 16] + i] = (uint16_t)v; }
         __syncthreads();
     }
 }
