@@ -11,7 +11,7 @@ K = [("lop3/imad/classify", find(src_k, "template <int LUT>"), find(src_k, "__de
      ("contig", find(src_k, "// k-th 4-byte word of the field"), find(src_k, "// A record the tile cannot hold") - 1),
      ("tally_rows", find(src_k, "// ballot of \"(word & mask) != 0\""), find(src_k, "__device__ __forceinline__ void flush_acc") - 2),
      ("flush", find(src_k, "__device__ __forceinline__ void flush_acc") - 1, find(src_k, "// building blocks of the tally kernel") - 2),
-     ("list_generic", find(src_k, "// Generic newline listing"), find(src_k, "// One warp-load of records") - 1),
+     ("list_generic", find(src_k, "// Exact newline listing"), find(src_k, "// One warp-load of records") - 1),
      ("batch_glue", find(src_k, "// One warp-load of records"), find(src_k, "// tally kernel.") - 2),
      ("k_stage", find(src_k, "// ---- stage ----"), find(src_k, "// ---- pass A") - 1),
      ("k_passA", find(src_k, "// ---- pass A"), find(src_k, "// ---- pass B") - 1),
