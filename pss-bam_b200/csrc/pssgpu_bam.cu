@@ -655,7 +655,9 @@ int feed_bam_impl(pssgpu_ctx *ctx, const uint8_t *data, size_t len, int last)
             int fr = bgzf_frame(data + off, len - off, &total, &po, &pl, &isz);
             if (fr < 0) return fail(ctx, PSSGPU_EINVAL, "feed_bam: not a BGZF block (at byte %llu)", (unsigned long long)(ctx->fed_bytes + off));
             if (fr == 0) { more = false; break; }
-            if ((off - start) + total > B->batch_comp || total_u + isz > B->batch_u) break;
+            // the first batch of a stream is a quarter batch: its copy is the one nothing overlaps, the GPU starts sooner
+            const size_t comp_cap = B->batches == 0 ? std::max<size_t>(B->batch_comp / 4, 1u << 20) : B->batch_comp;
+            if ((off - start) + total > comp_cap || total_u + isz > B->batch_u) break;
             desc[n_blocks++] = BamDesc{ (uint32_t)(off - start) + po, pl, (uint32_t)total_u, isz };
             total_u += isz;
             off += total;
