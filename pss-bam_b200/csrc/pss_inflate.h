@@ -376,8 +376,8 @@ struct InfLut {
     __device__ __forceinline__ explicit InfLut(const uint32_t *p) : a((uint32_t)__cvta_generic_to_shared(p)) {}
     __device__ __forceinline__ uint32_t operator[](uint32_t i) const
     {
-        uint32_t v;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a + 4u * i) : "memory");
+        uint32_t v;      // the address as one multiply-add (FMA pipe) instead of shift + add behind the index mask
+        asm volatile("{\n\t.reg .u32 t;\n\tmad.lo.u32 t, %1, 4, %2;\n\tld.shared.u32 %0, [t];\n\t}" : "=r"(v) : "r"(i), "r"(a) : "memory");
         return v;
     }
 };
