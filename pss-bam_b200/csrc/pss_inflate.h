@@ -42,10 +42,10 @@ namespace pssgpu {
 constexpr int kInfLitBits  = PSS_INF_LIT_BITS;               // first-level bits of the literal/length table
 constexpr int kInfDistBits = 8;
 #ifndef PSS_INF_LIT_SUB
-#define PSS_INF_LIT_SUB (PSS_INF_LIT_BITS >= 10 ? 320 : 352)
+#define PSS_INF_LIT_SUB (PSS_INF_LIT_BITS >= 10 ? 288 : 352)
 #endif
-constexpr int kInfLitSub   = PSS_INF_LIT_SUB;                // second-level entries (zlib's worst case: 1332 / 852 in all;
-                                                             // a block that needs more takes the canonical walk)
+constexpr int kInfLitSub   = PSS_INF_LIT_SUB;                // second-level entries (zlib's worst case needs 308 / 340; a block that
+                                                             // needs more than there are takes the canonical walk for the rest)
 constexpr int kInfMaxLit   = 288;
 constexpr int kInfMaxDist  = 32;
 
@@ -64,6 +64,7 @@ struct InflateTables {                       // one per warp
     uint32_t lit_first, lit_index;           // state of the canonical walk after kInfLitBits levels (longer codes resume there)
     uint32_t dist_first, dist_index;         // ... after kInfDistBits levels
     uint8_t  lens[kInfMaxLit + kInfMaxDist]; // code lengths of the block being set up
+    uint32_t window[32];                     // the current 32 words of compressed input (InfBits)
     uint32_t stage[32];                      // per lane: the aligned word around the source byte of the match in flight (inf_copy)
 };
 
@@ -91,15 +92,17 @@ struct InfLanes {
 
 // ---- bit reader -----------------------------------------------------------------------------------------------------
 // The compressed bytes are read as aligned 32-bit words starting at the word that holds the first byte.  On the device
-// lane l keeps word (32 * window + l) in a register and the next window is already in flight; `in_words` bounds the
-// reads (words beyond it read as 0 and raise kInfInputOverrun only if their bits are consumed).
+// the current 32-word window sits in the warp's shared memory (a refill is one broadcast load, no shuffle), lane l
+// holds word l of the next window in a register -- already in flight -- and stores it when the window is used up;
+// `in_words` bounds the reads (words beyond it read as 0 and raise kInfInputOverrun only if their bits are consumed).
 struct InfBits {
     const uint32_t *words;       // 4-byte aligned
     uint32_t        n_words;     // words that may be read
     uint32_t        next;        // index of the next word to enter the bit buffer
     uint64_t        buf;
     int             cnt;         // valid bits in buf
-    uint32_t        win, win_next;   // device: this lane's word of the current / next 32-word window
+    uint32_t        win_next;    // device: this lane's word of the next 32-word window
+    uint32_t        wbase;       // device: shared-space address of the current window
 
     PSS_IHD uint32_t load(uint32_t i) const
     {
@@ -109,7 +112,7 @@ struct InfBits {
         return i < n_words ? words[i] : 0u;
 #endif
     }
-    PSS_IHD void open(const uint8_t *p, uint32_t n_bytes)
+    PSS_IHD void open(const uint8_t *p, uint32_t n_bytes, uint32_t *window)
     {
         const uintptr_t a = (uintptr_t)p;
         const uint32_t  mis = (uint32_t)(a & 3u);
@@ -117,10 +120,14 @@ struct InfBits {
         n_words = (n_bytes + mis + 3u) >> 2;
         next = 0;
 #if defined(__CUDA_ARCH__)
-        win = load((uint32_t)InfLanes::lane());
+        wbase = (uint32_t)__cvta_generic_to_shared(window);
+        InfLanes::sync();                                    // nobody reads the old window any more
+        window[InfLanes::lane()] = load((uint32_t)InfLanes::lane());
         win_next = load(32u + (uint32_t)InfLanes::lane());
+        InfLanes::sync();
 #else
-        win = win_next = 0;
+        (void)window;
+        win_next = wbase = 0;
 #endif
         buf = 0; cnt = 0;
         const uint32_t w = take_word();
@@ -130,11 +137,14 @@ struct InfBits {
     PSS_IHD uint32_t take_word()
     {
 #if defined(__CUDA_ARCH__)
-        const uint32_t w = InfLanes::bcast(win, (int)(next & 31u));
+        uint32_t w;
+        asm volatile("{\n\t.reg .u32 t;\n\tmad.lo.u32 t, %1, 4, %2;\n\tld.shared.u32 %0, [t];\n\t}" : "=r"(w) : "r"(next & 31u), "r"(wbase) : "memory");
         next++;
-        if ((next & 31u) == 0u) {                  // warp uniform
-            win = win_next;
+        if ((next & 31u) == 0u) {                  // warp uniform: the window is used up, the next one moves in
+            InfLanes::sync();
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(wbase + 4u * (uint32_t)InfLanes::lane()), "r"(win_next) : "memory");
             win_next = load(next + 32u + (uint32_t)InfLanes::lane());
+            InfLanes::sync();
         }
         return w;
 #else
@@ -600,7 +610,7 @@ PSS_IHD int inflate_block(const uint8_t *in, uint32_t in_len, uint8_t *out, uint
 {
     const int lane = InfLanes::lane(), W = InfLanes::width();
     InfBits   B;
-    B.open(in, in_len);
+    B.open(in, in_len, T.window);
     uint32_t  mis = (uint32_t)((uintptr_t)in & 3u);
     uint32_t  op = 0;
     int       last;
@@ -626,7 +636,7 @@ PSS_IHD int inflate_block(const uint8_t *in, uint32_t in_len, uint8_t *out, uint
             in += at + len;
             in_len -= at + len;
             mis = (uint32_t)((uintptr_t)in & 3u);
-            B.open(in, in_len);
+            B.open(in, in_len, T.window);
             InfLanes::sync();
             continue;
         }
