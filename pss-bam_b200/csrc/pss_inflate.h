@@ -457,7 +457,9 @@ PSS_IHD void inf_copy(uint8_t *wp, uint8_t *wpl, uint32_t dist, uint32_t len, in
     uint32_t back = dist;
     if (dist < len) {                                                           // warp uniform: a run (binned qualities)
         // lane % dist without an integer division: (lane + 0.5) / dist is never within 1e-3 of an integer
-        const uint32_t q = (uint32_t)__fdividef((float)lane + 0.5f, (float)dist);
+        float r;                                             // 1 / dist, approximate (one MUFU): far more precise than needed
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((float)dist));
+        const uint32_t q = (uint32_t)(((float)lane + 0.5f) * r);
         back = dist + q * dist;
     }
     const uintptr_t src = (uintptr_t)(wpl - back);           // this lane's source byte; it fetches the aligned word around it
