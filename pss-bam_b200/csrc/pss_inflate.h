@@ -71,7 +71,8 @@ struct InflateTables {                       // one per warp
 enum : int {
     kInfOk = 0,
     kInfBadBlockType = 1, kInfBadStored = 2, kInfBadCodeLengths = 3, kInfBadSymbol = 4, kInfBadDistance = 5,
-    kInfOutputOverrun = 6, kInfInputOverrun = 7, kInfSizeMismatch = 8
+    kInfOutputOverrun = 6, kInfInputOverrun = 7, kInfSizeMismatch = 8,
+    kInfCrcMismatch = 9                                      // set by the inflate kernel (pss_crc32.h), not by inflate_block
 };
 
 // ---- lane model --------------------------------------------------------------------------------------------------

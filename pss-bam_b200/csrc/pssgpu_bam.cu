@@ -24,6 +24,7 @@
 #include <cstring>
 
 #include "pss_bamrec.h"
+#include "pss_crc32.h"
 #include "pss_inflate.h"
 
 namespace pssgpu {
@@ -79,6 +80,8 @@ struct BamIngest {
     uint8_t  *d_hdr = nullptr;        // copy of the BAM header (reference names)
     uint32_t *d_ref_off = nullptr, *d_ref_len = nullptr;
     char     *d_rg = nullptr;
+    uint32_t *d_crc_tab = nullptr;    // pss_crc32.h tables; null when $PSSGPU_BAM_CRC=0 switches the check off
+    bool      check_crc = true;
     int       rg_len = -1;
     int       inflate_grid = 0, inflate_minb = 3;
     uint64_t  batches = 0;
@@ -93,8 +96,10 @@ __device__ __forceinline__ void bam_fail(BamState *st, unsigned code, unsigned a
 // MINB = CTAs per SM the register allocation aims at: 3 (30 warps at the default 10 warps per CTA, 64 registers) or 2
 template <int MINB>
 __global__ void __launch_bounds__(kInfWarps * 32, MINB)
-bgzf_inflate_kernel(const BamDesc *__restrict__ desc, uint32_t n_blocks, const uint8_t *__restrict__ comp, uint8_t *udata, BamState *st)
+bgzf_inflate_kernel(const BamDesc *__restrict__ desc, uint32_t n_blocks, const uint8_t *__restrict__ comp, uint8_t *udata, BamState *st,
+                    const uint32_t *__restrict__ crc_tab)
 {
+    static_assert(sizeof(InflateTables) >= sizeof(uint32_t) * kCrcSmemWords, "the CRC tables borrow the warp's decode tables");
     extern __shared__ __align__(16) unsigned char smem[];
     InflateTables &T = reinterpret_cast<InflateTables *>(smem)[threadIdx.x >> 5];
     const uint32_t lane = threadIdx.x & 31u;
@@ -106,6 +111,18 @@ bgzf_inflate_kernel(const BamDesc *__restrict__ desc, uint32_t n_blocks, const u
         const BamDesc d = desc[b];
         int rc = kInfOk;
         if (d.isize) rc = inflate_block(comp + d.src_off, d.c_len, udata + d.dst_off, d.isize, T);
+        if (rc == kInfOk && d.isize && crc_tab) {
+            // the CRC32 of the gzip trailer (htslib checks it, so the reference never sees a damaged block): the decode
+            // tables are dead now, their shared memory takes the CRC tables; every lane sums its own words (pss_crc32.h)
+            uint32_t *ct = reinterpret_cast<uint32_t *>(&T);
+            __syncwarp();                                    // the block is written, the decode tables are no longer read
+            for (uint32_t i = lane; i < (uint32_t)kCrcSmemWords; i += 32) ct[i] = __ldg(crc_tab + i);
+            __syncwarp();
+            const uint32_t got = crc32_warp(udata + d.dst_off, d.isize, ct, crc_tab + kCrcXk);
+            const uint8_t *tr = comp + d.src_off + d.c_len;
+            const uint32_t want = (uint32_t)__ldg(tr) | ((uint32_t)__ldg(tr + 1) << 8) | ((uint32_t)__ldg(tr + 2) << 16) | ((uint32_t)__ldg(tr + 3) << 24);
+            if (got != want) rc = kInfCrcMismatch;
+        }
         if (rc != kInfOk && lane == 0) bam_fail(st, kBamErrInflate + (unsigned)rc, b);
         __syncwarp();
     }
@@ -401,9 +418,10 @@ static const char *bam_error_text(unsigned code)
 {
     if (code >= kBamErrInflate && code < kBamErrInflate + 16) {
         static const char *inf[] = { "", "reserved block type", "stored block length check", "invalid code lengths", "invalid literal/length symbol",
-                                     "invalid distance", "more data than ISIZE", "compressed data ends early", "less data than ISIZE" };
+                                     "invalid distance", "more data than ISIZE", "compressed data ends early", "less data than ISIZE",
+                                     "CRC32 of a BGZF block does not match its data" };
         const unsigned k = code - kBamErrInflate;
-        return k < 9 ? inf[k] : "inflate";
+        return k < 10 ? inf[k] : "inflate";
     }
     switch (code) {
     case kBamErrMagic: return "not a BAM stream (magic)";
@@ -441,7 +459,7 @@ void bam_destroy(pssgpu_ctx *ctx)
     cudaFree(B->d_state); cudaFree(B->d_ubuf); cudaFree(B->d_text); cudaFree(B->d_loc); cudaFree(B->d_comp[0]); cudaFree(B->d_comp[1]);
     cudaFree(B->d_s); cudaFree(B->d_e); cudaFree(B->d_n);
     for (int i = 0; i < 2; i++) { cudaFree(B->d_desc[i]); if (B->h_desc[i]) cudaFreeHost(B->h_desc[i]); }
-    cudaFree(B->d_hdr); cudaFree(B->d_ref_off); cudaFree(B->d_ref_len); cudaFree(B->d_rg);
+    cudaFree(B->d_hdr); cudaFree(B->d_ref_off); cudaFree(B->d_ref_len); cudaFree(B->d_rg); cudaFree(B->d_crc_tab);
     delete B;
     ctx->bam = nullptr;
 }
@@ -501,6 +519,13 @@ int bam_ensure(pssgpu_ctx *ctx)
     CU(cudaMalloc(&B->d_ref_off, (size_t)kBamMaxRefs * sizeof(uint32_t)));
     CU(cudaMalloc(&B->d_ref_len, (size_t)kBamMaxRefs * sizeof(uint32_t)));
     CU(cudaMalloc(&B->d_rg, 256));
+    if (const char *e = getenv("PSSGPU_BAM_CRC")) B->check_crc = atoi(e) != 0;
+    if (B->check_crc) {
+        std::vector<uint32_t> tab(kCrcTableWords);
+        crc32_build_tables(tab.data());
+        CU(cudaMalloc(&B->d_crc_tab, tab.size() * sizeof(uint32_t)));
+        CU(cudaMemcpy(B->d_crc_tab, tab.data(), tab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
     const size_t smem = (size_t)kInfWarps * sizeof(InflateTables);
     if (const char *e = getenv("PSSGPU_INFLATE_CTAS")) B->inflate_minb = atoi(e) == 2 ? 2 : 3;      // tuning switch
     CU(cudaFuncSetAttribute(bgzf_inflate_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -568,9 +593,9 @@ int bam_submit(pssgpu_ctx *ctx, const uint8_t *src, size_t comp_len, uint32_t n_
         const unsigned grid = (unsigned)std::min<uint64_t>((n_blocks + kInfWarps - 1) / kInfWarps, (uint64_t)B->inflate_grid);
         time_begin(ctx, comp_len);
         if (B->inflate_minb == 2)
-            bgzf_inflate_kernel<2><<<grid, kInfWarps * 32, smem, st>>>(B->d_desc[cur], n_blocks, B->d_comp[cur], B->d_ubuf + kBamCarryCap, S);
+            bgzf_inflate_kernel<2><<<grid, kInfWarps * 32, smem, st>>>(B->d_desc[cur], n_blocks, B->d_comp[cur], B->d_ubuf + kBamCarryCap, S, B->d_crc_tab);
         else
-            bgzf_inflate_kernel<3><<<grid, kInfWarps * 32, smem, st>>>(B->d_desc[cur], n_blocks, B->d_comp[cur], B->d_ubuf + kBamCarryCap, S);
+            bgzf_inflate_kernel<3><<<grid, kInfWarps * 32, smem, st>>>(B->d_desc[cur], n_blocks, B->d_comp[cur], B->d_ubuf + kBamCarryCap, S, B->d_crc_tab);
         time_end(ctx);
     }
     bam_prepare_kernel<<<1, 32, 0, st>>>(S, B->d_ubuf, total_u, B->d_hdr, B->d_ref_off, B->d_ref_len);

@@ -4,6 +4,7 @@
 #include <vector>
 
 #include "../../pss-bam_b200/csrc/pss_bamrec.h"
+#include "../../pss-bam_b200/csrc/pss_crc32.h"
 #include "../../pss-bam_b200/csrc/pss_inflate.h"
 
 using namespace pssgpu;
@@ -14,6 +15,27 @@ int emul_inflate(const uint8_t *in, uint32_t in_len, uint8_t *out, uint32_t out_
 {
     static thread_local InflateTables T;
     return inflate_block(in, in_len, out, out_len, T);
+}
+
+// CRC-32 of [p, p + n) the way the inflate kernel computes it: the 32 lanes of the warp played one after the other
+uint32_t emul_crc32(const uint8_t *p, uint32_t n)
+{
+    static uint32_t tab[kCrcTableWords];
+    static bool     built = false;
+    if (!built) { crc32_build_tables(tab); built = true; }
+    uint32_t       head;
+    uint32_t       s = crc32_head(p, n, tab, &head);
+    const uint32_t n_words = (n - head) >> 2;
+    if (n_words) {
+        uint32_t c = 0;
+        for (uint32_t lane = 0; lane < (uint32_t)kCrcLanes; lane++) {
+            uint32_t       shift;
+            const uint32_t u = crc32_lane_partial(reinterpret_cast<const uint32_t *>(p + head), n_words, lane, s, tab, &shift);
+            if (shift) c ^= crc_mulmod(tab[kCrcXk + shift], u);
+        }
+        s = c;
+    }
+    return crc32_tail(p + head + 4u * n_words, (n - head) & 3u, s, tab);
 }
 
 // header of an inflated BAM stream: returns its length (0: incomplete / not BAM) and fills the dictionary

@@ -733,7 +733,7 @@ BAM_EMUL_VARIANTS = {"": [], "walk": ["-DPSS_INF_LIT_SUB=8"], "lit9": ["-DPSS_IN
 
 def build_bam_emul(force=False, variant=""):
     src = os.path.join(ROOT, "tests", "host_emul", "pss_bam_emul.cpp")
-    hdrs = [os.path.join(ROOT, "pss-bam_b200", "csrc", h) for h in ("pss_inflate.h", "pss_bamrec.h", "pss_record.h")]
+    hdrs = [os.path.join(ROOT, "pss-bam_b200", "csrc", h) for h in ("pss_inflate.h", "pss_bamrec.h", "pss_record.h", "pss_crc32.h")]
     newest = max(os.path.getmtime(f) for f in [src] + hdrs)
     target = BAM_EMUL_SO if not variant else BAM_EMUL_SO.replace(".so", f"_{variant}.so")
     return _locked_build(target, newest, force,
@@ -762,8 +762,16 @@ class BamEmul:
                                             C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
             lib.emul_bam_render.restype = C.c_long
             lib.emul_bam_guess_stats.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)]
+            lib.emul_crc32.argtypes = [C.c_void_p, C.c_uint32]
+            lib.emul_crc32.restype = C.c_uint32
             cls._lib = lib
         return cls._lib
+
+    @classmethod
+    def crc32(cls, data: np.ndarray, offset: int, n: int) -> int:
+        """CRC-32 of data[offset : offset + n] by the lane code of the inflate kernel (pss_crc32.h)."""
+        assert data.dtype == np.uint8 and offset + n <= data.size
+        return int(cls.lib().emul_crc32(data.ctypes.data + offset, n))
 
     @classmethod
     def inflate(cls, bam: bytes) -> bytes:

@@ -67,6 +67,24 @@ def test_inflate_logic_matches_zlib(variant):
             assert lib.emul_inflate(C.addressof(buf) + pad, len(comp), C.addressof(out), n + 1) != 0
 
 
+def test_crc32_lane_logic_matches_zlib():
+    """pss_crc32.h: interleaved words per lane, advance tables, x^(32 k) fix-up -- every length class and alignment."""
+    rng = np.random.default_rng(77)
+    buf = rng.integers(0, 256, size=70000 + 16, dtype=np.uint8)
+    base = (-buf.ctypes.data) % 4                      # offset of a 4-byte aligned address
+    lengths = list(range(0, 300)) + [511, 512, 513, 1023, 4095, 4096, 4097, 65279, 65280, 65535, 65536]
+    lengths += [int(x) for x in rng.integers(300, 65536, size=60)]
+    for n in lengths:
+        for mis in range(4):
+            want = zlib.crc32(buf[base + mis: base + mis + n].tobytes())
+            got = BamEmul.crc32(buf, base + mis, n)
+            assert got == want, (n, mis, hex(got), hex(want))
+    z = np.zeros(65536 + 8, dtype=np.uint8)            # all-zero and all-ones payloads
+    assert BamEmul.crc32(z, 0, 65536) == zlib.crc32(bytes(65536))
+    z[:] = 255
+    assert BamEmul.crc32(z, 1, 65535) == zlib.crc32(b"\xff" * 65535)
+
+
 def test_inflate_logic_survives_corrupt_streams():
     lib = BamEmul.lib()
     rng = random.Random(2)

@@ -180,5 +180,37 @@ def test_bam_malformed_input_is_reported(small):
     blk = (b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + (len(comp) + 25).to_bytes(2, "little") + comp
            + zlib.crc32(raw).to_bytes(4, "little") + len(raw).to_bytes(4, "little"))
     assert "magic" in run(blk)
+    # the CRC32 of every block is checked on the device (htslib does, so the reference never tallies a damaged block):
+    # a wrong trailer, and a stored block whose payload changed under an intact deflate structure
+    bad = bytearray(bam)
+    at, total, po, pl, isize = blocks[len(blocks) // 2]
+    bad[at + total - 8] ^= 0x01
+    assert "CRC32" in run(bytes(bad))
+    bam0 = Synth.bam(sam, _refs(g), level=0)
+    b0 = bgzf_blocks(bam0)
+    at, total, po, pl, isize = b0[len(b0) // 2]
+    bad = bytearray(bam0)
+    bad[po + pl - 1] ^= 0x40                                               # last payload byte of a stored block: a QUAL or tag byte
+    assert "CRC32" in run(bytes(bad))
+    run(bam0, expect_ok=True)
     # and the context still works afterwards
     _check_pss(ctx, ora, bam, sam)
+
+
+def test_bam_crc_check_can_be_switched_off(small):
+    """$PSSGPU_BAM_CRC=0 (read when a context first ingests BAM): a wrong CRC32 trailer is then ignored, as before."""
+    g, ora, _ = small
+    sam = Synth.sam(reads_cfg_config1(seed=12), g, 0, 3000)
+    bam = Synth.bam(sam, _refs(g))
+    blocks = bgzf_blocks(bam)
+    bad = bytearray(bam)
+    at, total, po, pl, isize = blocks[1]
+    bad[at + total - 7] ^= 0x80
+    os.environ["PSSGPU_BAM_CRC"] = "0"
+    try:
+        ctx = pkg.Context(0)
+        ctx.upload_genome(ora.contigs())
+        _check_pss(ctx, ora, bytes(bad), sam)
+        ctx.close()
+    finally:
+        del os.environ["PSSGPU_BAM_CRC"]
