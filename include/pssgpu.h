@@ -184,8 +184,9 @@ int pssgpu_feed_device(pssgpu_ctx *ctx, const void *d_sam, size_t len);
  * identical to feeding `samtools view` output of the same file.  Returns once
  * the bytes have been copied to the device, like pssgpu_feed.  Malformed input
  * (bad BGZF / BAM structure, a file that ends inside a record) is reported by
- * pssgpu_sync / *_finish as PSSGPU_EINVAL.  CRC32s are not verified.  Do not mix
- * with pssgpu_feed within one tally. */
+ * pssgpu_sync / *_finish as PSSGPU_EINVAL; so is a block whose CRC32 does not
+ * match its data (htslib checks it too; $PSSGPU_BAM_CRC=0 switches the check
+ * off).  Do not mix with pssgpu_feed within one tally. */
 int pssgpu_feed_bam(pssgpu_ctx *ctx, const void *bgzf_bytes, size_t len, int last);
 /* `samtools view -r RG`, natively (pss-bam.c:153-155 `-R`): only alignments
  * whose RG:Z tag equals `read_group` are tallied; NULL switches the filter off.
@@ -281,6 +282,18 @@ int pssgpu_group_both_begin(pssgpu_group *g, const pssgpu_pss_params *pss, const
 /* Whole lines (a piece ends with '\n' unless `last`); pieces go to the members in turn. */
 int pssgpu_group_feed(pssgpu_group *g, const char *sam_bytes, size_t len, int last);
 int pssgpu_group_sync(pssgpu_group *g);
+/* A BAM FILE over the GPUs of a group (pssgpu_feed_bam's contract: the file's
+ * bytes in any chunking, `last` marks the end).  Records run across BGZF blocks,
+ * so the stream cannot be dealt like text; the inflate -- five sixths of the
+ * ingest -- can: batches of BGZF blocks go to the members in turn, each inflates
+ * its batches, member 0 fetches the inflated bytes with a peer copy and frames,
+ * renders and tallies them in file order (the other members' tables stay zero;
+ * the sums are the same).  Two GPUs alternate; with more, member 0 does not
+ * inflate.  Replaces the same samtools child (pss-bam.c:148-162, fragkon.c:84-93).
+ * batches_per_member: may be NULL; one entry per member otherwise. */
+int pssgpu_group_feed_bam(pssgpu_group *g, const void *bgzf_bytes, size_t len, int last);
+int pssgpu_group_bam_read_group(pssgpu_group *g, const char *read_group);
+int pssgpu_group_bam_info(pssgpu_group *g, pssgpu_bam_stats *out, uint64_t *batches_per_member);
 int pssgpu_group_pss_finish(pssgpu_group *g, uint64_t *fwd, uint64_t *rev);
 int pssgpu_group_fragkon_finish(pssgpu_group *g, uint64_t *fp, uint64_t *tp);
 int pssgpu_group_get_stats(pssgpu_group *g, pssgpu_stats *out, int fragkon);

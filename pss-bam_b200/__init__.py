@@ -117,6 +117,7 @@ ABI_SYMBOLS = (
     "pssgpu_group_init", "pssgpu_group_destroy", "pssgpu_group_size", "pssgpu_group_ctx", "pssgpu_group_last_error",
     "pssgpu_group_reduce_backend", "pssgpu_group_last_reduce_ms", "pssgpu_group_genome_upload", "pssgpu_group_genome_load_tagged",
     "pssgpu_group_pss_begin", "pssgpu_group_fragkon_begin", "pssgpu_group_both_begin", "pssgpu_group_feed", "pssgpu_group_sync",
+    "pssgpu_group_feed_bam", "pssgpu_group_bam_read_group", "pssgpu_group_bam_info",
     "pssgpu_group_pss_finish", "pssgpu_group_fragkon_finish", "pssgpu_group_get_stats", "pssgpu_group_kmer_spectrum",
     "pssgpu_pss_finish", "pssgpu_pss_finish_device", "pssgpu_get_stats", "pssgpu_both_begin", "pssgpu_get_fragkon_stats",
     "pssgpu_fragkon_default_params", "pssgpu_fragkon_begin", "pssgpu_fragkon_finish", "pssgpu_fragkon_finish_device",
@@ -183,6 +184,9 @@ def load_library():
     lib.pssgpu_group_fragkon_begin.argtypes = [P, C.POINTER(_FkParams)]
     lib.pssgpu_group_both_begin.argtypes = [P, C.POINTER(_PssParams), C.POINTER(_FkParams)]
     lib.pssgpu_group_feed.argtypes = [P, P, C.c_size_t, C.c_int]
+    lib.pssgpu_group_feed_bam.argtypes = [P, P, C.c_size_t, C.c_int]
+    lib.pssgpu_group_bam_read_group.argtypes = [P, C.c_char_p]
+    lib.pssgpu_group_bam_info.argtypes = [P, P, P]
     lib.pssgpu_group_sync.argtypes = [P]
     lib.pssgpu_group_pss_finish.argtypes = [P, P, P]
     lib.pssgpu_group_fragkon_finish.argtypes = [P, P, P]
@@ -515,6 +519,29 @@ class Group:
         addr, n, keep = _host_view(sam)
         self._ck(self.lib.pssgpu_group_feed(self.h, addr, n, 1 if last else 0))
         del keep
+
+    def feed_bam(self, bam, last=False):
+        """Bytes of a BAM file: the inflate is dealt to the members, member 0 frames, renders and tallies (pssgpu_group_feed_bam)."""
+        addr, n, keep = _host_view(bam)
+        self._ck(self.lib.pssgpu_group_feed_bam(self.h, addr, n, 1 if last else 0))
+        del keep
+
+    def feed_bam_ptr(self, host_ptr: int, nbytes: int, last: bool = False):
+        self._ck(self.lib.pssgpu_group_feed_bam(self.h, host_ptr, nbytes, 1 if last else 0))
+
+    def bam_read_group(self, rg):
+        self._ck(self.lib.pssgpu_group_bam_read_group(self.h, None if rg is None else (rg.encode() if isinstance(rg, str) else bytes(rg))))
+
+    def bam_info(self):
+        s = _BamStats()
+        per = (C.c_uint64 * self.size)()
+        self._ck(self.lib.pssgpu_group_bam_info(self.h, C.byref(s), per))
+        d = {k: int(getattr(s, k)) for k, _ in _BamStats._fields_}
+        d["batches_per_member"] = [int(x) for x in per]
+        return d
+
+    def sync(self):
+        self._ck(self.lib.pssgpu_group_sync(self.h))
 
     def pss_finish(self):
         R = self._R

@@ -77,6 +77,7 @@ struct BamIngest {
     uint32_t *d_s = nullptr, *d_e = nullptr, *d_n = nullptr;     // per block: guessed start, chain exit, records
     BamDesc  *d_desc[2] = { nullptr, nullptr };
     BamDesc  *h_desc[2] = { nullptr, nullptr };                  // pinned
+    uint8_t  *h_pfx[2] = { nullptr, nullptr };                   // pinned: a BGZF block that arrived in two feed calls
     uint8_t  *d_hdr = nullptr;        // copy of the BAM header (reference names)
     uint32_t *d_ref_off = nullptr, *d_ref_len = nullptr;
     char     *d_rg = nullptr;
@@ -85,12 +86,25 @@ struct BamIngest {
     int       rg_len = -1;
     int       inflate_grid = 0, inflate_minb = 3;
     uint64_t  batches = 0;
+    // several GPUs (pssgpu_group_feed_bam): this context frames, renders and tallies; `helpers` inflate batches for it
+    std::vector<pssgpu_ctx *> helpers;
+    std::vector<cudaEvent_t>  ev_fetched;        // per helper: its inflated batch has been copied over (its buffer is free)
+    std::vector<uint64_t>     helper_batches;
+    cudaEvent_t   desc_reader[2] = { nullptr, nullptr };   // a helper's copy that also reads h_desc[i] (its ev_copied)
+    unsigned int *d_remote_err = nullptr;        // error / error_arg of the helper whose batch was fetched last
+    uint64_t      dealt = 0, own_batches = 0;
 };
 
 // ------------------------------------------------------------------------------------------------------------ kernels
 __device__ __forceinline__ void bam_fail(BamState *st, unsigned code, unsigned arg)
 {
     if (atomicCAS(&st->error, 0u, code) == 0u) st->error_arg = arg;
+}
+
+// an inflate error flagged on the GPU that inflated a batch for this one (pssgpu_group_feed_bam)
+__global__ void bam_merge_error_kernel(BamState *st, const unsigned int *remote)
+{
+    if (remote[0]) bam_fail(st, remote[0], remote[1]);
 }
 
 // MINB = CTAs per SM the register allocation aims at: 3 (30 warps at the default 10 warps per CTA, 64 registers) or 2
@@ -443,6 +457,8 @@ void bam_reset(pssgpu_ctx *ctx)
     B->carry.clear();
     B->finished = false;
     B->batches = 0;
+    B->dealt = B->own_batches = 0;
+    for (uint64_t &h : B->helper_batches) h = 0;
     if (B->d_state) {
         BamState z;
         memset(&z, 0, sizeof z);
@@ -458,8 +474,9 @@ void bam_destroy(pssgpu_ctx *ctx)
     if (!B) return;
     cudaFree(B->d_state); cudaFree(B->d_ubuf); cudaFree(B->d_text); cudaFree(B->d_loc); cudaFree(B->d_comp[0]); cudaFree(B->d_comp[1]);
     cudaFree(B->d_s); cudaFree(B->d_e); cudaFree(B->d_n);
-    for (int i = 0; i < 2; i++) { cudaFree(B->d_desc[i]); if (B->h_desc[i]) cudaFreeHost(B->h_desc[i]); }
-    cudaFree(B->d_hdr); cudaFree(B->d_ref_off); cudaFree(B->d_ref_len); cudaFree(B->d_rg); cudaFree(B->d_crc_tab);
+    for (int i = 0; i < 2; i++) { cudaFree(B->d_desc[i]); if (B->h_desc[i]) cudaFreeHost(B->h_desc[i]); if (B->h_pfx[i]) cudaFreeHost(B->h_pfx[i]); }
+    cudaFree(B->d_hdr); cudaFree(B->d_ref_off); cudaFree(B->d_ref_len); cudaFree(B->d_rg); cudaFree(B->d_crc_tab); cudaFree(B->d_remote_err);
+    for (cudaEvent_t e : B->ev_fetched) cudaEventDestroy(e);
     delete B;
     ctx->bam = nullptr;
 }
@@ -493,53 +510,61 @@ int bam_check(pssgpu_ctx *ctx, bool finishing)
 
 namespace {
 
-int bam_ensure(pssgpu_ctx *ctx)
+// inflate_only: the context inflates batches for another one (pssgpu_group_feed_bam) -- the inflated buffer, the
+// compressed staging and the inflate tables are all it needs; the framing / rendering buffers (4.8 GB at the default
+// batch size) are allocated when the context is first fed a BAM itself
+int bam_ensure(pssgpu_ctx *ctx, bool inflate_only = false)
 {
     if (!ctx->bam) ctx->bam = new BamIngest();
     BamIngest *B = ctx->bam;
-    if (B->d_state) return PSSGPU_OK;
-    size_t mb = kBamBatchCompDefault >> 20;
-    if (const char *e = getenv("PSSGPU_BAM_BATCH_MB")) mb = std::min<size_t>(std::max<size_t>(1, strtoull(e, nullptr, 10)), 512);
-    B->batch_comp = mb << 20;
-    B->batch_u = 6 * B->batch_comp;                        // a batch also closes when its inflated size reaches this
-    B->text_cap = 3 * B->batch_u + (64ull << 20);          // lines are ~1.3 x the record bytes; beyond the cap: error, never silence
-    CU(cudaMalloc(&B->d_state, sizeof(BamState)));
-    CU(cudaMalloc(&B->d_ubuf, kBamCarryCap + B->batch_u + (1u << 20)));
-    for (int i = 0; i < 2; i++) CU(cudaMalloc(&B->d_comp[i], B->batch_comp + (128u << 10)));
+    if (!B->d_state) {
+        size_t mb = kBamBatchCompDefault >> 20;
+        if (const char *e = getenv("PSSGPU_BAM_BATCH_MB")) mb = std::min<size_t>(std::max<size_t>(1, strtoull(e, nullptr, 10)), 512);
+        B->batch_comp = mb << 20;
+        B->batch_u = 6 * B->batch_comp;                        // a batch also closes when its inflated size reaches this
+        B->text_cap = 3 * B->batch_u + (64ull << 20);          // lines are ~1.3 x the record bytes; beyond the cap: error, never silence
+        CU(cudaMalloc(&B->d_ubuf, kBamCarryCap + B->batch_u + (1u << 20)));
+        for (int i = 0; i < 2; i++) CU(cudaMalloc(&B->d_comp[i], B->batch_comp + (128u << 10)));
+        for (int i = 0; i < 2; i++) {
+            CU(cudaMalloc(&B->d_desc[i], kBamMaxBlocks * sizeof(BamDesc)));
+            CU(cudaMallocHost(&B->h_desc[i], kBamMaxBlocks * sizeof(BamDesc)));
+            CU(cudaMallocHost(&B->h_pfx[i], 65536 + 64));
+        }
+        if (const char *e = getenv("PSSGPU_BAM_CRC")) B->check_crc = atoi(e) != 0;
+        if (B->check_crc) {
+            std::vector<uint32_t> tab(kCrcTableWords);
+            crc32_build_tables(tab.data());
+            CU(cudaMalloc(&B->d_crc_tab, tab.size() * sizeof(uint32_t)));
+            CU(cudaMemcpy(B->d_crc_tab, tab.data(), tab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        }
+        const size_t smem = (size_t)kInfWarps * sizeof(InflateTables);
+        if (const char *e = getenv("PSSGPU_INFLATE_CTAS")) B->inflate_minb = atoi(e) == 2 ? 2 : 3;      // tuning switch
+        CU(cudaFuncSetAttribute(bgzf_inflate_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(bgzf_inflate_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        if (B->inflate_minb == 2) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bgzf_inflate_kernel<2>, kInfWarps * 32, smem));
+        else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bgzf_inflate_kernel<3>, kInfWarps * 32, smem));
+        if (occ < 1) return fail(ctx, PSSGPU_ECUDA, "BAM ingest: the inflate kernel does not fit an SM");
+        B->inflate_grid = occ * ctx->sm_count;
+        CU(cudaMemset(B->d_ubuf, 0, kBamCarryCap));
+        BamState z;
+        memset(&z, 0, sizeof z);
+        z.entry = kBamCarryCap;
+        CU(cudaMalloc(&B->d_state, sizeof(BamState)));         // last: d_state != nullptr <=> the inflate part is complete
+        CU(cudaMemcpy(B->d_state, &z, sizeof z, cudaMemcpyHostToDevice));
+    }
+    if (inflate_only || B->d_rg) return PSSGPU_OK;
     CU(cudaMalloc(&B->d_text, B->text_cap + 4096));
     CU(cudaMalloc(&B->d_loc, (size_t)kBamMaxBlocks * kBamLocCap * sizeof(uint32_t)));
     CU(cudaMalloc(&B->d_s, kBamMaxBlocks * sizeof(uint32_t)));
     CU(cudaMalloc(&B->d_e, kBamMaxBlocks * sizeof(uint32_t)));
     CU(cudaMalloc(&B->d_n, kBamMaxBlocks * sizeof(uint32_t)));
-    for (int i = 0; i < 2; i++) {
-        CU(cudaMalloc(&B->d_desc[i], kBamMaxBlocks * sizeof(BamDesc)));
-        CU(cudaMallocHost(&B->h_desc[i], kBamMaxBlocks * sizeof(BamDesc)));
-    }
     CU(cudaMalloc(&B->d_hdr, kBamCarryCap + 64));
     CU(cudaMalloc(&B->d_ref_off, (size_t)kBamMaxRefs * sizeof(uint32_t)));
     CU(cudaMalloc(&B->d_ref_len, (size_t)kBamMaxRefs * sizeof(uint32_t)));
-    CU(cudaMalloc(&B->d_rg, 256));
-    if (const char *e = getenv("PSSGPU_BAM_CRC")) B->check_crc = atoi(e) != 0;
-    if (B->check_crc) {
-        std::vector<uint32_t> tab(kCrcTableWords);
-        crc32_build_tables(tab.data());
-        CU(cudaMalloc(&B->d_crc_tab, tab.size() * sizeof(uint32_t)));
-        CU(cudaMemcpy(B->d_crc_tab, tab.data(), tab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    }
-    const size_t smem = (size_t)kInfWarps * sizeof(InflateTables);
-    if (const char *e = getenv("PSSGPU_INFLATE_CTAS")) B->inflate_minb = atoi(e) == 2 ? 2 : 3;      // tuning switch
-    CU(cudaFuncSetAttribute(bgzf_inflate_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU(cudaFuncSetAttribute(bgzf_inflate_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    if (B->inflate_minb == 2) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bgzf_inflate_kernel<2>, kInfWarps * 32, smem));
-    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bgzf_inflate_kernel<3>, kInfWarps * 32, smem));
-    if (occ < 1) return fail(ctx, PSSGPU_ECUDA, "BAM ingest: the inflate kernel does not fit an SM");
-    B->inflate_grid = occ * ctx->sm_count;
-    BamState z;
-    memset(&z, 0, sizeof z);
-    z.entry = kBamCarryCap;
-    CU(cudaMemcpy(B->d_state, &z, sizeof z, cudaMemcpyHostToDevice));
-    CU(cudaMemset(B->d_ubuf, 0, kBamCarryCap));
+    CU(cudaMalloc(&B->d_remote_err, 2 * sizeof(unsigned int)));
+    CU(cudaMalloc(&B->d_rg, 256));                             // last: d_rg != nullptr <=> the framing part is complete
+    if (B->use_rg && B->rg_len > 0) CU(cudaMemcpy(B->d_rg, B->read_group.data(), (size_t)B->rg_len, cudaMemcpyHostToDevice));
     return PSSGPU_OK;
 }
 
@@ -573,30 +598,93 @@ int bgzf_frame(const uint8_t *p, size_t n, uint32_t *total, uint32_t *pay_off, u
     return 1;
 }
 
-// Submit the blocks framed in h_desc[cur][0 .. n_blocks): compressed bytes [src, src + comp_len) -> staging, kernels.
-int bam_submit(pssgpu_ctx *ctx, const uint8_t *src, size_t comp_len, uint32_t n_blocks, uint64_t total_u, int is_last)
+// compressed bytes + block descriptors -> W's staging buffers, inflate on W's stream into W's inflated buffer; `desc` is
+// pinned host memory.  W may be the context that frames the batch or a helper on another GPU.
+int bam_stage_and_inflate(pssgpu_ctx *W, const uint8_t *pfx, size_t pfx_len, const uint8_t *src, size_t comp_len, const BamDesc *desc,
+                          uint32_t n_blocks)
+{
+    pssgpu_ctx *ctx = W;                                   // (the CU macro reports through `ctx`)
+    BamIngest  *B = W->bam;
+    const int   cur = W->cur;
+    // pfx: a block that arrived in two feed calls (pinned copy), in front of the blocks that lie in the caller's buffer
+    if (pfx_len) CU(cudaMemcpyAsync(B->d_comp[cur], pfx, pfx_len, cudaMemcpyHostToDevice, W->copy_stream));
+    if (comp_len) CU(cudaMemcpyAsync(B->d_comp[cur] + pfx_len, src, comp_len, cudaMemcpyHostToDevice, W->copy_stream));
+    CU(cudaMemcpyAsync(B->d_desc[cur], desc, n_blocks * sizeof(BamDesc), cudaMemcpyHostToDevice, W->copy_stream));
+    W->h2d_bytes += pfx_len + comp_len;
+    CU(cudaEventRecord(W->ev_copied[cur], W->copy_stream));
+    CU(cudaStreamWaitEvent(W->stream, W->ev_copied[cur], 0));
+    cudaStream_t st = W->stream;
+    CU(cudaMemsetAsync(&B->d_state->work_ctr, 0, sizeof(unsigned int), st));
+    const size_t   smem = (size_t)kInfWarps * sizeof(InflateTables);
+    const unsigned grid = (unsigned)std::min<uint64_t>((n_blocks + kInfWarps - 1) / kInfWarps, (uint64_t)B->inflate_grid);
+    time_begin(W, pfx_len + comp_len);
+    if (B->inflate_minb == 2)
+        bgzf_inflate_kernel<2><<<grid, kInfWarps * 32, smem, st>>>(B->d_desc[cur], n_blocks, B->d_comp[cur], B->d_ubuf + kBamCarryCap, B->d_state, B->d_crc_tab);
+    else
+        bgzf_inflate_kernel<3><<<grid, kInfWarps * 32, smem, st>>>(B->d_desc[cur], n_blocks, B->d_comp[cur], B->d_ubuf + kBamCarryCap, B->d_state, B->d_crc_tab);
+    time_end(W);
+    CU(cudaGetLastError());
+    return PSSGPU_OK;
+}
+
+// Submit the blocks framed in h_desc[cur][0 .. n_blocks): compressed bytes pfx[0 .. pfx_len) + [src, src + comp_len) ->
+// staging, kernels.  may_deal: with helpers (pssgpu_group_feed_bam) the batch may be inflated on another GPU and fetched
+// from there.
+int bam_submit(pssgpu_ctx *ctx, const uint8_t *pfx, size_t pfx_len, const uint8_t *src, size_t comp_len, uint32_t n_blocks, uint64_t total_u,
+               int is_last, bool may_deal = false)
 {
     BamIngest *B = ctx->bam;
     const int  cur = ctx->cur;
-    if (n_blocks) {
-        CU(cudaMemcpyAsync(B->d_comp[cur], src, comp_len, cudaMemcpyHostToDevice, ctx->copy_stream));
-        CU(cudaMemcpyAsync(B->d_desc[cur], B->h_desc[cur], n_blocks * sizeof(BamDesc), cudaMemcpyHostToDevice, ctx->copy_stream));
-        ctx->h2d_bytes += comp_len;
-    }
-    CU(cudaEventRecord(ctx->ev_copied[cur], ctx->copy_stream));
-    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[cur], 0));
     cudaStream_t st = ctx->stream;
     BamState    *S = B->d_state;
-    CU(cudaMemsetAsync(&S->work_ctr, 0, sizeof(unsigned int), st));
-    if (n_blocks) {
-        const size_t smem = (size_t)kInfWarps * sizeof(InflateTables);
-        const unsigned grid = (unsigned)std::min<uint64_t>((n_blocks + kInfWarps - 1) / kInfWarps, (uint64_t)B->inflate_grid);
-        time_begin(ctx, comp_len);
-        if (B->inflate_minb == 2)
-            bgzf_inflate_kernel<2><<<grid, kInfWarps * 32, smem, st>>>(B->d_desc[cur], n_blocks, B->d_comp[cur], B->d_ubuf + kBamCarryCap, S, B->d_crc_tab);
-        else
-            bgzf_inflate_kernel<3><<<grid, kInfWarps * 32, smem, st>>>(B->d_desc[cur], n_blocks, B->d_comp[cur], B->d_ubuf + kBamCarryCap, S, B->d_crc_tab);
-        time_end(ctx);
+    int          hi = -1;                                  // helper that inflates this batch
+    if (n_blocks && may_deal && !B->helpers.empty()) {
+        // two GPUs: the batches alternate; more: the first GPU only frames, renders and tallies (a quarter of the work of
+        // a batch, plus fetching it), the others inflate in turn
+        const uint64_t k = B->dealt++;
+        const size_t   nh = B->helpers.size();
+        if (nh == 1) hi = (k & 1) ? 0 : -1;
+        else hi = (int)(k % nh);
+    }
+    B->desc_reader[cur] = nullptr;
+    if (hi < 0) {
+        if (n_blocks) {
+            int rc = bam_stage_and_inflate(ctx, pfx, pfx_len, src, comp_len, B->h_desc[cur], n_blocks);
+            if (rc != PSSGPU_OK) return rc;
+            B->own_batches++;
+        } else {
+            CU(cudaEventRecord(ctx->ev_copied[cur], ctx->copy_stream));
+            CU(cudaStreamWaitEvent(st, ctx->ev_copied[cur], 0));
+        }
+    } else {
+        pssgpu_ctx *W = B->helpers[hi];
+        BamIngest  *Bw = W->bam;
+        const int   wc = W->cur;
+        {
+            Bind bind(W);
+            // the helper's inflated buffer is free once its previous batch has been fetched
+            if (B->helper_batches[hi]) {
+                if (cudaStreamWaitEvent(W->stream, B->ev_fetched[hi], 0) != cudaSuccess)
+                    return fail(ctx, PSSGPU_ECUDA, "feed_bam: GPU %d cannot wait for GPU %d", W->device, ctx->device);
+            }
+            int rc = bam_stage_and_inflate(W, pfx, pfx_len, src, comp_len, B->h_desc[cur], n_blocks);
+            if (rc == PSSGPU_OK && cudaEventRecord(W->ev_tallied[wc], W->stream) != cudaSuccess) rc = PSSGPU_ECUDA;      // "inflated"
+            W->cur ^= 1;
+            // its other staging buffer is free once the batch that used it has been inflated
+            if (rc == PSSGPU_OK && cudaStreamWaitEvent(W->copy_stream, W->ev_tallied[W->cur], 0) != cudaSuccess) rc = PSSGPU_ECUDA;
+            if (rc != PSSGPU_OK) return fail(ctx, rc, "feed_bam: inflate on GPU %d: %s", W->device, pssgpu_last_error(W));
+        }
+        B->desc_reader[cur] = W->ev_copied[wc];
+        B->helper_batches[hi]++;
+        // this GPU: the descriptors, then -- once the helper is done -- the inflated bytes and its error flag over NVLink
+        CU(cudaMemcpyAsync(B->d_desc[cur], B->h_desc[cur], n_blocks * sizeof(BamDesc), cudaMemcpyHostToDevice, ctx->copy_stream));
+        CU(cudaEventRecord(ctx->ev_copied[cur], ctx->copy_stream));
+        CU(cudaStreamWaitEvent(st, ctx->ev_copied[cur], 0));
+        CU(cudaStreamWaitEvent(st, W->ev_tallied[wc], 0));
+        CU(cudaMemcpyPeerAsync(B->d_ubuf + kBamCarryCap, ctx->device, Bw->d_ubuf + kBamCarryCap, W->device, total_u, st));
+        CU(cudaMemcpyPeerAsync(B->d_remote_err, ctx->device, &Bw->d_state->error, W->device, 2 * sizeof(unsigned int), st));
+        CU(cudaEventRecord(B->ev_fetched[hi], st));
+        bam_merge_error_kernel<<<1, 1, 0, st>>>(S, B->d_remote_err);
     }
     bam_prepare_kernel<<<1, 32, 0, st>>>(S, B->d_ubuf, total_u, B->d_hdr, B->d_ref_off, B->d_ref_len);
     if (n_blocks) {
@@ -633,7 +721,7 @@ int feed_bam_impl(pssgpu_ctx *ctx, const uint8_t *data, size_t len, int last)
     BamIngest *B = ctx->bam;
     if (B->finished && len) return fail(ctx, PSSGPU_EINVAL, "feed_bam: data after last=1");
     size_t off = 0;
-    // a block left incomplete by the previous call: completed in the carry buffer and submitted on its own
+    // a block left incomplete by the previous call is completed in the carry buffer
     while (!B->carry.empty() && off < len) {
         uint32_t total = 0, po = 0, pl = 0, isz = 0;
         int fr = bgzf_frame(B->carry.data(), B->carry.size(), &total, &po, &pl, &isz);
@@ -651,30 +739,32 @@ int feed_bam_impl(pssgpu_ctx *ctx, const uint8_t *data, size_t len, int last)
         B->carry.insert(B->carry.end(), data + off, data + off + take);
         off += take;
     }
+    // ... completed now: it becomes the first block of the next batch (through a pinned copy next to the descriptors)
+    bool     pfx_pending = false;
+    uint32_t pfx_total = 0, pfx_po = 0, pfx_pl = 0, pfx_isz = 0;
     if (!B->carry.empty()) {
-        uint32_t total = 0, po = 0, pl = 0, isz = 0;
-        int fr = bgzf_frame(B->carry.data(), B->carry.size(), &total, &po, &pl, &isz);
+        int fr = bgzf_frame(B->carry.data(), B->carry.size(), &pfx_total, &pfx_po, &pfx_pl, &pfx_isz);
         if (fr < 0) return fail(ctx, PSSGPU_EINVAL, "feed_bam: not a BGZF block (at byte %llu)", (unsigned long long)ctx->fed_bytes);
-        if (fr == 1) {
-            const int cur = ctx->cur;
-            CU(cudaEventSynchronize(ctx->ev_copied[cur]));          // h_desc[cur] is free again
-            B->h_desc[cur][0] = BamDesc{ po, pl, 0u, isz };
-            // cudaMemcpyAsync from the (pageable) carry vector: the copy is staged before the call returns
-            int rc = bam_submit(ctx, B->carry.data(), total, 1, isz, 0);
-            if (rc != PSSGPU_OK) return rc;
-            CU(cudaStreamSynchronize(ctx->copy_stream));
-            B->carry.clear();
-        }
+        pfx_pending = fr == 1;
     }
     // whole blocks in place
-    while (off < len) {
+    while (off < len || pfx_pending) {
         const int cur = ctx->cur;
-        CU(cudaEventSynchronize(ctx->ev_copied[cur]));              // h_desc[cur] is free again
+        CU(cudaEventSynchronize(ctx->ev_copied[cur]));              // h_desc[cur] / h_pfx[cur] are free again
+        if (B->desc_reader[cur]) CU(cudaEventSynchronize(B->desc_reader[cur]));      // ... also on the GPU that inflated that batch
         BamDesc *desc = B->h_desc[cur];
         const size_t start = off;
-        uint32_t n_blocks = 0;
+        uint32_t n_blocks = 0, pfx_len = 0;
         uint64_t total_u = 0;
         bool     more = true;
+        if (pfx_pending) {
+            memcpy(B->h_pfx[cur], B->carry.data(), pfx_total);
+            B->carry.clear();
+            desc[n_blocks++] = BamDesc{ pfx_po, pfx_pl, 0u, pfx_isz };
+            total_u = pfx_isz;
+            pfx_len = pfx_total;
+            pfx_pending = false;
+        }
         while (off < len && n_blocks < kBamMaxBlocks) {
             uint32_t total = 0, po = 0, pl = 0, isz = 0;
             int fr = bgzf_frame(data + off, len - off, &total, &po, &pl, &isz);
@@ -683,12 +773,12 @@ int feed_bam_impl(pssgpu_ctx *ctx, const uint8_t *data, size_t len, int last)
             // the first batch of a stream is a quarter batch: its copy is the one nothing overlaps, the GPU starts sooner
             const size_t comp_cap = B->batches == 0 ? std::max<size_t>(B->batch_comp / 4, 1u << 20) : B->batch_comp;
             if ((off - start) + total > comp_cap || total_u + isz > B->batch_u) break;
-            desc[n_blocks++] = BamDesc{ (uint32_t)(off - start) + po, pl, (uint32_t)total_u, isz };
+            desc[n_blocks++] = BamDesc{ pfx_len + (uint32_t)(off - start) + po, pl, (uint32_t)total_u, isz };
             total_u += isz;
             off += total;
         }
         if (n_blocks) {
-            int rc = bam_submit(ctx, data + start, off - start, n_blocks, total_u, 0);
+            int rc = bam_submit(ctx, B->h_pfx[cur], pfx_len, data + start, off - start, n_blocks, total_u, 0, true);
             if (rc != PSSGPU_OK) return rc;
         }
         if (!more) {                                     // an incomplete block at the end of this call
@@ -700,7 +790,7 @@ int feed_bam_impl(pssgpu_ctx *ctx, const uint8_t *data, size_t len, int last)
     if (last) {
         if (!B->carry.empty()) return fail(ctx, PSSGPU_EINVAL, "feed_bam: the stream ends inside a BGZF block (%zu bytes)", B->carry.size());
         // an empty batch with the is_last mark: an unfinished record / header left in the carry is an error
-        int rc = bam_submit(ctx, nullptr, 0, 0, 0, 1);
+        int rc = bam_submit(ctx, nullptr, 0, nullptr, 0, 0, 0, 1);
         if (rc != PSSGPU_OK) return rc;
         B->finished = true;
     }
@@ -708,6 +798,52 @@ int feed_bam_impl(pssgpu_ctx *ctx, const uint8_t *data, size_t len, int last)
 }
 
 }  // namespace
+
+// pssgpu_group_feed_bam: `helpers` (contexts on other GPUs, or -- in tests -- on the same one) inflate batches for ctx
+int bam_set_helpers(pssgpu_ctx *ctx, const std::vector<pssgpu_ctx *> &helpers)
+{
+    {
+        Bind bind(ctx);
+        int  rc = bam_ensure(ctx);
+        if (rc != PSSGPU_OK) return rc;
+    }
+    BamIngest *B = ctx->bam;
+    if (B->helpers == helpers) return PSSGPU_OK;
+    if (B->batches) return fail(ctx, PSSGPU_EINVAL, "feed_bam: the GPUs of a stream cannot change while it is fed");
+    for (pssgpu_ctx *h : helpers) {
+        Bind bind(h);
+        int  rc = bam_ensure(h, true);
+        if (rc != PSSGPU_OK) return fail(ctx, rc, "feed_bam: GPU %d: %s", h->device, pssgpu_last_error(h));
+        if (h->bam->batch_comp != B->batch_comp) return fail(ctx, PSSGPU_EINVAL, "feed_bam: GPU %d was set up with another batch size", h->device);
+        if (h->device != ctx->device) {                    // peer access both ways where the box has it (otherwise the copy is staged)
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, h->device, ctx->device) == cudaSuccess && can) cudaDeviceEnablePeerAccess(ctx->device, 0);
+            cudaGetLastError();
+        }
+    }
+    Bind bind(ctx);
+    for (pssgpu_ctx *h : helpers)
+        if (h->device != ctx->device) {
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, ctx->device, h->device) == cudaSuccess && can) cudaDeviceEnablePeerAccess(h->device, 0);
+            cudaGetLastError();
+        }
+    for (cudaEvent_t e : B->ev_fetched) cudaEventDestroy(e);
+    B->ev_fetched.assign(helpers.size(), nullptr);
+    for (cudaEvent_t &e : B->ev_fetched) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    B->helper_batches.assign(helpers.size(), 0);
+    B->helpers = helpers;
+    return PSSGPU_OK;
+}
+
+// batches inflated on the context's own GPU, and on every helper, since *_begin
+void bam_dealing(pssgpu_ctx *ctx, uint64_t *own, std::vector<uint64_t> *per_helper)
+{
+    BamIngest *B = ctx->bam;
+    *own = B ? B->own_batches : 0;
+    if (B) *per_helper = B->helper_batches; else per_helper->clear();
+}
+
 }  // namespace pssgpu
 
 using namespace pssgpu;
@@ -741,7 +877,11 @@ int pssgpu_feed_bam(pssgpu_ctx *ctx, const void *bgzf_bytes, size_t len, int las
     int rc = bam_ensure(ctx);
     if (rc == PSSGPU_OK) rc = feed_bam_impl(ctx, (const uint8_t *)bgzf_bytes, len, last);
     // like pssgpu_feed: the caller's bytes have been copied when we return, the kernels may still run
-    const cudaError_t e = cudaStreamSynchronize(ctx->copy_stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->copy_stream);
+    for (pssgpu_ctx *h : ctx->bam ? ctx->bam->helpers : std::vector<pssgpu_ctx *>()) {
+        const cudaError_t eh = cudaStreamSynchronize(h->copy_stream);
+        if (e == cudaSuccess) e = eh;
+    }
     if (rc != PSSGPU_OK) return rc;
     if (e != cudaSuccess) return fail(ctx, PSSGPU_ECUDA, "feed_bam: %s", cudaGetErrorString(e));
     return PSSGPU_OK;

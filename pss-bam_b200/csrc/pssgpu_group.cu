@@ -319,6 +319,46 @@ int pssgpu_group_feed(pssgpu_group *g, const char *sam, size_t len, int last)
     return PSSGPU_OK;
 }
 
+// A BAM file over the GPUs of the group.  Its byte stream cannot be dealt like text (records run across BGZF blocks and
+// carry no sync marks), but the inflate -- five sixths of the ingest -- can: batches of BGZF blocks go to the members in
+// turn, every member inflates its batches, and the first member fetches the inflated bytes (peer copy over NVLink) and
+// frames, renders and tallies them in file order (pssgpu_bam.cu bam_submit).  With two GPUs the batches alternate; with
+// more the first GPU does not inflate at all.
+int pssgpu_group_feed_bam(pssgpu_group *g, const void *bgzf_bytes, size_t len, int last)
+{
+    if (!g || (!bgzf_bytes && len)) return PSSGPU_EINVAL;
+    pssgpu_ctx *own = g->ctx[0];
+    std::vector<pssgpu_ctx *> helpers(g->ctx.begin() + 1, g->ctx.end());
+    if (getenv("PSSGPU_GROUP_BAM_ONE_GPU")) helpers.clear();              // measurement switch: decode everything on member 0
+    int rc = bam_set_helpers(own, helpers);
+    if (rc == PSSGPU_OK) rc = pssgpu_feed_bam(own, bgzf_bytes, len, last);
+    if (rc != PSSGPU_OK) return member_fail(g, 0, rc);
+    return PSSGPU_OK;
+}
+
+int pssgpu_group_bam_read_group(pssgpu_group *g, const char *read_group)
+{
+    if (!g) return PSSGPU_EINVAL;
+    const int rc = pssgpu_bam_read_group(g->ctx[0], read_group);
+    return rc == PSSGPU_OK ? rc : member_fail(g, 0, rc);
+}
+
+// out: what pssgpu_bam_info reports for the member that frames the stream; batches_per_member (may be NULL, one entry
+// per member): who inflated how many batches
+int pssgpu_group_bam_info(pssgpu_group *g, pssgpu_bam_stats *out, uint64_t *batches_per_member)
+{
+    if (!g || !out) return PSSGPU_EINVAL;
+    const int rc = pssgpu_bam_info(g->ctx[0], out);
+    if (rc != PSSGPU_OK) return member_fail(g, 0, rc);
+    if (batches_per_member) {
+        uint64_t own = 0;
+        std::vector<uint64_t> per;
+        bam_dealing(g->ctx[0], &own, &per);
+        for (size_t i = 0; i < g->ctx.size(); i++) batches_per_member[i] = i == 0 ? own : (i - 1 < per.size() ? per[i - 1] : 0);
+    }
+    return PSSGPU_OK;
+}
+
 int pssgpu_group_pss_finish(pssgpu_group *g, uint64_t *fwd, uint64_t *rev)
 {
     if (!g || !fwd || !rev) return PSSGPU_EINVAL;

@@ -110,6 +110,8 @@ int launch_tally_mode(pssgpu_ctx *ctx, const uint8_t *d_sam, size_t len, uint64_
 // pssgpu_bam.cu
 void bam_reset(pssgpu_ctx *ctx);          // a new tally begins: forget the stream position
 void bam_destroy(pssgpu_ctx *ctx);
+int  bam_set_helpers(pssgpu_ctx *ctx, const std::vector<pssgpu_ctx *> &helpers);      // pssgpu_group_feed_bam
+void bam_dealing(pssgpu_ctx *ctx, uint64_t *own, std::vector<uint64_t> *per_helper);
 int  bam_check(pssgpu_ctx *ctx, bool finishing);   // after a stream sync: PSSGPU_OK or the ingest error the device flagged
                                                    // (finishing: an unfinished block / record left over is an error too)
 

@@ -10,6 +10,9 @@
 #include <unistd.h>
 
 #define PSS_PIPE_CHUNK (32u << 20)
+/* A BAM file is read in pieces of the device batch size: a feed call forms its batches from its own bytes, and a batch
+ * must hold several thousand BGZF blocks to fill the inflate kernel (one warp per block, 4 440 warps). */
+#define PSS_BAM_CHUNK (256u << 20)
 
 void pss_die(pssgpu_ctx *ctx, const char *what)
 {
@@ -193,7 +196,7 @@ FILE *pss_bam_to_sam(const char *bam_fn, const char *read_group)
 typedef struct pump {
     FILE           *in;
     char           *buf[2];
-    size_t          got[2];
+    size_t          got[2], chunk;
     int             full[2], eof;
     pthread_mutex_t mu;
     pthread_cond_t  cv;
@@ -207,7 +210,7 @@ static void *pump_reader(void *arg)
         pthread_mutex_lock(&p->mu);
         while (p->full[k]) pthread_cond_wait(&p->cv, &p->mu);
         pthread_mutex_unlock(&p->mu);
-        const size_t got = fread(p->buf[k], 1, PSS_PIPE_CHUNK, p->in);
+        const size_t got = fread(p->buf[k], 1, p->chunk, p->in);
         pthread_mutex_lock(&p->mu);
         p->got[k] = got;
         p->full[k] = 1;
@@ -219,9 +222,9 @@ static void *pump_reader(void *arg)
     }
 }
 
-static int pump_run(pssgpu_ctx *ctx, FILE *in, int as_bam);
+static int pump_run(pssgpu_ctx *ctx, pssgpu_group *g, FILE *in, int as_bam);
 
-int pss_stream_sam(pssgpu_ctx *ctx, FILE *sam) { return pump_run(ctx, sam, 0); }
+int pss_stream_sam(pssgpu_ctx *ctx, FILE *sam) { return pump_run(ctx, NULL, sam, 0); }
 
 int pss_is_bgzf(const char *fn)
 {
@@ -242,27 +245,41 @@ int pss_stream_input(pssgpu_ctx *ctx, const char *bam_fn, const char *read_group
         FILE *f = fopen(bam_fn, "rb");
         if (!f) { fprintf(stderr, "Error: Unable to open %s.\n", bam_fn); exit(1); }
         rc = pssgpu_bam_read_group(ctx, read_group);
-        if (rc == PSSGPU_OK) rc = pump_run(ctx, f, 1);
+        if (rc == PSSGPU_OK) rc = pump_run(ctx, NULL, f, 1);
         fclose(f);
         return rc;
     }
     {
         FILE *sam = pss_bam_to_sam(bam_fn, read_group);
-        rc = pump_run(ctx, sam, 0);
+        rc = pump_run(ctx, NULL, sam, 0);
         pclose(sam);
         return rc;
     }
 }
 
-static int pump_run(pssgpu_ctx *ctx, FILE *sam, int as_bam)
+/* g != NULL: a BAM file over the GPUs of a group (pssgpu_group_feed_bam); else the one context */
+static int pump_feed(pssgpu_ctx *ctx, pssgpu_group *g, const char *buf, size_t n, int as_bam, int last)
+{
+    if (g) return pssgpu_group_feed_bam(g, buf, n, last);
+    return as_bam ? pssgpu_feed_bam(ctx, buf, n, last) : pssgpu_feed(ctx, buf, n, last);
+}
+
+static int pump_run(pssgpu_ctx *ctx, pssgpu_group *g, FILE *sam, int as_bam)
 {
     pump      p;
     pthread_t th;
     int       rc = PSSGPU_OK, k = 0;
     memset(&p, 0, sizeof p);
     p.in = sam;
-    p.buf[0] = (char *)pssgpu_host_alloc(PSS_PIPE_CHUNK);
-    p.buf[1] = (char *)pssgpu_host_alloc(PSS_PIPE_CHUNK);
+    p.chunk = PSS_PIPE_CHUNK;
+    if (as_bam) {                                                           /* no larger than the file */
+        struct stat sb;
+        p.chunk = PSS_BAM_CHUNK;
+        if (fstat(fileno(sam), &sb) == 0 && S_ISREG(sb.st_mode) && (size_t)sb.st_size + 1 < p.chunk)
+            p.chunk = (size_t)sb.st_size + 1 > (1u << 20) ? (size_t)sb.st_size + 1 : (1u << 20);
+    }
+    p.buf[0] = (char *)pssgpu_host_alloc(p.chunk);
+    p.buf[1] = (char *)pssgpu_host_alloc(p.chunk);
     if (!p.buf[0] || !p.buf[1]) { pssgpu_host_free(p.buf[0]); pssgpu_host_free(p.buf[1]); return PSSGPU_ENOMEM; }
     pthread_mutex_init(&p.mu, NULL);
     pthread_cond_init(&p.cv, NULL);
@@ -277,7 +294,7 @@ static int pump_run(pssgpu_ctx *ctx, FILE *sam, int as_bam)
         pthread_mutex_unlock(&p.mu);
         if (got == 0) break;
         if (rc == PSSGPU_OK)                                               /* after an error the pipe is still drained */
-            rc = as_bam ? pssgpu_feed_bam(ctx, p.buf[k], got, 0) : pssgpu_feed(ctx, p.buf[k], got, 0);
+            rc = pump_feed(ctx, g, p.buf[k], got, as_bam, 0);
         pthread_mutex_lock(&p.mu);
         p.full[k] = 0;
         pthread_cond_broadcast(&p.cv);
@@ -286,8 +303,8 @@ static int pump_run(pssgpu_ctx *ctx, FILE *sam, int as_bam)
     }
     pthread_join(th, NULL);
     if (rc == PSSGPU_OK)                                                  /* a last line without '\n' / the end of the BAM */
-        rc = as_bam ? pssgpu_feed_bam(ctx, p.buf[0], 0, 1) : pssgpu_feed(ctx, p.buf[0], 0, 1);
-    if (rc == PSSGPU_OK) rc = pssgpu_sync(ctx);
+        rc = pump_feed(ctx, g, p.buf[0], 0, as_bam, 1);
+    if (rc == PSSGPU_OK) rc = g ? pssgpu_group_sync(g) : pssgpu_sync(ctx);
     pthread_mutex_destroy(&p.mu);
     pthread_cond_destroy(&p.cv);
     pssgpu_host_free(p.buf[0]);
@@ -363,10 +380,15 @@ int pss_stream_input_group(pssgpu_group *g, const char *bam_fn, const char *read
     int rc;
     if (n == 1) return pss_stream_input(pssgpu_group_ctx(g, 0), bam_fn, read_group);
     if (pss_is_bgzf(bam_fn) && !getenv("PSSGPU_USE_SAMTOOLS")) {
-        /* BAM records run across BGZF blocks and carry no sync marks: the byte stream of one file cannot be dealt to
-         * several GPUs without decoding it.  It is decoded -- and tallied -- on the first member; the others add zeros. */
-        fprintf(stderr, "Note: a BAM file is decoded on one GPU (device member 0 of %d).\n", n);
-        return pss_stream_input(pssgpu_group_ctx(g, 0), bam_fn, read_group);
+        /* BAM records run across BGZF blocks and carry no sync marks: the byte stream of one file cannot be dealt like
+         * text.  The inflate can: batches of BGZF blocks go to the members in turn, the first member fetches the inflated
+         * bytes and frames, renders and tallies them (pssgpu_group_feed_bam); the others add zeros to the tables. */
+        FILE *f = fopen(bam_fn, "rb");
+        if (!f) { fprintf(stderr, "Error: Unable to open %s.\n", bam_fn); exit(1); }
+        rc = pssgpu_group_bam_read_group(g, read_group);
+        if (rc == PSSGPU_OK) rc = pump_run(pssgpu_group_ctx(g, 0), g, f, 1);
+        fclose(f);
+        return rc;
     }
     {
         FILE *sam = pss_bam_to_sam(bam_fn, read_group);

@@ -42,6 +42,7 @@ def _group_case(devices, env_extra):
         g = Synth.genome(93, [900_000, 400_000, 77_777], n_frac=0.01, lower_frac=0.03)
         ora = Oracle(fasta=g.fasta_bytes())
         sam = Synth.sam(reads_cfg_config2(seed=94), g, 0, 120_000)
+        os.environ["PSSGPU_BAM_BATCH_MB"] = "1"               # read when a context first ingests BAM
         grp = pkg.Group(devices)
         assert grp.size == len(devices)
         grp.upload_genome(ora.contigs())
@@ -60,11 +61,45 @@ def _group_case(devices, env_extra):
         assert grp.stats() == fst and np.array_equal(gfp, fp) and np.array_equal(gtp, tp)
         for k in (4, 8, 12):                                  # genome-sharded spectrum + sum of the 4^k counters
             assert np.array_equal(grp.kmer_spectrum(k), ora.kmer_spectrum(k)), k
+        # a BAM FILE over the group (pssgpu_group_feed_bam): batches of BGZF blocks are inflated by the members in turn,
+        # member 0 fetches, frames, renders and tallies; 1 MiB batches so that this small file makes a dozen of them
+        bam = Synth.bam(sam, list(zip(g.names, g.lens)) + [("chrUn_synthetic_decoy", 1000)], level=6, qual_mode=1)
+        for chunk in (None, 700_001):
+            grp.pss_begin(pkg.PssOptions())
+            if chunk is None:
+                grp.feed_bam(bam, last=True)
+            else:
+                for off in range(0, len(bam), chunk):
+                    grp.feed_bam(bam[off:off + chunk])
+                grp.feed_bam(b"", last=True)
+            gf, gr = grp.pss_finish()
+            assert grp.stats() == st and np.array_equal(gf, f) and np.array_equal(gr, r)
+            info = grp.bam_info()
+            per = info["batches_per_member"]
+            assert info["records"] == 120_000 and sum(per) == info["batches"] - 1 and info["batches"] > 6, info
+            assert all(x > 0 for x in per[1:]) and (per[0] > 0) == (len(devices) == 2), info
+        grp.bam_read_group("no_such_group")
+        grp.pss_begin(pkg.PssOptions())
+        grp.feed_bam(bam, last=True)
+        gf, gr = grp.pss_finish()
+        assert gf.sum() == 0 and grp.bam_info()["dropped_by_read_group"] == 120_000
+        grp.bam_read_group(None)
+        bad = bytearray(bam)                                  # a damaged block inflated on another GPU is reported here
+        bad[len(bam) // 2] ^= 0x10
+        grp.pss_begin(pkg.PssOptions())
+        with pytest.raises(pkg.PssGpuError):
+            grp.feed_bam(bytes(bad), last=True)
+            grp.pss_finish()
+        grp.pss_begin(pkg.PssOptions())
+        grp.feed_bam(bam, last=True)
+        gf, gr = grp.pss_finish()
+        assert grp.stats() == st and np.array_equal(gf, f)
         backend = grp.reduce_backend
         grp.close()
     finally:
         for k in env_extra:
             os.environ.pop(k, None)
+        os.environ.pop("PSSGPU_BAM_BATCH_MB", None)
     # the host programs with $PSSGPU_DEVICES: byte-identical golden outputs
     gold = os.path.join(ROOT, "tests", "golden", "v1")
     man = json.load(open(os.path.join(gold, "manifest.json")))
@@ -92,6 +127,23 @@ def _group_case(devices, env_extra):
     for case in man["gkc"]:
         rr = subprocess.run([os.path.join(bindir, "genome-kmer-count"), "-f", "genome.fa", "-k", str(case["k"])], cwd=d, env=e, capture_output=True)
         assert rr.returncode == 0 and rr.stdout == rd(case["out"]), rr.stderr[-2000:]
+    # the host program reading a BAM FILE with the group (its bytes go to the GPUs) against the samtools-shim text path
+    # on one GPU: same file name in two directories, so that the outputs must be byte-identical
+    d1, d2 = tmpdir(), tmpdir()
+    for dd in (d1, d2):
+        with open(os.path.join(dd, "genome.fa"), "wb") as fo:
+            fo.write(g.fasta_bytes())
+    with open(os.path.join(d1, "reads.bam"), "wb") as fo:
+        fo.write(sam)                                         # (the shim `cat`s it)
+    with open(os.path.join(d2, "reads.bam"), "wb") as fo:
+        fo.write(bam)
+    e1 = dict(e, PSSGPU_DEVICES=str(devices[0]))
+    e2 = dict(e, PSSGPU_BAM_BATCH_MB="1")
+    for dd, ee in ((d1, e1), (d2, e2)):
+        rr = subprocess.run([os.path.join(bindir, "pss-bam"), "-F", "genome.fa", "-B", "reads.bam", "-o", "out"], cwd=dd, env=ee, capture_output=True)
+        assert rr.returncode == 0, rr.stderr[-2000:]
+    for name in ("out.pss.counts.txt", "out.pss.rates.txt"):
+        assert open(os.path.join(d1, name), "rb").read() == open(os.path.join(d2, name), "rb").read(), name
     return backend
 
 
