@@ -285,11 +285,11 @@ int pssgpu_group_sync(pssgpu_group *g);
 /* A BAM FILE over the GPUs of a group (pssgpu_feed_bam's contract: the file's
  * bytes in any chunking, `last` marks the end).  Records run across BGZF blocks,
  * so the stream cannot be dealt like text; the inflate -- five sixths of the
- * ingest -- can: batches of BGZF blocks go to the members in turn, each inflates
- * its batches, member 0 fetches the inflated bytes with a peer copy and frames,
- * renders and tallies them in file order (the other members' tables stay zero;
- * the sums are the same).  Two GPUs alternate; with more, member 0 does not
- * inflate.  Replaces the same samtools child (pss-bam.c:148-162, fragkon.c:84-93).
+ * ingest -- can: batches of BGZF blocks go to the GPU with the fewest in flight,
+ * each inflates its batches, member 0 fetches the inflated bytes with a peer
+ * copy and frames, renders and tallies them in file order (the other members'
+ * tables stay zero; the sums are the same).  Replaces the same samtools child
+ * (pss-bam.c:148-162, fragkon.c:84-93).
  * batches_per_member: may be NULL; one entry per member otherwise. */
 int pssgpu_group_feed_bam(pssgpu_group *g, const void *bgzf_bytes, size_t len, int last);
 int pssgpu_group_bam_read_group(pssgpu_group *g, const char *read_group);

@@ -20,6 +20,7 @@
 #include "pssgpu_internal.h"
 
 #include <algorithm>
+#include <array>
 #include <cstdlib>
 #include <cstring>
 
@@ -90,6 +91,8 @@ struct BamIngest {
     std::vector<pssgpu_ctx *> helpers;
     std::vector<cudaEvent_t>  ev_fetched;        // per helper: its inflated batch has been copied over (its buffer is free)
     std::vector<uint64_t>     helper_batches;
+    std::vector<std::array<bool, 2>> helper_busy;  // per helper and staging buffer: a batch dealt there has not been inflated yet
+    size_t        deal_start = 0;
     cudaEvent_t   desc_reader[2] = { nullptr, nullptr };   // a helper's copy that also reads h_desc[i] (its ev_copied)
     unsigned int *d_remote_err = nullptr;        // error / error_arg of the helper whose batch was fetched last
     uint64_t      dealt = 0, own_batches = 0;
@@ -454,11 +457,14 @@ void bam_reset(pssgpu_ctx *ctx)
 {
     BamIngest *B = ctx->bam;
     if (!B) return;
+    Bind bind(ctx);
     B->carry.clear();
     B->finished = false;
     B->batches = 0;
     B->dealt = B->own_batches = 0;
+    B->deal_start = 0;
     for (uint64_t &h : B->helper_batches) h = 0;
+    for (auto &b : B->helper_busy) b = { false, false };
     if (B->d_state) {
         BamState z;
         memset(&z, 0, sizeof z);
@@ -466,6 +472,7 @@ void bam_reset(pssgpu_ctx *ctx)
         cudaMemcpyAsync(B->d_state, &z, sizeof z, cudaMemcpyHostToDevice, ctx->stream);
         cudaStreamSynchronize(ctx->stream);
     }
+    for (pssgpu_ctx *h : B->helpers) bam_reset(h);       // their error flags (a helper need not be a member that *_begin reaches)
 }
 
 void bam_destroy(pssgpu_ctx *ctx)
@@ -639,12 +646,26 @@ int bam_submit(pssgpu_ctx *ctx, const uint8_t *pfx, size_t pfx_len, const uint8_
     BamState    *S = B->d_state;
     int          hi = -1;                                  // helper that inflates this batch
     if (n_blocks && may_deal && !B->helpers.empty()) {
-        // two GPUs: the batches alternate; more: the first GPU only frames, renders and tallies (a quarter of the work of
-        // a batch, plus fetching it), the others inflate in turn
-        const uint64_t k = B->dealt++;
-        const size_t   nh = B->helpers.size();
-        if (nh == 1) hi = (k & 1) ? 0 : -1;
-        else hi = (int)(k % nh);
+        // the helper with the fewest batches in flight (staged or inflating: at most two, its staging is double buffered);
+        // ties go to the first in the list from a rotating start -- the caller lists the other GPUs before the second
+        // context on this one, whose inflates share the SMs with the framing / rendering / tallying of every batch
+        const size_t nh = B->helpers.size();
+        int          best = 3;
+        for (size_t k = 0; k < nh; k++) {
+            const size_t h = (B->deal_start + k) % nh;
+            pssgpu_ctx  *W = B->helpers[h];
+            int          fl = 0;
+            for (int b = 0; b < 2; b++) {
+                if (B->helper_busy[h][b] && cudaEventQuery(W->ev_tallied[b]) == cudaSuccess) B->helper_busy[h][b] = false;
+                fl += B->helper_busy[h][b] ? 1 : 0;
+            }
+            cudaGetLastError();                            // (cudaErrorNotReady is an answer, not an error)
+            const int cost = 2 * fl + (W->device == ctx->device ? 1 : 0);
+            if (cost < best) { best = cost; hi = (int)h; }
+        }
+        if (hi < 0) hi = (int)(B->deal_start % nh);
+        B->deal_start = ((size_t)hi + 1) % nh;
+        B->dealt++;
     }
     B->desc_reader[cur] = nullptr;
     if (hi < 0) {
@@ -675,6 +696,7 @@ int bam_submit(pssgpu_ctx *ctx, const uint8_t *pfx, size_t pfx_len, const uint8_
             if (rc != PSSGPU_OK) return fail(ctx, rc, "feed_bam: inflate on GPU %d: %s", W->device, pssgpu_last_error(W));
         }
         B->desc_reader[cur] = W->ev_copied[wc];
+        B->helper_busy[hi][wc] = true;
         B->helper_batches[hi]++;
         // this GPU: the descriptors, then -- once the helper is done -- the inflated bytes and its error flag over NVLink
         CU(cudaMemcpyAsync(B->d_desc[cur], B->h_desc[cur], n_blocks * sizeof(BamDesc), cudaMemcpyHostToDevice, ctx->copy_stream));
@@ -832,6 +854,8 @@ int bam_set_helpers(pssgpu_ctx *ctx, const std::vector<pssgpu_ctx *> &helpers)
     B->ev_fetched.assign(helpers.size(), nullptr);
     for (cudaEvent_t &e : B->ev_fetched) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     B->helper_batches.assign(helpers.size(), 0);
+    B->helper_busy.assign(helpers.size(), std::array<bool, 2>{ false, false });
+    B->deal_start = 0;
     B->helpers = helpers;
     return PSSGPU_OK;
 }

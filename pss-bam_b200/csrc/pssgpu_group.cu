@@ -66,6 +66,7 @@ struct pssgpu_group {
     bool        use_nccl = false;
     std::string err;
     size_t      next = 0;                           // round-robin cursor of pssgpu_group_feed
+    pssgpu_ctx *bam_self = nullptr;                 // pssgpu_group_feed_bam: a second context on the first GPU that only inflates
     double      last_reduce_ms = 0.0;
 };
 
@@ -245,6 +246,10 @@ int pssgpu_group_init(const int *devices, int n, pssgpu_group **out)
 void pssgpu_group_destroy(pssgpu_group *g)
 {
     if (!g) return;
+    if (g->bam_self) {
+        for (pssgpu_ctx *c : g->ctx) { Bind bind(c); cudaStreamSynchronize(c->stream); }      // (they may wait on its events)
+        pssgpu_destroy(g->bam_self);
+    }
     for (size_t i = 0; i < g->ctx.size(); i++) {
         { Bind bind(g->ctx[i]); cudaStreamSynchronize(g->ctx[i]->stream); cudaFree(g->d_red[i]); }
         if (g->use_nccl && g->comm[i]) g->nccl.CommDestroy(g->comm[i]);
@@ -320,16 +325,24 @@ int pssgpu_group_feed(pssgpu_group *g, const char *sam, size_t len, int last)
 }
 
 // A BAM file over the GPUs of the group.  Its byte stream cannot be dealt like text (records run across BGZF blocks and
-// carry no sync marks), but the inflate -- five sixths of the ingest -- can: batches of BGZF blocks go to the members in
-// turn, every member inflates its batches, and the first member fetches the inflated bytes (peer copy over NVLink) and
-// frames, renders and tallies them in file order (pssgpu_bam.cu bam_submit).  With two GPUs the batches alternate; with
-// more the first GPU does not inflate at all.
+// carry no sync marks), but the inflate -- five sixths of the ingest -- can: batches of BGZF blocks go to whichever
+// GPU has the fewest in flight, every GPU inflates its batches, and the first member fetches the inflated bytes (peer
+// copy over NVLink) and frames, renders and tallies them in file order (pssgpu_bam.cu bam_submit).  The first GPU
+// inflates too -- through a second context of its own, so that its inflates queue beside, not between, the in-order
+// framing of the batches the others deliver; having that work as well, it ends up with fewer batches than they.
 int pssgpu_group_feed_bam(pssgpu_group *g, const void *bgzf_bytes, size_t len, int last)
 {
     if (!g || (!bgzf_bytes && len)) return PSSGPU_EINVAL;
     pssgpu_ctx *own = g->ctx[0];
-    std::vector<pssgpu_ctx *> helpers(g->ctx.begin() + 1, g->ctx.end());
-    if (getenv("PSSGPU_GROUP_BAM_ONE_GPU")) helpers.clear();              // measurement switch: decode everything on member 0
+    std::vector<pssgpu_ctx *> helpers;
+    if (g->ctx.size() > 1 && !getenv("PSSGPU_GROUP_BAM_ONE_GPU")) {       // (measurement switch: decode everything on member 0)
+        if (!g->bam_self && pssgpu_init(g->dev[0], &g->bam_self) != PSSGPU_OK) {
+            g->bam_self = nullptr;
+            return gfail(g, PSSGPU_ECUDA, "group_feed_bam: second context on GPU %d: %s", g->dev[0], pssgpu_last_error(nullptr));
+        }
+        helpers.assign(g->ctx.begin() + 1, g->ctx.end());
+        helpers.push_back(g->bam_self);
+    }
     int rc = bam_set_helpers(own, helpers);
     if (rc == PSSGPU_OK) rc = pssgpu_feed_bam(own, bgzf_bytes, len, last);
     if (rc != PSSGPU_OK) return member_fail(g, 0, rc);
@@ -354,7 +367,9 @@ int pssgpu_group_bam_info(pssgpu_group *g, pssgpu_bam_stats *out, uint64_t *batc
         uint64_t own = 0;
         std::vector<uint64_t> per;
         bam_dealing(g->ctx[0], &own, &per);
-        for (size_t i = 0; i < g->ctx.size(); i++) batches_per_member[i] = i == 0 ? own : (i - 1 < per.size() ? per[i - 1] : 0);
+        // helpers = members 1 .. n-1, then the second context on the first GPU
+        const size_t n = g->ctx.size();
+        for (size_t i = 0; i < n; i++) batches_per_member[i] = i == 0 ? own + (per.size() == n ? per[n - 1] : 0) : (i - 1 < per.size() ? per[i - 1] : 0);
     }
     return PSSGPU_OK;
 }

@@ -77,7 +77,7 @@ def _group_case(devices, env_extra):
             info = grp.bam_info()
             per = info["batches_per_member"]
             assert info["records"] == 120_000 and sum(per) == info["batches"] - 1 and info["batches"] > 6, info
-            assert all(x > 0 for x in per[1:]) and (per[0] > 0) == (len(devices) == 2), info
+            assert per[1] > 0 and max(per) < sum(per), info       # dealt: nobody inflated everything
         grp.bam_read_group("no_such_group")
         grp.pss_begin(pkg.PssOptions())
         grp.feed_bam(bam, last=True)
