@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--genome-mb", type=int, default=200)
     ap.add_argument("--group", type=int, default=0, help="also feed the BAM to a group of this many GPUs (pssgpu_group_feed_bam)")
     ap.add_argument("--chunk-mb", type=int, default=0, help="feed the BAM in pieces of this size (0: one call)")
+    ap.add_argument("--batch-mbs", default="", help="comma list: also time the one-GPU BAM path with these $PSSGPU_BAM_BATCH_MB values")
     a = ap.parse_args()
     Synth.set_threads(os.cpu_count() or 1)
     g = Synth.genome(35, [a.genome_mb * 600_000, a.genome_mb * 400_000], n_frac=0.01, lower_frac=0.03)
@@ -65,6 +66,15 @@ def main():
            "bam": {"s": bam_t, "reads_per_s": a.reads / bam_t, "compressed_gb_per_s": nbam / bam_t / 1e9,
                    "kernel_ms_inflate_render_tally": bam_tm["kernel_ms"], "launches": bam_tm["launches"], "info": info}}
     ctx.close()
+    for mb in [int(x) for x in a.batch_mbs.split(",") if x]:
+        os.environ["PSSGPU_BAM_BATCH_MB"] = str(mb)            # read when a context first ingests BAM
+        ctx = pkg.Context(0)
+        ctx.upload_genome(list(zip(g.names, g.seqs)))
+        t, tm, f2, r2 = run(lambda: ctx.feed_bam_ptr(hbam.data_ptr(), nbam, last=True))
+        out.setdefault("batch_mb", {})[str(mb)] = {"s": t, "reads_per_s": a.reads / t, "kernel_ms": tm["kernel_ms"], "batches": ctx.bam_info()["batches"],
+                                                   "tables_equal": bool(np.array_equal(sf, f2) and np.array_equal(sr, r2))}
+        ctx.close()
+        del os.environ["PSSGPU_BAM_BATCH_MB"]
     if a.group > 1:
         grp = pkg.Group(list(range(a.group)))
         grp.upload_genome(list(zip(g.names, g.seqs)))
