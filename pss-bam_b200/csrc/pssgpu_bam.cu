@@ -37,6 +37,7 @@ constexpr uint32_t kBamMaxBlocks = 32768;
 constexpr uint32_t kBamLocCap    = 2048;          // record starts per block: 65536 / 38 bytes < 1725, + the carried one
 constexpr uint32_t kBamMaxRefs   = 1u << 21;
 constexpr uint32_t kBamNone      = 0xffffffffu;
+constexpr int      kBamSlots     = 8;             // batches the host may be ahead of the framing GPU when several GPUs inflate
 #ifndef PSS_INF_WARPS
 #define PSS_INF_WARPS 10
 #endif
@@ -76,9 +77,13 @@ struct BamIngest {
     uint8_t  *d_comp[2] = { nullptr, nullptr };                  // compressed staging, double buffered
     uint32_t *d_loc = nullptr;        // kBamMaxBlocks x kBamLocCap record starts (offsets in ubuf)
     uint32_t *d_s = nullptr, *d_e = nullptr, *d_n = nullptr;     // per block: guessed start, chain exit, records
-    BamDesc  *d_desc[2] = { nullptr, nullptr };
-    BamDesc  *h_desc[2] = { nullptr, nullptr };                  // pinned
-    uint8_t  *h_pfx[2] = { nullptr, nullptr };                   // pinned: a BGZF block that arrived in two feed calls
+    // descriptor slots: two when this context inflates its own batches (slot = the staging buffer, ctx->cur), a ring of
+    // kBamSlots when helpers inflate for it -- the host must be able to deal as many batches ahead as the helpers can hold
+    BamDesc  *d_desc[kBamSlots] = {};
+    BamDesc  *h_desc[kBamSlots] = {};                            // pinned
+    uint8_t  *h_pfx[kBamSlots] = {};                             // pinned: a BGZF block that arrived in two feed calls
+    cudaEvent_t ev_ring_copied[kBamSlots] = {}, ev_ring_done[kBamSlots] = {};    // ring mode: descriptors copied / batch processed
+    int       ring_slot = 0;
     uint8_t  *d_hdr = nullptr;        // copy of the BAM header (reference names)
     uint32_t *d_ref_off = nullptr, *d_ref_len = nullptr;
     char     *d_rg = nullptr;
@@ -93,7 +98,7 @@ struct BamIngest {
     std::vector<uint64_t>     helper_batches;
     std::vector<std::array<bool, 2>> helper_busy;  // per helper and staging buffer: a batch dealt there has not been inflated yet
     size_t        deal_start = 0;
-    cudaEvent_t   desc_reader[2] = { nullptr, nullptr };   // a helper's copy that also reads h_desc[i] (its ev_copied)
+    cudaEvent_t   desc_reader[kBamSlots] = {};             // a helper's copy that also reads h_desc[i] (its ev_copied)
     unsigned int *d_remote_err = nullptr;        // error / error_arg of the helper whose batch was fetched last
     uint64_t      dealt = 0, own_batches = 0;
 };
@@ -463,6 +468,7 @@ void bam_reset(pssgpu_ctx *ctx)
     B->batches = 0;
     B->dealt = B->own_batches = 0;
     B->deal_start = 0;
+    B->ring_slot = 0;
     for (uint64_t &h : B->helper_batches) h = 0;
     for (auto &b : B->helper_busy) b = { false, false };
     if (B->d_state) {
@@ -481,7 +487,13 @@ void bam_destroy(pssgpu_ctx *ctx)
     if (!B) return;
     cudaFree(B->d_state); cudaFree(B->d_ubuf); cudaFree(B->d_text); cudaFree(B->d_loc); cudaFree(B->d_comp[0]); cudaFree(B->d_comp[1]);
     cudaFree(B->d_s); cudaFree(B->d_e); cudaFree(B->d_n);
-    for (int i = 0; i < 2; i++) { cudaFree(B->d_desc[i]); if (B->h_desc[i]) cudaFreeHost(B->h_desc[i]); if (B->h_pfx[i]) cudaFreeHost(B->h_pfx[i]); }
+    for (int i = 0; i < kBamSlots; i++) {
+        cudaFree(B->d_desc[i]);
+        if (B->h_desc[i]) cudaFreeHost(B->h_desc[i]);
+        if (B->h_pfx[i]) cudaFreeHost(B->h_pfx[i]);
+        if (B->ev_ring_copied[i]) cudaEventDestroy(B->ev_ring_copied[i]);
+        if (B->ev_ring_done[i]) cudaEventDestroy(B->ev_ring_done[i]);
+    }
     cudaFree(B->d_hdr); cudaFree(B->d_ref_off); cudaFree(B->d_ref_len); cudaFree(B->d_rg); cudaFree(B->d_crc_tab); cudaFree(B->d_remote_err);
     for (cudaEvent_t e : B->ev_fetched) cudaEventDestroy(e);
     delete B;
@@ -532,10 +544,12 @@ int bam_ensure(pssgpu_ctx *ctx, bool inflate_only = false)
         B->text_cap = 3 * B->batch_u + (64ull << 20);          // lines are ~1.3 x the record bytes; beyond the cap: error, never silence
         CU(cudaMalloc(&B->d_ubuf, kBamCarryCap + B->batch_u + (1u << 20)));
         for (int i = 0; i < 2; i++) CU(cudaMalloc(&B->d_comp[i], B->batch_comp + (128u << 10)));
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < kBamSlots; i++) {
             CU(cudaMalloc(&B->d_desc[i], kBamMaxBlocks * sizeof(BamDesc)));
             CU(cudaMallocHost(&B->h_desc[i], kBamMaxBlocks * sizeof(BamDesc)));
             CU(cudaMallocHost(&B->h_pfx[i], 65536 + 64));
+            CU(cudaEventCreateWithFlags(&B->ev_ring_copied[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&B->ev_ring_done[i], cudaEventDisableTiming));
         }
         if (const char *e = getenv("PSSGPU_BAM_CRC")) B->check_crc = atoi(e) != 0;
         if (B->check_crc) {
@@ -605,6 +619,15 @@ int bgzf_frame(const uint8_t *p, size_t n, uint32_t *total, uint32_t *pay_off, u
     return 1;
 }
 
+// the descriptor slot of the next batch and the events that guard it (see BamIngest)
+struct BamSlot { int i; cudaEvent_t copied, done; };
+BamSlot bam_slot(pssgpu_ctx *ctx)
+{
+    BamIngest *B = ctx->bam;
+    if (B->helpers.empty()) return BamSlot{ ctx->cur, ctx->ev_copied[ctx->cur], ctx->ev_tallied[ctx->cur] };
+    return BamSlot{ B->ring_slot, B->ev_ring_copied[B->ring_slot], B->ev_ring_done[B->ring_slot] };
+}
+
 // compressed bytes + block descriptors -> W's staging buffers, inflate on W's stream into W's inflated buffer; `desc` is
 // pinned host memory.  W may be the context that frames the batch or a helper on another GPU.
 int bam_stage_and_inflate(pssgpu_ctx *W, const uint8_t *pfx, size_t pfx_len, const uint8_t *src, size_t comp_len, const BamDesc *desc,
@@ -641,7 +664,9 @@ int bam_submit(pssgpu_ctx *ctx, const uint8_t *pfx, size_t pfx_len, const uint8_
                int is_last, bool may_deal = false)
 {
     BamIngest *B = ctx->bam;
-    const int  cur = ctx->cur;
+    const bool    ring = !B->helpers.empty();
+    const BamSlot slot = bam_slot(ctx);
+    const int     cur = slot.i;
     cudaStream_t st = ctx->stream;
     BamState    *S = B->d_state;
     int          hi = -1;                                  // helper that inflates this batch
@@ -674,8 +699,8 @@ int bam_submit(pssgpu_ctx *ctx, const uint8_t *pfx, size_t pfx_len, const uint8_
             if (rc != PSSGPU_OK) return rc;
             B->own_batches++;
         } else {
-            CU(cudaEventRecord(ctx->ev_copied[cur], ctx->copy_stream));
-            CU(cudaStreamWaitEvent(st, ctx->ev_copied[cur], 0));
+            CU(cudaEventRecord(slot.copied, ctx->copy_stream));
+            CU(cudaStreamWaitEvent(st, slot.copied, 0));
         }
     } else {
         pssgpu_ctx *W = B->helpers[hi];
@@ -700,8 +725,8 @@ int bam_submit(pssgpu_ctx *ctx, const uint8_t *pfx, size_t pfx_len, const uint8_
         B->helper_batches[hi]++;
         // this GPU: the descriptors, then -- once the helper is done -- the inflated bytes and its error flag over NVLink
         CU(cudaMemcpyAsync(B->d_desc[cur], B->h_desc[cur], n_blocks * sizeof(BamDesc), cudaMemcpyHostToDevice, ctx->copy_stream));
-        CU(cudaEventRecord(ctx->ev_copied[cur], ctx->copy_stream));
-        CU(cudaStreamWaitEvent(st, ctx->ev_copied[cur], 0));
+        CU(cudaEventRecord(slot.copied, ctx->copy_stream));
+        CU(cudaStreamWaitEvent(st, slot.copied, 0));
         CU(cudaStreamWaitEvent(st, W->ev_tallied[wc], 0));
         CU(cudaMemcpyPeerAsync(B->d_ubuf + kBamCarryCap, ctx->device, Bw->d_ubuf + kBamCarryCap, W->device, total_u, st));
         CU(cudaMemcpyPeerAsync(B->d_remote_err, ctx->device, &Bw->d_state->error, W->device, 2 * sizeof(unsigned int), st));
@@ -729,11 +754,12 @@ int bam_submit(pssgpu_ctx *ctx, const uint8_t *pfx, size_t pfx_len, const uint8_
         int rc = launch_tally_mode(ctx, B->d_text, bound, ctx->fed_bytes, &S->text_len);
         if (rc != PSSGPU_OK) return rc;
     }
-    CU(cudaEventRecord(ctx->ev_tallied[cur], ctx->stream));
-    ctx->cur ^= 1;
-    // the other staging buffer (and its descriptor array) is free once the batch that used it has been inflated; the
-    // simple, sufficient condition: that whole batch is done
-    CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_tallied[ctx->cur], 0));
+    CU(cudaEventRecord(slot.done, ctx->stream));
+    if (ring) B->ring_slot = (cur + 1) % kBamSlots;
+    else ctx->cur ^= 1;
+    // the next staging buffer / descriptor slot is free once the batch that used it has been inflated; the simple,
+    // sufficient condition: that whole batch is done
+    CU(cudaStreamWaitEvent(ctx->copy_stream, bam_slot(ctx).done, 0));
     B->batches++;
     return PSSGPU_OK;
 }
@@ -771,8 +797,9 @@ int feed_bam_impl(pssgpu_ctx *ctx, const uint8_t *data, size_t len, int last)
     }
     // whole blocks in place
     while (off < len || pfx_pending) {
-        const int cur = ctx->cur;
-        CU(cudaEventSynchronize(ctx->ev_copied[cur]));              // h_desc[cur] / h_pfx[cur] are free again
+        const BamSlot slot = bam_slot(ctx);
+        const int     cur = slot.i;
+        CU(cudaEventSynchronize(slot.copied));                      // h_desc[cur] / h_pfx[cur] are free again
         if (B->desc_reader[cur]) CU(cudaEventSynchronize(B->desc_reader[cur]));      // ... also on the GPU that inflated that batch
         BamDesc *desc = B->h_desc[cur];
         const size_t start = off;
