@@ -4,8 +4,9 @@
 // pssgpu_feed_bam takes the bytes of a BAM file as they are on disk.  The host only frames BGZF blocks (an 18-byte
 // header every ~20 KB); everything else runs on the GPU, batch by batch, stream ordered, without a host round trip:
 //
-//   H2D        the compressed blocks of a batch (<= 32 MiB), double buffered on the copy stream
-//   inflate    one warp per BGZF block (pss_inflate.h), persistent warps pulling blocks from a queue
+//   H2D        the compressed blocks of a batch (<= 256 MiB), double buffered on the copy stream
+//   inflate    one warp per BGZF block (pss_inflate.h), persistent warps pulling blocks from a queue; the warp then checks
+//              the block's CRC32 (pss_crc32.h), as htslib does
 //   prepare    (first batch) BAM header: magic, l_text, the reference dictionary -> device table
 //   guess      one warp per block: where does the first record of this block start?  (records ignore block boundaries
 //              and carry no sync marks: 32 lanes test 32 offsets at a time for three plausible records in a row), then
@@ -17,6 +18,10 @@
 //              filter of `samtools view -r`; CTA-level allocation in the text buffer (line order is irrelevant to a tally)
 //   carry      the unfinished tail moves in front of the next batch
 //   tally      the tally kernel of pss_kernels.cuh over the rendered text; its length comes from device memory
+//
+// Several GPUs, one file (pssgpu_group_feed_bam): H2D + inflate of a batch may run on another GPU ("helper": the one with
+// the fewest batches in flight); the inflated bytes then come over NVLink (cudaMemcpyPeerAsync) and everything from
+// `prepare` on runs here, in file order -- the framing state never leaves this GPU.  Streams and events only.
 #include "pssgpu_internal.h"
 
 #include <algorithm>
