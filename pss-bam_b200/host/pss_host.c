@@ -1,6 +1,7 @@
 /* pss_host.c -- see pss_host.h */
 #define _GNU_SOURCE
 #include "pss_host.h"
+#include "pss_io.h"
 
 #include <limits.h>
 #include <pthread.h>
@@ -198,6 +199,8 @@ typedef struct pump {
     char           *buf[2];
     size_t          got[2], chunk;
     int             full[2], eof;
+    int             fd, read_threads;      /* fd >= 0: a regular file, read with read_threads concurrent pread()s */
+    off_t           offset;
     pthread_mutex_t mu;
     pthread_cond_t  cv;
 } pump;
@@ -210,7 +213,13 @@ static void *pump_reader(void *arg)
         pthread_mutex_lock(&p->mu);
         while (p->full[k]) pthread_cond_wait(&p->cv, &p->mu);
         pthread_mutex_unlock(&p->mu);
-        const size_t got = fread(p->buf[k], 1, p->chunk, p->in);
+        size_t got;
+        if (p->fd >= 0) {
+            got = pss_pread_parallel(p->fd, p->buf[k], p->chunk, p->offset, p->read_threads);
+            p->offset += (off_t)got;
+        } else {
+            got = fread(p->buf[k], 1, p->chunk, p->in);
+        }
         pthread_mutex_lock(&p->mu);
         p->got[k] = got;
         p->full[k] = 1;
@@ -272,11 +281,20 @@ static int pump_run(pssgpu_ctx *ctx, pssgpu_group *g, FILE *sam, int as_bam)
     memset(&p, 0, sizeof p);
     p.in = sam;
     p.chunk = PSS_PIPE_CHUNK;
+    p.fd = -1;
     if (as_bam) {                                                           /* no larger than the file */
         struct stat sb;
         p.chunk = PSS_BAM_CHUNK;
-        if (fstat(fileno(sam), &sb) == 0 && S_ISREG(sb.st_mode) && (size_t)sb.st_size + 1 < p.chunk)
-            p.chunk = (size_t)sb.st_size + 1 > (1u << 20) ? (size_t)sb.st_size + 1 : (1u << 20);
+        if (getenv("PSS_BAM_CHUNK_MB") && atoi(getenv("PSS_BAM_CHUNK_MB")) > 0)      /* test switch: many small pieces */
+            p.chunk = (size_t)atoi(getenv("PSS_BAM_CHUNK_MB")) << 20;
+        if (fstat(fileno(sam), &sb) == 0 && S_ISREG(sb.st_mode)) {
+            const char *e = getenv("PSS_READ_THREADS");
+            if ((size_t)sb.st_size + 1 < p.chunk) p.chunk = (size_t)sb.st_size + 1 > (1u << 20) ? (size_t)sb.st_size + 1 : (1u << 20);
+            /* the file itself, by several pread()s at once: one thread copies out of the page cache at a third of
+             * the rate the GPU inflates at */
+            p.read_threads = e ? atoi(e) : 4;
+            if (p.read_threads > 0) { p.fd = fileno(sam); p.offset = ftello(sam); if (p.offset < 0) p.fd = -1; }
+        }
     }
     p.buf[0] = (char *)pssgpu_host_alloc(p.chunk);
     p.buf[1] = (char *)pssgpu_host_alloc(p.chunk);

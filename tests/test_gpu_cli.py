@@ -183,3 +183,30 @@ def test_cli_reads_real_bam_files(env, prog):
             assert r.returncode == 0, r.stderr[-2000:]
             assert not case["sparse"] and r.stdout == _gold(case["out"]), case
     assert done >= 2
+
+
+def test_cli_bam_file_in_pieces_and_by_parallel_reads(env):
+    """The BAM reader of the host programs: 1 MiB pieces (BGZF blocks cut by every piece boundary) read with three
+    concurrent pread()s, and plain fread()s, against the samtools-shim text path on the same alignments."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from pss_testlib import Synth, reads_cfg_config2
+    d, e = env
+    g = Synth.genome(61, [500_000, 250_000], n_frac=0.01, lower_frac=0.03)
+    sam = Synth.sam(reads_cfg_config2(seed=62), g, 0, 60_000)
+    bam = Synth.bam(sam, list(zip(g.names, g.lens)) + [("chrUn_synthetic_decoy", 1000)], level=6, qual_mode=1)
+    assert len(bam) > (3 << 20)
+    outs = []
+    for k, (content, extra) in enumerate(((sam, {}), (bam, {"PSS_BAM_CHUNK_MB": "1", "PSS_READ_THREADS": "3"}),
+                                          (bam, {"PSS_BAM_CHUNK_MB": "1", "PSS_READ_THREADS": "0"}), (bam, {}))):
+        wd = os.path.join(d, f"pieces_{k}")
+        os.makedirs(wd)
+        with open(os.path.join(wd, "genome.fa"), "wb") as f:
+            f.write(g.fasta_bytes())
+        with open(os.path.join(wd, "reads.bam"), "wb") as f:
+            f.write(content)
+        r = subprocess.run([os.path.join(BIN, "pss-bam"), "-F", "genome.fa", "-B", "reads.bam", "-o", "out"], cwd=wd, env=dict(e, **extra),
+                           capture_output=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append((open(os.path.join(wd, "out.pss.counts.txt"), "rb").read(), open(os.path.join(wd, "out.pss.rates.txt"), "rb").read()))
+    assert outs[0][0].count(b"\n") > 30 and all(o == outs[0] for o in outs[1:])

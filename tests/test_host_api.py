@@ -161,3 +161,28 @@ def test_writers_reproduce_reference_files(lib, case):
         assert open("out.pss.rates.txt", "rb").read() == gold_rates
     finally:
         os.chdir(cwd)
+
+
+def test_parallel_pread_reads_what_the_file_holds(tmp_path):
+    """pss_io.c: the BAM file reader of the host programs (several pread()s at once) against plain reads: every
+    thread count, offsets inside and at the end of the file, requests that run past the end."""
+    so = os.path.join(ROOT, "tests", "host_emul", "libpssio.so")
+    subprocess.run(["gcc", "-O2", "-g", "-std=gnu11", "-Wall", "-fPIC", "-shared", "-o", so, os.path.join(HOST, "pss_io.c"), "-lpthread"], check=True)
+    h = C.CDLL(so)
+    h.pss_pread_parallel.restype = C.c_size_t
+    h.pss_pread_parallel.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_int64, C.c_int]
+    rng = np.random.default_rng(5)
+    data = rng.integers(0, 256, size=5 * (1 << 20) + 12345, dtype=np.uint8).tobytes()
+    fn = tmp_path / "blob"
+    fn.write_bytes(data)
+    fd = os.open(fn, os.O_RDONLY)
+    try:
+        buf = (C.c_char * (len(data) + 4096))()
+        for threads in (0, 1, 2, 3, 4, 7, 16, 99):
+            for off, n in ((0, len(data)), (0, len(data) + 4000), (1, 3 << 20), (len(data) - 5, 100), (len(data), 10), (777, 0),
+                           ((1 << 20) - 1, (2 << 20) + 2)):
+                got = h.pss_pread_parallel(fd, buf, n, off, threads)
+                assert got == max(0, min(n, len(data) - off)), (threads, off, n, got)
+                assert buf.raw[:got] == data[off:off + got], (threads, off, n)
+    finally:
+        os.close(fd)
